@@ -1,0 +1,139 @@
+"""ORACLE (test infrastructure only): XC energy densities in plain torch fp64, potentials by
+autograd -- the reference's own default route (dqc/xc/base_xc.py:39-125, exercised against libxc
+in dqc/test/test_xc.py:327-388).  The arithmetic the reference gets from libxc 6 (pylibxc2, absent
+here) is restated from the published functional forms:
+  lda_x       Slater exchange                      -- pinned by dqc/test/test_xc.py:390-391,416-417
+  lda_c_pw    Perdew-Wang 92 (original parameters) -- pinned (rtol 1e-5) by test_xc.py:393-414
+  gga_x_pbe   PBE exchange                         -- pinned (rtol 1e-5) by test_xc.py:419-425
+  gga_c_pbe   PBE correlation on PW92-modified     -- PARITY UNPINNED in-tree (libxc formula restated)
+Conventions follow dqc/xc/libxc.py:124-242 and libxc_wrapper.py:380-413: the energy returned is
+per unit VOLUME (zk * rho); the potential bundle is value = de/drho, grad = 2 (de/dsigma) grad rho
+(unpolarised) -- which is exactly d e / d(grad rho), what autograd gives.
+All formulas are written spin-resolved; the unpolarised case calls them with rho/2, grad/2.
+"""
+import math
+import torch
+
+PI = math.pi
+_PW = {  # a, alpha1, beta1..beta4 for (eps0, eps1, -alpha_c); fz20
+    "pw": dict(a=(0.031091, 0.015545, 0.016887), fz20=1.709921),
+    "pw_mod": dict(a=(0.0310907, 0.01554535, 0.0168869), fz20=1.709920934161365617563962776245),
+}
+_PW_ALPHA1 = (0.21370, 0.20548, 0.11125)
+_PW_BETA = ((7.5957, 3.5876, 1.6382, 0.49294), (14.1189, 6.1977, 3.3662, 0.62517),
+            (10.357, 3.6231, 0.88026, 0.49671))
+PBE_KAPPA = 0.8040
+PBE_BETA = 0.06672455060314922
+PBE_MU = PBE_BETA * PI * PI / 3.0
+PBE_GAMMA = (1.0 - math.log(2.0)) / (PI * PI)
+FAMILY = {"lda_x": 1, "lda_c_pw": 1, "lda_c_pw_mod": 1, "gga_x_pbe": 2, "gga_c_pbe": 2}
+
+
+def _lda_x_unpol(rho):
+    return -0.75 * (3.0 / PI) ** (1.0 / 3) * rho ** (4.0 / 3)
+
+
+def _pw_g(rs, k, a):
+    b1, b2, b3, b4 = _PW_BETA[k]
+    den = 2 * a * (b1 * torch.sqrt(rs) + b2 * rs + b3 * rs ** 1.5 + b4 * rs * rs)
+    return -2 * a * (1 + _PW_ALPHA1[k] * rs) * torch.log1p(1.0 / den)
+
+
+def _pw_eps(rs, zeta, variant):
+    a, fz20 = _PW[variant]["a"], _PW[variant]["fz20"]
+    g0, g1, g2 = (_pw_g(rs, k, a[k]) for k in range(3))
+    fz = ((1 + zeta) ** (4.0 / 3) + (1 - zeta) ** (4.0 / 3) - 2) / (2 ** (4.0 / 3) - 2)
+    z4 = zeta ** 4
+    return g0 + z4 * fz * (g1 - g0 + g2 / fz20) - fz * g2 / fz20
+
+
+def edens_pol(name, ru, rd, gu=None, gd=None):
+    """Energy per unit volume from spin densities ru, rd (n,) and gradients gu, gd (3, n)."""
+    rho = ru + rd
+    if name == "lda_x":
+        return 0.5 * (_lda_x_unpol(2 * ru) + _lda_x_unpol(2 * rd))
+    if name in ("lda_c_pw", "lda_c_pw_mod"):
+        rs = (3.0 / (4 * PI * rho)) ** (1.0 / 3)
+        return rho * _pw_eps(rs, (ru - rd) / rho, "pw" if name == "lda_c_pw" else "pw_mod")
+    if name == "gga_x_pbe":
+        def one(r2, g2):  # r2 = 2 rho_sigma, g2 = grad of it
+            kf = (3 * PI * PI * r2) ** (1.0 / 3)
+            s2 = (g2 * g2).sum(0) / (2 * kf * r2) ** 2
+            return _lda_x_unpol(r2) * (1 + PBE_KAPPA - PBE_KAPPA / (1 + PBE_MU * s2 / PBE_KAPPA))
+        return 0.5 * (one(2 * ru, 2 * gu) + one(2 * rd, 2 * gd))
+    if name == "gga_c_pbe":
+        g = gu + gd
+        sigma = (g * g).sum(0)
+        zeta = (ru - rd) / rho
+        rs = (3.0 / (4 * PI * rho)) ** (1.0 / 3)
+        eps = _pw_eps(rs, zeta, "pw_mod")
+        phi = 0.5 * ((1 + zeta) ** (2.0 / 3) + (1 - zeta) ** (2.0 / 3))
+        kf = (3 * PI * PI * rho) ** (1.0 / 3)
+        ks = torch.sqrt(4 * kf / PI)
+        t2 = sigma / (2 * phi * ks * rho) ** 2
+        gp3 = PBE_GAMMA * phi ** 3
+        A = PBE_BETA / PBE_GAMMA / torch.expm1(-eps / gp3)
+        At2 = A * t2
+        H = gp3 * torch.log1p(PBE_BETA / PBE_GAMMA * t2 * (1 + At2) / (1 + At2 + At2 * At2))
+        return rho * (eps + H)
+    raise KeyError(name)
+
+
+def edens_unpol(name, rho, grad=None):
+    half_g = None if grad is None else 0.5 * grad
+    return edens_pol(name, 0.5 * rho, 0.5 * rho, half_g, half_g)
+
+
+def parse(xcstr):
+    """"a*f1 + f2" -> [(coef, name), ...] (the reference builds the same sum with eval,
+    dqc/api/getxc.py:38-59)."""
+    terms = []
+    for part in xcstr.replace("-", "+-").split("+"):
+        part = part.strip()
+        if not part:
+            continue
+        coef, name = 1.0, part
+        if "*" in part:
+            a, b = [x.strip() for x in part.split("*")]
+            try:
+                coef, name = float(a), b
+            except ValueError:
+                coef, name = float(b), a
+        terms.append((coef, name))
+    return terms
+
+
+def family(xcstr):
+    return max(FAMILY[n] for _, n in parse(xcstr))
+
+
+def eval_unpol(xcstr, rho, grad=None):
+    """Returns (edens (n,), vrho (n,), vgrad (3, n) or None) for the unpolarised case."""
+    fam = family(xcstr)
+    rho = rho.detach().clone().requires_grad_(True)
+    g = None if fam == 1 else grad.detach().clone().requires_grad_(True)
+    e = sum(c * edens_unpol(n, rho, g if FAMILY[n] == 2 else None) for c, n in parse(xcstr))
+    inputs = (rho,) if g is None else (rho, g)
+    grads = torch.autograd.grad(e.sum(), inputs, allow_unused=True)
+    vg = None
+    if g is not None:
+        vg = grads[1] if grads[1] is not None else torch.zeros_like(g)
+    return e.detach(), grads[0].detach(), (vg.detach() if vg is not None else None)
+
+
+def eval_pol(xcstr, ru, rd, gu=None, gd=None):
+    """Returns (edens, (vrho_u, vrho_d), (vgrad_u, vgrad_d) or None)."""
+    fam = family(xcstr)
+    ru = ru.detach().clone().requires_grad_(True)
+    rd = rd.detach().clone().requires_grad_(True)
+    if fam == 2:
+        gu = gu.detach().clone().requires_grad_(True)
+        gd = gd.detach().clone().requires_grad_(True)
+    e = sum(c * (edens_pol(n, ru, rd, gu, gd) if FAMILY[n] == 2 else edens_pol(n, ru, rd))
+            for c, n in parse(xcstr))
+    inputs = (ru, rd) if fam == 1 else (ru, rd, gu, gd)
+    grads = torch.autograd.grad(e.sum(), inputs, allow_unused=True)
+    grads = [x if x is not None else torch.zeros_like(i) for x, i in zip(grads, inputs)]
+    if fam == 1:
+        return e.detach(), (grads[0], grads[1]), None
+    return e.detach(), (grads[0], grads[1]), (grads[2], grads[3])
