@@ -1,0 +1,339 @@
+"""ctypes binding of libb200qc.so -- the only route from the PyTorch host code to the CUDA kernels.
+
+Mirrors the reference's own idiom (ctypes CDLL handles + raw pointers, dqc/hamilton/intor/utils.py:15-29,
+molintor.py:629-638), except that every pointer is a device pointer of a torch CUDA tensor and the
+current torch stream is passed explicitly.  There is NO CPU fallback: if the library cannot be
+loaded or no CUDA device is present, every entry point raises.
+"""
+import ctypes
+import os
+from typing import Optional
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.realpath(__file__))
+_SO_PATH = os.path.join(_HERE, "libb200qc.so")
+_lib = None
+_rys_loaded = False
+
+GRID_ALIGN = 128  # leading dimension of the grid axis (K2/K4 CTA tile)
+AO_ALIGN = 64     # leading dimension of the AO axis
+
+FUNC_IDS = {"lda_x": 1, "lda_c_pw": 2, "lda_c_pw_mod": 3, "gga_x_pbe": 101, "gga_c_pbe": 102}
+FUNC_FAMILY = {"lda_x": 1, "lda_c_pw": 1, "lda_c_pw_mod": 1, "gga_x_pbe": 2, "gga_c_pbe": 2}
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "b200qc_last_error": (ctypes.c_char_p, []),
+    "b200qc_version": (ctypes.c_int, []),
+    "b200qc_launch_count": (ctypes.c_int64, []),
+    "b200qc_basis_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_basis_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "b200qc_rys_upload": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_eval_gto": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_void_p]),
+    "b200qc_becke_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_rho": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_xc_unpol": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_xc_pol": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_vxc_worksize": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int64]),
+    "b200qc_vxc_mat": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p]),
+    "b200qc_int1e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_int2c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_int3c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_int2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_jk_direct": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_dfj_worksize": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int64]),
+    "b200qc_dfj": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_pack_tril": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
+}
+
+
+class B200QCError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    """Names declared in include/b200qc.h (used by the CPU test that checks the .so exports them)."""
+    return sorted(_SIGS.keys())
+
+
+def load(require_cuda: bool = True):
+    """Load libb200qc.so (once).  Raises -- never falls back -- when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO_PATH):
+            raise B200QCError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback for the Fock-build path." % _SO_PATH)
+        lib = ctypes.CDLL(_SO_PATH)
+        missing = [name for name in _SIGS if not hasattr(lib, name)]
+        if missing:
+            raise B200QCError("libb200qc.so does not export %s (header/library mismatch; rebuild)" % missing)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    if require_cuda and not torch.cuda.is_available():
+        raise B200QCError("no CUDA device: the B200 Fock-build path has no CPU fallback")
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load(False).b200qc_last_error()
+        raise B200QCError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    if t is None:
+        return ctypes.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor required"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _np(a: np.ndarray) -> ctypes.c_void_p:
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def launch_count() -> int:
+    return int(load(False).b200qc_launch_count())
+
+
+def round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def ensure_rys_table():
+    """Upload the Rys interpolation table (dqc_b200/data/rys_table.npz) once per process."""
+    global _rys_loaded
+    if _rys_loaded:
+        return
+    lib = load()
+    with np.load(os.path.join(_HERE, "data", "rys_table.npz")) as z:
+        nmax, h, deg, xmax = z["meta"]
+        nmax, deg = int(nmax), int(deg)
+        coefs = [np.ascontiguousarray(z["coef_%d" % n], dtype=np.float64) for n in range(1, nmax + 1)]
+        herms = [np.ascontiguousarray(z["herm_%d" % n], dtype=np.float64) for n in range(1, nmax + 1)]
+    cptr = (ctypes.c_void_p * nmax)(*[c.ctypes.data for c in coefs])
+    hptr = (ctypes.c_void_p * nmax)(*[c.ctypes.data for c in herms])
+    _check(lib.b200qc_rys_upload(nmax, float(h), deg, float(xmax), cptr, hptr), "rys_upload")
+    _rys_loaded = True
+
+
+class DeviceBasis(object):
+    """Handle of a basis uploaded to the GPU (b200qc_basis_upload)."""
+
+    def __init__(self, atm, bas, env, ao_loc, spherical=True, device=None):
+        if not spherical:
+            raise NotImplementedError("only spherical AOs (the reference's default everywhere) are built")
+        lib = load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.atm = np.ascontiguousarray(atm, dtype=np.int32)
+        self.bas = np.ascontiguousarray(bas, dtype=np.int32)
+        self.env = np.ascontiguousarray(env, dtype=np.float64)
+        self.ao_loc = np.ascontiguousarray(ao_loc, dtype=np.int32)
+        h = ctypes.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _check(lib.b200qc_basis_upload(_np(self.atm), len(self.atm), _np(self.bas), len(self.bas),
+                                           _np(self.env), len(self.env), _np(self.ao_loc), ctypes.byref(h)),
+                   "basis_upload")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                load(False).b200qc_basis_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def nao(self, sh0, sh1):
+        return int(self.ao_loc[sh1] - self.ao_loc[sh0])
+
+
+# ------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (one per C entry point)
+
+def eval_gto(basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, deriv: int,
+             ngrid_ld: Optional[int] = None, ao_ld: Optional[int] = None) -> torch.Tensor:
+    """Returns the padded AO buffer (ncomp, ngrid_ld, ao_ld), zero in the padding."""
+    lib = load()
+    ngrid = coords.shape[0]
+    nao = basis.nao(sh0, sh1)
+    ngrid_ld = round_up(max(ngrid, 1), GRID_ALIGN) if ngrid_ld is None else ngrid_ld
+    ao_ld = round_up(nao, AO_ALIGN) if ao_ld is None else ao_ld
+    ncomp = 4 if deriv else 1
+    ao = torch.zeros((ncomp, ngrid_ld, ao_ld), dtype=torch.float64, device=coords.device)
+    coords = coords.contiguous()
+    _check(lib.b200qc_eval_gto(basis.handle, sh0, sh1, deriv, _ptr(coords), ngrid, _ptr(ao), ngrid_ld, ao_ld,
+                               _stream()), "eval_gto")
+    return ao
+
+
+def becke_weights(xyz, owner, atompos, aij=None):
+    lib = load()
+    xyz = xyz.contiguous()
+    owner = owner.to(torch.int32).contiguous()
+    w = torch.empty(xyz.shape[0], dtype=torch.float64, device=xyz.device)
+    _check(lib.b200qc_becke_weights(_ptr(xyz), _ptr(owner), xyz.shape[0], _ptr(atompos.contiguous()),
+                                    atompos.shape[0], _ptr(aij), _ptr(w), _stream()), "becke_weights")
+    return w
+
+
+def rho(ao: torch.Tensor, dm_pad: torch.Tensor, with_grad: bool):
+    """ao (ncomp, ngrid_ld, ao_ld); dm_pad (ao_ld, ao_ld).  Returns rho (ngrid_ld), grad (3, ngrid_ld)|None."""
+    lib = load()
+    _, ngl, aol = ao.shape
+    r = torch.empty(ngl, dtype=torch.float64, device=ao.device)
+    g = torch.empty((3, ngl), dtype=torch.float64, device=ao.device) if with_grad else None
+    _check(lib.b200qc_rho(_ptr(ao), ngl, aol, _ptr(dm_pad), _ptr(r), _ptr(g), _stream()), "rho")
+    return r, g
+
+
+def _terms(terms):
+    ids = np.array([FUNC_IDS[n] for _, n in terms], dtype=np.int32)
+    coefs = np.array([float(c) for c, _ in terms], dtype=np.float64)
+    return ids, coefs
+
+
+def xc_unpol(terms, rho_t, grad_t, want_e=True, want_v=True):
+    """terms: [(coef, name)].  rho (n,), grad (3, n)|None -> edens, vrho, vgrad (3, n)|None."""
+    lib = load()
+    ids, coefs = _terms(terms)
+    n = rho_t.shape[-1]
+    gga = grad_t is not None
+    e = torch.empty_like(rho_t) if want_e else None
+    vr = torch.empty_like(rho_t) if want_v else None
+    vg = torch.empty_like(grad_t) if (want_v and gga) else None
+    _check(lib.b200qc_xc_unpol(len(ids), _np(ids), _np(coefs), n, n, _ptr(rho_t), _ptr(grad_t), _ptr(e), _ptr(vr),
+                               _ptr(vg), _stream()), "xc_unpol")
+    return e, vr, vg
+
+
+def xc_pol(terms, rho_t, grad_t, want_e=True, want_v=True):
+    """rho (2, n), grad (2, 3, n)|None -> edens (n,), vrho (2, n), vgrad (2, 3, n)|None."""
+    lib = load()
+    ids, coefs = _terms(terms)
+    n = rho_t.shape[-1]
+    gga = grad_t is not None
+    e = torch.empty(n, dtype=rho_t.dtype, device=rho_t.device) if want_e else None
+    vr = torch.empty_like(rho_t) if want_v else None
+    vg = torch.empty_like(grad_t) if (want_v and gga) else None
+    _check(lib.b200qc_xc_pol(len(ids), _np(ids), _np(coefs), n, n, _ptr(rho_t), _ptr(grad_t), _ptr(e), _ptr(vr),
+                             _ptr(vg), _stream()), "xc_pol")
+    return e, vr, vg
+
+
+_work_cache = {}
+
+
+def _workspace(numel: int, device) -> torch.Tensor:
+    key = (str(device),)
+    buf = _work_cache.get(key)
+    if buf is None or buf.numel() < numel:
+        _work_cache[key] = None
+        buf = torch.empty(numel, dtype=torch.float64, device=device)
+        _work_cache[key] = buf
+    return buf
+
+
+def vxc_mat(ao, weights, vrho, vgrad):
+    """Returns the padded (ao_ld, ao_ld) matrix sum_g w phi^T (vrho phi + 2 vgrad . dphi)."""
+    lib = load()
+    _, ngl, aol = ao.shape
+    work = _workspace(int(lib.b200qc_vxc_worksize(ngl, aol)), ao.device)
+    mat = torch.empty((aol, aol), dtype=torch.float64, device=ao.device)
+    _check(lib.b200qc_vxc_mat(_ptr(ao), ngl, aol, _ptr(weights), _ptr(vrho), _ptr(vgrad), _ptr(mat), _ptr(work),
+                              _stream()), "vxc_mat")
+    return mat
+
+
+def int1e(basis: DeviceBasis, kind: str, shls, rinv_orig=None):
+    lib = load()
+    ensure_rys_table()
+    kinds = {"ovlp": 0, "kin": 1, "nuc": 2, "rinv": 3}
+    sl = np.array(shls, dtype=np.int32)
+    out = torch.zeros((basis.nao(sl[0], sl[1]), basis.nao(sl[2], sl[3])), dtype=torch.float64, device=basis.device)
+    ro = np.zeros(3) if rinv_orig is None else np.ascontiguousarray(rinv_orig, dtype=np.float64)
+    _check(lib.b200qc_int1e(basis.handle, kinds[kind], _np(sl), _np(ro), _ptr(out), _stream()), "int1e")
+    return out
+
+
+def int2c2e(basis: DeviceBasis, shls):
+    lib = load()
+    ensure_rys_table()
+    sl = np.array(shls, dtype=np.int32)
+    out = torch.zeros((basis.nao(sl[0], sl[1]), basis.nao(sl[2], sl[3])), dtype=torch.float64, device=basis.device)
+    _check(lib.b200qc_int2c2e(basis.handle, _np(sl), _ptr(out), _stream()), "int2c2e")
+    return out
+
+
+def int3c2e(basis: DeviceBasis, shls):
+    lib = load()
+    ensure_rys_table()
+    sl = np.array(shls, dtype=np.int32)
+    shape = tuple(basis.nao(sl[2 * q], sl[2 * q + 1]) for q in range(3))
+    out = torch.zeros(shape, dtype=torch.float64, device=basis.device)
+    _check(lib.b200qc_int3c2e(basis.handle, _np(sl), _ptr(out), _stream()), "int3c2e")
+    return out
+
+
+def int2e(basis: DeviceBasis, shls):
+    lib = load()
+    ensure_rys_table()
+    sl = np.array(shls, dtype=np.int32)
+    shape = tuple(basis.nao(sl[2 * q], sl[2 * q + 1]) for q in range(4))
+    out = torch.zeros(shape, dtype=torch.float64, device=basis.device)
+    _check(lib.b200qc_int2e(basis.handle, _np(sl), _ptr(out), _stream()), "int2e")
+    return out
+
+
+def jk_direct(basis: DeviceBasis, sh0, sh1, dm, with_j=True, with_k=True):
+    """dm (nset, nao, nao) AO basis -> vj, vk (nset, nao, nao) (either may be None)."""
+    lib = load()
+    ensure_rys_table()
+    dm = dm.contiguous()
+    vj = torch.zeros_like(dm) if with_j else None
+    vk = torch.zeros_like(dm) if with_k else None
+    _check(lib.b200qc_jk_direct(basis.handle, sh0, sh1, _ptr(dm), dm.shape[0], _ptr(vj), _ptr(vk), _stream()),
+           "jk_direct")
+    return vj, vk
+
+
+def pack_tril(full):
+    lib = load()
+    nao, _, naux = full.shape
+    out = torch.empty((nao * (nao + 1) // 2, naux), dtype=torch.float64, device=full.device)
+    _check(lib.b200qc_pack_tril(_ptr(full.contiguous()), nao, naux, _ptr(out), _stream()), "pack_tril")
+    return out
+
+
+def dfj(j3c_packed, nao, inv_j2c, dm):
+    lib = load()
+    naux = j3c_packed.shape[1]
+    work = _workspace(int(lib.b200qc_dfj_worksize(nao, naux)), dm.device)
+    vj = torch.empty((nao, nao), dtype=torch.float64, device=dm.device)
+    _check(lib.b200qc_dfj(_ptr(j3c_packed), nao, naux, _ptr(inv_j2c.contiguous()), _ptr(dm.contiguous()), _ptr(vj),
+                          _ptr(work), _stream()), "dfj")
+    return vj

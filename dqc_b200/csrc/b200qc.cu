@@ -1,0 +1,16 @@
+// b200qc -- single translation unit of the B200-native Fock-build library (see include/b200qc.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include "common.cuh"
+#include "tables.cuh"
+#include "ao_eval.cuh"
+#include "becke.cuh"
+#include "xc.cuh"
+#include "gemm_f64.cuh"
+#include "rho.cuh"
+#include "vxc.cuh"
+#ifdef B200QC_WITH_INTS
+#include "rys.cuh"
+#include "ints.cuh"
+#include "dfj.cuh"
+#endif
+#include "stubs_tmp.cuh"

@@ -1,0 +1,188 @@
+// Host-side construction of the constant tables + basis upload + error plumbing.
+#pragma once
+#include "common.cuh"
+#include <cmath>
+#include <mutex>
+
+static thread_local std::string g_last_error;
+static void b200qc_set_error(const std::string &msg) { g_last_error = msg; }
+
+extern "C" const char *b200qc_last_error(void) { return g_last_error.c_str(); }
+extern "C" int b200qc_version(void) { return 100; }
+extern "C" int64_t b200qc_launch_count(void) { return g_launch_count; }
+
+namespace {
+double h_binom(int n, int k) {
+    if (k < 0 || k > n) return 0.0;
+    double r = 1.0;
+    for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+    return r;
+}
+double h_fact(int n) {
+    double r = 1.0;
+    for (int i = 2; i <= n; i++) r *= i;
+    return r;
+}
+// libcint cartesian order: lx descending, then ly descending
+int h_cart_index(int l, int lx, int ly) {
+    int idx = 0;
+    for (int x = l; x > lx; x--) idx += l - x + 1;
+    return idx + (l - lx - ly);
+}
+// Real solid harmonics r^l Y_lm as polynomials in x, y, z (Helgaker/Jorgensen/Olsen eq. 6.4.47),
+// m = -l..l; s and p follow libcint's special cases (p ordered x, y, z).
+void h_fill_c2s(int l, double *M) {
+    int nc = NCART(l), ns = 2 * l + 1;
+    for (int i = 0; i < ns * nc; i++) M[i] = 0.0;
+    if (l == 0) {
+        M[0] = 0.282094791773878143;
+        return;
+    }
+    if (l == 1) {
+        M[0] = M[4] = M[8] = 0.488602511902919921;
+        return;
+    }
+    const double pi = 3.14159265358979323846;
+    double pref = std::sqrt((2 * l + 1) / (4 * pi));
+    for (int m = -l; m <= l; m++) {
+        int am = m < 0 ? -m : m;
+        double N = std::sqrt(2.0 * h_fact(l + am) * h_fact(l - am) / (m == 0 ? 2.0 : 1.0)) /
+                   (std::pow(2.0, am) * h_fact(l));
+        int vm2 = m < 0 ? 1 : 0;
+        for (int t = 0; t <= (l - am) / 2; t++)
+            for (int u = 0; u <= t; u++)
+                for (int v2 = vm2; v2 <= am; v2 += 2) {
+                    int sp = t + (v2 - vm2) / 2;
+                    double C = ((sp & 1) ? -1.0 : 1.0) * std::pow(0.25, t) * h_binom(l, t) *
+                               h_binom(l - t, am + t) * h_binom(t, u) * h_binom(am, v2);
+                    int ex = 2 * t + am - 2 * u - v2, ey = 2 * u + v2;
+                    if (ex < 0) continue;
+                    M[(m + l) * nc + h_cart_index(l, ex, ey)] += pref * N * C;
+                }
+    }
+}
+std::once_flag g_tables_once;
+int g_tables_status = 0;
+}  // namespace
+
+static int qc_init_tables() {
+    std::call_once(g_tables_once, [] {
+        C2STables t;
+        h_fill_c2s(0, t.s0);
+        h_fill_c2s(1, t.s1);
+        h_fill_c2s(2, t.s2);
+        h_fill_c2s(3, t.s3);
+        h_fill_c2s(4, t.s4);
+        signed char pw[B200QC_LMAX + 1][15][3] = {};
+        for (int l = 0; l <= B200QC_LMAX; l++) {
+            int k = 0;
+            for (int x = l; x >= 0; x--)
+                for (int y = l - x; y >= 0; y--) {
+                    pw[l][k][0] = (signed char)x;
+                    pw[l][k][1] = (signed char)y;
+                    pw[l][k][2] = (signed char)(l - x - y);
+                    k++;
+                }
+        }
+        cudaError_t e = cudaMemcpyToSymbol(c_c2s, &t, sizeof(t));
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_cart_pow, pw, sizeof(pw));
+        if (e != cudaSuccess) {
+            b200qc_set_error(std::string("constant table upload failed: ") + cudaGetErrorString(e));
+            g_tables_status = 1;
+        }
+    });
+    return g_tables_status;
+}
+
+extern "C" int b200qc_basis_upload(const int *h_atm, int natm, const int *h_bas, int nbas,
+                                   const double *h_env, int nenv, const int *h_ao_loc,
+                                   b200qc_basis **out) {
+    QC_REQUIRE(out != nullptr && natm > 0 && nbas > 0, "bad arguments");
+    if (qc_init_tables()) return 1;
+    auto *b = new b200qc_basis();
+    b->natm = natm;
+    b->nbas = nbas;
+    b->nenv = nenv;
+    b->h_atm.assign(h_atm, h_atm + natm * ATM_SLOTS);
+    b->h_bas.assign(h_bas, h_bas + nbas * BAS_SLOTS);
+    b->h_env.assign(h_env, h_env + nenv);
+    b->h_ao_loc.assign(h_ao_loc, h_ao_loc + nbas + 1);
+    b->h_shells.resize(nbas);
+    for (int i = 0; i < nbas; i++) {
+        const int *bs = h_bas + i * BAS_SLOTS;
+        ShellRec &s = b->h_shells[i];
+        int pc = h_atm[bs[0] * ATM_SLOTS + 1];
+        s.x = h_env[pc];
+        s.y = h_env[pc + 1];
+        s.z = h_env[pc + 2];
+        s.l = bs[1];
+        s.nprim = bs[2];
+        s.ptr_exp = bs[5];
+        s.ptr_coef = bs[6];
+        s.ao_off = h_ao_loc[i];
+        s.atom = bs[0];
+        if (s.l > B200QC_LMAX) {
+            delete b;
+            b200qc_set_error("angular momentum above g is not supported");
+            return 2;
+        }
+        if (bs[3] != 1) {
+            delete b;
+            b200qc_set_error("only nctr = 1 shells (the reference never emits anything else)");
+            return 2;
+        }
+    }
+    QC_CHECK(cudaMalloc(&b->d_atm, sizeof(int) * natm * ATM_SLOTS));
+    QC_CHECK(cudaMalloc(&b->d_bas, sizeof(int) * nbas * BAS_SLOTS));
+    QC_CHECK(cudaMalloc(&b->d_ao_loc, sizeof(int) * (nbas + 1)));
+    QC_CHECK(cudaMalloc(&b->d_env, sizeof(double) * nenv));
+    QC_CHECK(cudaMalloc(&b->d_shells, sizeof(ShellRec) * nbas));
+    QC_CHECK(cudaMemcpy(b->d_atm, h_atm, sizeof(int) * natm * ATM_SLOTS, cudaMemcpyHostToDevice));
+    QC_CHECK(cudaMemcpy(b->d_bas, h_bas, sizeof(int) * nbas * BAS_SLOTS, cudaMemcpyHostToDevice));
+    QC_CHECK(cudaMemcpy(b->d_ao_loc, h_ao_loc, sizeof(int) * (nbas + 1), cudaMemcpyHostToDevice));
+    QC_CHECK(cudaMemcpy(b->d_env, h_env, sizeof(double) * nenv, cudaMemcpyHostToDevice));
+    QC_CHECK(cudaMemcpy(b->d_shells, b->h_shells.data(), sizeof(ShellRec) * nbas, cudaMemcpyHostToDevice));
+    *out = b;
+    return 0;
+}
+
+extern "C" int b200qc_basis_free(b200qc_basis *b) {
+    if (!b) return 0;
+    cudaFree(b->d_atm);
+    cudaFree(b->d_bas);
+    cudaFree(b->d_ao_loc);
+    cudaFree(b->d_env);
+    cudaFree(b->d_shells);
+    delete b;
+    return 0;
+}
+
+static std::vector<double *> g_rys_dev;
+
+extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
+                                 const double *const *h_coef, const double *const *h_herm) {
+    QC_REQUIRE(nmax >= 1 && nmax <= RYS_NMAX, "nmax out of range");
+    for (double *p : g_rys_dev) cudaFree(p);
+    g_rys_dev.clear();
+    RysTable t = {};
+    t.nmax = nmax;
+    t.deg = deg;
+    t.h = h;
+    t.xmax = xmax;
+    t.nint = (int)std::llround(xmax / h);
+    for (int n = 1; n <= nmax; n++) {
+        size_t cnt = (size_t)t.nint * 2 * n * (deg + 1);
+        double *d = nullptr;
+        QC_CHECK(cudaMalloc(&d, cnt * sizeof(double)));
+        QC_CHECK(cudaMemcpy(d, h_coef[n - 1], cnt * sizeof(double), cudaMemcpyHostToDevice));
+        g_rys_dev.push_back(d);
+        t.coef[n - 1] = d;
+        for (int r = 0; r < n; r++) {
+            t.herm[n - 1][0][r] = h_herm[n - 1][r];
+            t.herm[n - 1][1][r] = h_herm[n - 1][n + r];
+        }
+    }
+    QC_CHECK(cudaMemcpyToSymbol(c_rys, &t, sizeof(t)));
+    g_rys_ready = true;
+    return 0;
+}

@@ -1,0 +1,316 @@
+// K3 -- pointwise LDA/GGA exchange-correlation (value + first derivatives).
+// Replaces pylibxc's LibXCFunctional.compute as driven by dqc/xc/libxc_wrapper.py:380-413 with the
+// input/output massaging of dqc/xc/libxc.py:124-242 fused in (sigma = |grad rho|^2 is formed here,
+// the energy comes back per unit volume, the gradient potential as 2 vsigma grad rho).
+// Functional forms are the published ones (Slater; Perdew-Wang 92 with libxc's `pw` and `pw_mod`
+// parameter sets; PBE exchange and correlation); derivatives are hand-derived and checked in
+// tests against torch autograd of the energy (the reference's own default route).
+#pragma once
+#include "common.cuh"
+
+#define XC_LDA_X 1
+#define XC_LDA_C_PW 2
+#define XC_LDA_C_PW_MOD 3
+#define XC_GGA_X_PBE 101
+#define XC_GGA_C_PBE 102
+#define XC_MAX_TERMS 8
+#define XC_RHO_CUT 1e-15   // densities at or below this contribute exactly zero (libxc-style threshold)
+
+struct XCTerms {
+    int n;
+    int id[XC_MAX_TERMS];
+    double coef[XC_MAX_TERMS];
+};
+
+namespace xc {
+constexpr double PI = 3.14159265358979323846;
+constexpr double KAPPA = 0.8040;
+constexpr double BETA = 0.06672455060314922;
+constexpr double MU = BETA * PI * PI / 3.0;
+constexpr double GAMMA = 0.031090690869654895034;  // (1 - ln 2) / pi^2
+constexpr double CX = -0.73855876638202240588;     // -3/4 (3/pi)^(1/3)
+constexpr double FZ_DEN = 0.51984209978974632953;  // 2^(4/3) - 2
+
+struct PWParams {
+    double a[3], alpha1[3], b1[3], b2[3], b3[3], b4[3], fz20;
+};
+__device__ __forceinline__ PWParams pw_params(bool mod) {
+    PWParams p;
+    if (mod) {
+        p.a[0] = 0.0310907; p.a[1] = 0.01554535; p.a[2] = 0.0168869;
+        p.fz20 = 1.709920934161365617563962776245;
+    } else {
+        p.a[0] = 0.031091; p.a[1] = 0.015545; p.a[2] = 0.016887;
+        p.fz20 = 1.709921;
+    }
+    p.alpha1[0] = 0.21370; p.alpha1[1] = 0.20548; p.alpha1[2] = 0.11125;
+    p.b1[0] = 7.5957; p.b1[1] = 14.1189; p.b1[2] = 10.357;
+    p.b2[0] = 3.5876; p.b2[1] = 6.1977; p.b2[2] = 3.6231;
+    p.b3[0] = 1.6382; p.b3[1] = 3.3662; p.b3[2] = 0.88026;
+    p.b4[0] = 0.49294; p.b4[1] = 0.62517; p.b4[2] = 0.49671;
+    return p;
+}
+// G(rs) = -2a(1+alpha1 rs) ln(1 + 1/Q1) and dG/drs
+__device__ __forceinline__ void pw_g(const PWParams &p, int k, double rs, double &g, double &dg) {
+    const double srs = sqrt(rs);
+    const double a = p.a[k];
+    const double Q1 = 2 * a * (p.b1[k] * srs + p.b2[k] * rs + p.b3[k] * rs * srs + p.b4[k] * rs * rs);
+    const double dQ1 = 2 * a * (0.5 * p.b1[k] / srs + p.b2[k] + 1.5 * p.b3[k] * srs + 2 * p.b4[k] * rs);
+    const double lg = log1p(1.0 / Q1);
+    const double Q0 = -2 * a * (1 + p.alpha1[k] * rs);
+    g = Q0 * lg;
+    dg = -2 * a * p.alpha1[k] * lg - Q0 * dQ1 / (Q1 * (Q1 + 1.0));
+}
+// PW92 eps_c(rs, zeta) with d/drs and d/dzeta
+__device__ __forceinline__ void pw_eps(bool mod, double rs, double zeta, double &eps, double &deps_drs,
+                                       double &deps_dz) {
+    const PWParams p = pw_params(mod);
+    double g0, d0;
+    pw_g(p, 0, rs, g0, d0);
+    if (zeta == 0.0) {
+        eps = g0;
+        deps_drs = d0;
+        deps_dz = 0.0;
+        return;
+    }
+    double g1, d1, g2, d2;
+    pw_g(p, 1, rs, g1, d1);
+    pw_g(p, 2, rs, g2, d2);
+    const double opz = fmax(1.0 + zeta, 1e-15), omz = fmax(1.0 - zeta, 1e-15);
+    const double f = (opz * cbrt(opz) + omz * cbrt(omz) - 2.0) / FZ_DEN;
+    const double df = (4.0 / 3.0) * (cbrt(opz) - cbrt(omz)) / FZ_DEN;
+    const double z3 = zeta * zeta * zeta, z4 = z3 * zeta;
+    const double w = g1 - g0 + g2 / p.fz20;
+    eps = g0 + z4 * f * w - f * g2 / p.fz20;
+    deps_drs = d0 + z4 * f * (d1 - d0 + d2 / p.fz20) - f * d2 / p.fz20;
+    deps_dz = (4 * z3 * f + z4 * df) * w - df * g2 / p.fz20;
+}
+
+// ---- unpolarised: (rho, sigma) -> e (per volume), de/drho, de/dsigma ----
+__device__ __forceinline__ void lda_x_unpol(double rho, double &e, double &vr) {
+    const double r13 = cbrt(rho);
+    e = CX * rho * r13;
+    vr = (4.0 / 3.0) * CX * r13;
+}
+__device__ __forceinline__ void lda_c_pw_unpol(bool mod, double rho, double &e, double &vr) {
+    const double rs = cbrt(3.0 / (4 * PI * rho));
+    double eps, drs, dz;
+    pw_eps(mod, rs, 0.0, eps, drs, dz);
+    e = rho * eps;
+    vr = eps - (rs / 3.0) * drs;
+}
+__device__ __forceinline__ void gga_x_pbe_unpol(double rho, double sigma, double &e, double &vr, double &vs) {
+    const double r13 = cbrt(rho);
+    const double elda = CX * rho * r13;
+    const double c = 4.0 * 9.5707800006273050 ;  // 4 (3 pi^2)^(2/3)
+    const double r83 = rho * rho * r13 * r13;     // rho^(8/3)
+    const double s2 = sigma / (c * r83);
+    const double den = 1.0 + MU * s2 / KAPPA;
+    const double F = 1.0 + KAPPA - KAPPA / den;
+    const double dF = MU / (den * den);  // dF/ds2
+    e = elda * F;
+    vr = (4.0 / 3.0) * (elda / rho) * F - elda * dF * (8.0 / 3.0) * s2 / rho;
+    vs = elda * dF / (c * r83);
+}
+// PBE correlation, general spin polarisation.  Outputs e, de/drho_up, de/drho_dn, de/dsigma_total.
+__device__ __forceinline__ void gga_c_pbe_core(double rho, double zeta, double sigma, double &e, double &vu,
+                                               double &vd, double &vs) {
+    const double rs = cbrt(3.0 / (4 * PI * rho));
+    double eps, deps_drs, deps_dz;
+    pw_eps(true, rs, zeta, eps, deps_drs, deps_dz);
+    double phi = 1.0, dphi = 0.0;
+    if (zeta != 0.0) {
+        const double opz = fmax(1.0 + zeta, 1e-15), omz = fmax(1.0 - zeta, 1e-15);
+        const double a = cbrt(opz), b = cbrt(omz);
+        phi = 0.5 * (a * a + b * b);
+        dphi = (1.0 / 3.0) * (1.0 / a - 1.0 / b);
+    }
+    const double phi3 = phi * phi * phi;
+    const double r13 = cbrt(rho);
+    // t^2 = sigma pi / (16 (3 pi^2)^(1/3) phi^2 rho^(7/3))
+    const double ct = PI / (16.0 * 3.0936677262801355);
+    const double r73 = rho * rho * r13;
+    const double y = ct * sigma / (phi * phi * r73);
+    const double gp3 = GAMMA * phi3;
+    const double q = -eps / gp3;
+    const double E = expm1(q);
+    const double bg = BETA / GAMMA;
+    const double A = bg / E;
+    const double Ay = A * y;
+    const double N = 1.0 + Ay, D = 1.0 + Ay + Ay * Ay;
+    const double P = bg * y * N / D;
+    const double lg = log1p(P);
+    const double H = gp3 * lg;
+    const double P_y = bg * (1.0 + 2.0 * Ay) / (D * D);
+    const double P_A = -bg * A * y * y * y * (2.0 + Ay) / (D * D);
+    const double H_y = gp3 * P_y / (1.0 + P);
+    const double H_A = gp3 * P_A / (1.0 + P);
+    const double A_q = -A * (E + 1.0) / E;
+    const double H_eps = H_A * A_q * (-1.0 / gp3);
+    const double H_phi = 3.0 * GAMMA * phi * phi * lg + H_A * A_q * (3.0 * eps / (gp3 * phi)) + H_y * (-2.0 * y / phi);
+    e = rho * (eps + H);
+    // d/drho at fixed zeta, then the zeta part
+    const double deps_drho = -(rs / (3.0 * rho)) * deps_drs;
+    const double common = (eps + H) + rho * (deps_drho * (1.0 + H_eps) + H_y * (-(7.0 / 3.0) * y / rho));
+    const double dz = rho * (deps_dz * (1.0 + H_eps) + H_phi * dphi);  // rho * d(eps+H)/dzeta
+    vu = common + dz * (1.0 - zeta) / rho;
+    vd = common - dz * (1.0 + zeta) / rho;
+    vs = rho * H_y * ct / (phi * phi * r73);
+}
+}  // namespace xc
+
+// rho (n), grad (3, ld) -> edens (n), vrho (n), vgrad (3, ld)
+__global__ void xc_unpol_kernel(XCTerms terms, int64_t n, int64_t ld, const double *__restrict__ rho,
+                                const double *__restrict__ grad, double *__restrict__ edens,
+                                double *__restrict__ vrho, double *__restrict__ vgrad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double r = rho[i];
+    double gx = 0, gy = 0, gz = 0, sigma = 0;
+    if (grad) {
+        gx = grad[i];
+        gy = grad[ld + i];
+        gz = grad[2 * ld + i];
+        sigma = gx * gx + gy * gy + gz * gz;
+    }
+    double e = 0, vr = 0, vs = 0;
+    if (r > XC_RHO_CUT) {
+        for (int k = 0; k < terms.n; k++) {
+            double ek = 0, vrk = 0, vsk = 0;
+            switch (terms.id[k]) {
+                case XC_LDA_X: xc::lda_x_unpol(r, ek, vrk); break;
+                case XC_LDA_C_PW: xc::lda_c_pw_unpol(false, r, ek, vrk); break;
+                case XC_LDA_C_PW_MOD: xc::lda_c_pw_unpol(true, r, ek, vrk); break;
+                case XC_GGA_X_PBE: xc::gga_x_pbe_unpol(r, sigma, ek, vrk, vsk); break;
+                case XC_GGA_C_PBE: {
+                    double vd;
+                    xc::gga_c_pbe_core(r, 0.0, sigma, ek, vrk, vd, vsk);
+                    break;
+                }
+            }
+            e += terms.coef[k] * ek;
+            vr += terms.coef[k] * vrk;
+            vs += terms.coef[k] * vsk;
+        }
+    }
+    if (edens) edens[i] = e;
+    if (vrho) vrho[i] = vr;
+    if (vgrad) {
+        vgrad[i] = 2.0 * vs * gx;
+        vgrad[ld + i] = 2.0 * vs * gy;
+        vgrad[2 * ld + i] = 2.0 * vs * gz;
+    }
+}
+
+// spin-polarised: rho (2, ld), grad (2, 3, ld) -> edens (n), vrho (2, ld), vgrad (2, 3, ld)
+// vgrad_u = 2 vs_uu grad_u + vs_ud grad_d, vgrad_d = 2 vs_dd grad_d + vs_ud grad_u (libxc.py:212-215)
+__global__ void xc_pol_kernel(XCTerms terms, int64_t n, int64_t ld, const double *__restrict__ rho,
+                              const double *__restrict__ grad, double *__restrict__ edens,
+                              double *__restrict__ vrho, double *__restrict__ vgrad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ru = rho[i], rd = rho[ld + i];
+    double gu[3] = {0, 0, 0}, gd[3] = {0, 0, 0};
+    if (grad) {
+        for (int d = 0; d < 3; d++) {
+            gu[d] = grad[d * ld + i];
+            gd[d] = grad[(3 + d) * ld + i];
+        }
+    }
+    const double suu = gu[0] * gu[0] + gu[1] * gu[1] + gu[2] * gu[2];
+    const double sdd = gd[0] * gd[0] + gd[1] * gd[1] + gd[2] * gd[2];
+    const double sud = gu[0] * gd[0] + gu[1] * gd[1] + gu[2] * gd[2];
+    const double rt = ru + rd;
+    double e = 0, vu = 0, vd = 0, vsuu = 0, vsud = 0, vsdd = 0;
+    for (int k = 0; k < terms.n; k++) {
+        double ek = 0, vuk = 0, vdk = 0, suuk = 0, sudk = 0, sddk = 0;
+        const int id = terms.id[k];
+        if (id == XC_LDA_X || id == XC_GGA_X_PBE) {
+            // spin scaling: E[ru, rd] = (E[2 ru] + E[2 rd]) / 2
+            for (int s = 0; s < 2; s++) {
+                const double r2 = 2.0 * (s ? rd : ru);
+                if (!(r2 > XC_RHO_CUT)) continue;
+                double es, vr, vs = 0;
+                if (id == XC_LDA_X) xc::lda_x_unpol(r2, es, vr);
+                else xc::gga_x_pbe_unpol(r2, 4.0 * (s ? sdd : suu), es, vr, vs);
+                ek += 0.5 * es;
+                // d/dr_s [0.5 E(2 r_s, 4 sigma_ss)] = vr ; d/dsigma_ss = 2 vs
+                if (s) { vdk = vr; sddk = 2.0 * vs; } else { vuk = vr; suuk = 2.0 * vs; }
+            }
+        } else if (rt > XC_RHO_CUT) {
+            const double zeta = fmin(fmax((ru - rd) / rt, -1.0), 1.0);
+            if (id == XC_LDA_C_PW || id == XC_LDA_C_PW_MOD) {
+                const double rs = cbrt(3.0 / (4 * xc::PI * rt));
+                double eps, drs, dz;
+                xc::pw_eps(id == XC_LDA_C_PW_MOD, rs, zeta, eps, drs, dz);
+                ek = rt * eps;
+                const double common = eps - (rs / 3.0) * drs;
+                vuk = common + dz * (1.0 - zeta);
+                vdk = common - dz * (1.0 + zeta);
+            } else if (id == XC_GGA_C_PBE) {
+                double vs;
+                xc::gga_c_pbe_core(rt, zeta, suu + 2.0 * sud + sdd, ek, vuk, vdk, vs);
+                suuk = vs; sudk = 2.0 * vs; sddk = vs;
+            }
+        }
+        const double c = terms.coef[k];
+        e += c * ek; vu += c * vuk; vd += c * vdk;
+        vsuu += c * suuk; vsud += c * sudk; vsdd += c * sddk;
+    }
+    if (edens) edens[i] = e;
+    if (vrho) {
+        vrho[i] = vu;
+        vrho[ld + i] = vd;
+    }
+    if (vgrad) {
+        for (int d = 0; d < 3; d++) {
+            vgrad[d * ld + i] = 2.0 * vsuu * gu[d] + vsud * gd[d];
+            vgrad[(3 + d) * ld + i] = 2.0 * vsdd * gd[d] + vsud * gu[d];
+        }
+    }
+}
+
+static int xc_pack_terms(int nterm, const int *ids, const double *coefs, XCTerms &t, bool &gga) {
+    QC_REQUIRE(nterm >= 1 && nterm <= XC_MAX_TERMS, "1..8 functional terms supported");
+    t.n = nterm;
+    gga = false;
+    for (int k = 0; k < nterm; k++) {
+        const int id = ids[k];
+        QC_REQUIRE(id == XC_LDA_X || id == XC_LDA_C_PW || id == XC_LDA_C_PW_MOD || id == XC_GGA_X_PBE ||
+                       id == XC_GGA_C_PBE, "unknown functional id");
+        gga = gga || id >= 100;
+        t.id[k] = id;
+        t.coef[k] = coefs[k];
+    }
+    return 0;
+}
+
+extern "C" int b200qc_xc_unpol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n,
+                               int64_t ld, const double *rho, const double *grad, double *edens,
+                               double *vrho, double *vgrad, void *stream) {
+    XCTerms t;
+    bool gga;
+    if (int rc = xc_pack_terms(nterm, h_func_ids, h_coefs, t, gga)) return rc;
+    QC_REQUIRE(!gga || grad != nullptr, "GGA functional needs the density gradient");
+    if (n == 0) return 0;
+    xc_unpol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(t, n, ld, rho, grad, edens, vrho,
+                                                                               gga ? vgrad : nullptr);
+    QC_LAUNCHED(1);
+    if (!gga && vgrad) QC_CHECK(cudaMemsetAsync(vgrad, 0, sizeof(double) * 3 * ld, as_stream(stream)));
+    return 0;
+}
+
+extern "C" int b200qc_xc_pol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n,
+                             int64_t ld, const double *rho, const double *grad, double *edens,
+                             double *vrho, double *vgrad, void *stream) {
+    XCTerms t;
+    bool gga;
+    if (int rc = xc_pack_terms(nterm, h_func_ids, h_coefs, t, gga)) return rc;
+    QC_REQUIRE(!gga || grad != nullptr, "GGA functional needs the density gradient");
+    if (n == 0) return 0;
+    xc_pol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(t, n, ld, rho, gga ? grad : nullptr,
+                                                                             edens, vrho, gga ? vgrad : nullptr);
+    QC_LAUNCHED(1);
+    if (!gga && vgrad) QC_CHECK(cudaMemsetAsync(vgrad, 0, sizeof(double) * 6 * ld, as_stream(stream)));
+    return 0;
+}

@@ -1,0 +1,120 @@
+/*
+ * b200qc -- C ABI of the B200-native SCF Fock-build path.
+ *
+ * This is the drop-in boundary.  The reference (diffqc/dqc) reaches its native code through
+ * ctypes handles to `dqclibs` (dqc/hamilton/intor/utils.py:15-19) and `pylibxc`
+ * (dqc/xc/libxc.py:25-26); every entry point below names the reference call site / native symbol
+ * it replaces.  Conventions (same ownership rule as dqclibs):
+ *   - the caller allocates every output; the library only writes;
+ *   - every data pointer is a DEVICE pointer (fp64 / int32) unless the name starts with `h_`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
+ *     with respect to the host unless stated otherwise;
+ *   - return value 0 = success, non-zero = failure, message via b200qc_last_error();
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ * Basis data travel in libcint's (atm, bas, env) layout exactly as the reference packs them
+ * (dqc/hamilton/intor/lcintwrap.py:36-117).
+ */
+#ifndef B200QC_H
+#define B200QC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200qc_basis b200qc_basis; /* device-resident (atm, bas, env, ao_loc) */
+
+const char *b200qc_last_error(void);
+int b200qc_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t b200qc_launch_count(void);
+
+/* ---- basis / tables ------------------------------------------------------------------ */
+/* Replaces the (atm, bas, env) argument pack every dqclibs call receives
+ * (molintor.py:629-638, gtoeval.py:219-233) and CINTcgto_spheric (lcintwrap.py:376-383):
+ * the triplet is uploaded once and referred to by handle.  h_* are host pointers. */
+int b200qc_basis_upload(const int *h_atm, int natm, const int *h_bas, int nbas, const double *h_env,
+                        int nenv, const int *h_ao_loc, b200qc_basis **out);
+int b200qc_basis_free(b200qc_basis *basis);
+/* Rys-quadrature interpolation table (dqc_b200/data/rys_table.npz, tools/make_rys_table.py);
+ * plays the role of libcint's built-in root tables / the `<intor>_optimizer` pair data
+ * (molintor.py:695-708).  h_coef[n-1] points to (nint, 2n, deg+1) doubles, h_herm[n-1] to (2, n). */
+int b200qc_rys_upload(int nmax, double h, int deg, double xmax, const double *const *h_coef,
+                      const double *const *h_herm);
+
+/* ---- K1: AO values on the grid -- replaces GTOval_sph / GTOval_ip_sph ------------------ */
+/* gtoeval.py:196-239 (eval_gto / eval_gradgto with to_transpose=True).
+ * coords: (ngrid, 3).  ao: [ncomp][ngrid_ld][ao_ld] with ncomp = 1 (deriv 0: values) or
+ * 4 (deriv 1: value, d/dx, d/dy, d/dz); rows >= ngrid and columns >= nao are left untouched. */
+int b200qc_eval_gto(const b200qc_basis *basis, int sh0, int sh1, int deriv, const double *coords,
+                    int64_t ngrid, double *ao, int64_t ngrid_ld, int64_t ao_ld, void *stream);
+
+/* ---- grid weights -- replaces the torch loop of multiatoms_grid.py:173-273 ------------- */
+/* owner[g] = atom the point belongs to; aij = (natom, natom) hetero-nuclear shifts or NULL;
+ * w[g] = P_owner / sum_k P_k. */
+int b200qc_becke_weights(const double *xyz, const int *owner, int64_t ngrid, const double *atompos,
+                         int natom, const double *aij, double *w, void *stream);
+
+/* ---- K2: density on the grid -- replaces hcgto.py:371-443 (_dm2densinfo) --------------- */
+/* dm: (ao_ld, ao_ld) symmetric AO-basis density, zero padded.  rho: (ngrid_ld);
+ * grad: (3, ngrid_ld) or NULL (LDA).  ncomp of `ao` is 1 if grad == NULL else 4.
+ * ngrid_ld must be a multiple of 128 and ao_ld a multiple of 64 (zero padded). */
+int b200qc_rho(const double *ao, int64_t ngrid_ld, int64_t ao_ld, const double *dm, double *rho,
+               double *grad, void *stream);
+
+/* ---- K3: pointwise XC -- replaces pylibxc LibXCFunctional.compute ---------------------- */
+/* libxc_wrapper.py:380-413 with the pre/post-processing of libxc.py:124-242 fused in:
+ * input rho (n), grad (3, n) or NULL; outputs (each may be NULL):
+ *   edens = sum_k coef_k zk_k rho            (energy per unit volume)
+ *   vrho  = sum_k coef_k d e_k / d rho
+ *   vgrad = sum_k coef_k 2 (d e_k/d sigma) grad   (3, n)
+ * func ids: 1 lda_x, 2 lda_c_pw, 3 lda_c_pw_mod, 101 gga_x_pbe, 102 gga_c_pbe. */
+int b200qc_xc_unpol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n, int64_t ld,
+                    const double *rho, const double *grad, double *edens, double *vrho, double *vgrad,
+                    void *stream);
+/* spin-polarised variant: rho (2, n) = up, down; grad (2, 3, n); vrho (2, n); vgrad (2, 3, n) */
+int b200qc_xc_pol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n, int64_t ld,
+                  const double *rho, const double *grad, double *edens, double *vrho, double *vgrad,
+                  void *stream);
+
+/* ---- K4: Vxc integration -- replaces hcgto.py:445-495 (_get_vxc_from_potinfo) ---------- */
+/* mat (ao_ld, ao_ld) = sum_g w_g phi_g^T (vrho_g phi_g + sum_d 2 vgrad_{d,g} d_d phi_g)
+ * (no symmetrisation, no basis change: the caller does X^T M X and (M + M^T)/2 like the
+ * reference).  work: scratch of b200qc_vxc_worksize() doubles. */
+int64_t b200qc_vxc_worksize(int64_t ngrid_ld, int64_t ao_ld);
+int b200qc_vxc_mat(const double *ao, int64_t ngrid_ld, int64_t ao_ld, const double *weights,
+                   const double *vrho, const double *vgrad, double *mat, double *work, void *stream);
+
+/* ---- one- and two-electron integrals (Rys quadrature) ---------------------------------- */
+/* kind: 0 int1e_ovlp, 1 int1e_kin, 2 int1e_nuc, 3 int1e_rinv (origin rinv_orig[3], host).
+ * Replaces GTOint2c (molintor.py:624-644).  out: (nao_i, nao_j) row-major for shells
+ * [ish0, ish1) x [jsh0, jsh1) -- i.e. already in the orientation the reference has after swapaxes. */
+int b200qc_int1e(const b200qc_basis *basis, int kind, const int *h_shls_slice /*4*/,
+                 const double *h_rinv_orig, double *out, void *stream);
+/* (P|Q): replaces GTOint2c with int2c2e_sph (molintor.py:36-54). out (nP, nQ). */
+int b200qc_int2c2e(const b200qc_basis *basis, const int *h_shls_slice /*4*/, double *out, void *stream);
+/* (ij|P): replaces GTOnr3c_drv + GTOnr3c_fill_s1 with int3c2e_sph (molintor.py:646-665).
+ * out (nao_i, nao_j, naux) row-major. */
+int b200qc_int3c2e(const b200qc_basis *basis, const int *h_shls_slice /*6*/, double *out, void *stream);
+/* (ij|kl) dense: replaces GTOnr2e_fill_drv + fills4 (molintor.py:667-688, symmetry.py:55-64).
+ * out (ni, nj, nk, nl) row-major.  Meant for small systems / tests. */
+int b200qc_int2e(const b200qc_basis *basis, const int *h_shls_slice /*8*/, double *out, void *stream);
+/* K8: direct J/K -- replaces the dense-ERI einsums of hcgto.py:204-241 without storing (ij|kl).
+ * dm: (nset, nao, nao) AO basis; vj/vk: (nset, nao, nao) or NULL;
+ *   vj[kl] = sum_ij dm[ij] (ij|kl),  vk[jk] = sum_il dm[il] (ij|kl)   (no -1/2 factor). */
+int b200qc_jk_direct(const b200qc_basis *basis, int sh0, int sh1, const double *dm, int nset,
+                     double *vj, double *vk, void *stream);
+
+/* ---- K9: density-fitted J -- replaces dfmol.py:60-79 ----------------------------------- */
+/* j3c: (npair, naux) packed lower-triangular AO pairs (i >= j, pair = i(i+1)/2 + j);
+ * dm: (nao, nao) AO basis; inv_j2c: (naux, naux); vj: (nao, nao) = sum_P (ij|P) c_P with
+ * c = inv_j2c . (sum_ij dm_ij (ij|P)).  work: 2*naux + nblock*naux doubles (see worksize). */
+int64_t b200qc_dfj_worksize(int64_t nao, int64_t naux);
+int b200qc_dfj(const double *j3c_packed, int64_t nao, int64_t naux, const double *inv_j2c,
+               const double *dm, double *vj, double *work, void *stream);
+/* pack (nao, nao, naux) -> (npair, naux) */
+int b200qc_pack_tril(const double *full, int64_t nao, int64_t naux, double *packed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

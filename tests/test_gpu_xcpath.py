@@ -1,0 +1,207 @@
+"""GPU parity of the XC grid path (K1 AO eval, Becke weights, K2 density, K3 functional, K4 Vxc)
+against the CPU oracle, all through the C-ABI (dqc_b200._lib -> libb200qc.so)."""
+import numpy as np
+import pytest
+import torch
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad_dm(dm, ld, dev):
+    out = torch.zeros(ld, ld, dtype=torch.float64, device=dev)
+    out[:dm.shape[0], :dm.shape[1]] = dm.to(dev)
+    return out
+
+
+@pytest.mark.parametrize("which", ["h2o-def2svp", "highl", "c-etbjfit"])
+@pytest.mark.parametrize("ngrid", [1, 77, 1000])
+def test_ao_eval_matches_oracle(cuda, which, ngrid):
+    from dqc_b200 import _lib
+    from oracle import cint
+    if which == "h2o-def2svp":
+        w, _ = util.make_wrapper(*util.H2O, "def2-svp")
+    elif which == "highl":
+        w, _ = util.highl_wrapper()
+    else:
+        w, _ = util.make_wrapper([6], [[0.1, 0.2, -0.3]], "etb-jfit")
+    atm, bas, env = w.atm_bas_env
+    pts = util.random_points(ngrid, seed=ngrid)
+    db = w.device_basis(cuda)
+    for deriv in (0, 1):
+        ao = _lib.eval_gto(db, 0, len(w), torch.tensor(pts, device=cuda), deriv)
+        torch.cuda.synchronize()
+        nao = w.nao()
+        ref0 = cint.eval_gto(atm, bas, env, pts, 0)
+        got = ao[:, :ngrid, :nao].cpu().numpy()
+        assert np.abs(got[0] - ref0).max() < 1e-12
+        if deriv:
+            ref1 = cint.eval_gto(atm, bas, env, pts, 1)
+            assert np.abs(got[1:] - ref1).max() < 1e-11
+        # padding stays zero
+        assert float(ao[:, ngrid:, :].abs().max()) == 0.0 if ao.shape[1] > ngrid else True
+        assert float(ao[:, :, nao:].abs().max()) == 0.0 if ao.shape[2] > nao else True
+
+
+@pytest.mark.parametrize("adjust,radii", [("becke", True), ("treutler", True), ("becke", False)])
+def test_becke_weights_match_oracle(cuda, adjust, radii):
+    from dqc_b200 import _lib
+    from dqc_b200.utils.periodictable import atom_expected_radii
+    from oracle import becke_ref
+    zs, pos = util.CH4ISH
+    pos = np.array(pos)
+    rng = np.random.RandomState(3)
+    owner = np.repeat(np.arange(len(zs)), 700)
+    # points scattered around their owner, some far away (so that the 0.74 cut-off triggers)
+    xyz = pos[owner] + rng.normal(size=(len(owner), 3)) * rng.choice([0.3, 1.5, 4.0], size=(len(owner), 1))
+    rad = np.array([atom_expected_radii[z] for z in zs]) if radii else None
+    ref = becke_ref.becke_weights(xyz, owner, pos, rad, adjust)
+    aij = None
+    if radii:
+        r = torch.tensor(rad if adjust == "becke" else rad ** 0.5, device=cuda)
+        u = (r - r.unsqueeze(1)) / (r + r.unsqueeze(1))
+        aij = torch.clamp(u / (u * u - 1), min=-0.45, max=0.45).contiguous()
+    got = _lib.becke_weights(torch.tensor(xyz, device=cuda), torch.tensor(owner, device=cuda),
+                             torch.tensor(pos, device=cuda), aij).cpu().numpy()
+    assert (ref == 0).sum() > 0  # the cut-off is exercised
+    assert np.abs(got - ref).max() < 1e-13
+
+
+XCS = ["lda_x", "lda_c_pw", "lda_c_pw_mod", "gga_x_pbe", "gga_c_pbe", "lda_x + lda_c_pw",
+       "gga_x_pbe + gga_c_pbe", "0.7*gga_x_pbe + 0.3*lda_x + gga_c_pbe"]
+
+
+@pytest.mark.parametrize("xcstr", XCS)
+def test_xc_unpol_matches_autograd_oracle(cuda, xcstr):
+    from dqc_b200 import _lib
+    from oracle import xc_ref
+    g = torch.Generator().manual_seed(1)
+    n = 4097
+    rho = 10 ** (torch.rand(n, dtype=torch.float64, generator=g) * 9 - 7)   # 1e-7 .. 1e2
+    grad = torch.randn(3, n, dtype=torch.float64, generator=g) * rho ** (4.0 / 3) * 2
+    fam = xc_ref.family(xcstr)
+    e_ref, vr_ref, vg_ref = xc_ref.eval_unpol(xcstr, rho, grad if fam == 2 else None)
+    e, vr, vg = _lib.xc_unpol(xc_ref.parse(xcstr), rho.to(cuda), grad.to(cuda).contiguous() if fam == 2 else None)
+    rel = lambda a, b: float(((a.cpu() - b).abs() / (b.abs() + 1e-12 * b.abs().max())).max())
+    assert rel(e, e_ref) < 1e-11
+    assert rel(vr, vr_ref) < 1e-10
+    if fam == 2:
+        assert float((vg.cpu() - vg_ref).abs().max() / vg_ref.abs().max()) < 1e-11
+        assert rel(vg, vg_ref) < 1e-8
+
+
+@pytest.mark.parametrize("xcstr", XCS)
+def test_xc_pol_matches_autograd_oracle(cuda, xcstr):
+    from dqc_b200 import _lib
+    from oracle import xc_ref
+    g = torch.Generator().manual_seed(2)
+    n = 3001
+    rho = 10 ** (torch.rand(2, n, dtype=torch.float64, generator=g) * 8 - 6)
+    grad = torch.randn(2, 3, n, dtype=torch.float64, generator=g) * (rho ** (4.0 / 3)).unsqueeze(1) * 2
+    fam = xc_ref.family(xcstr)
+    args = (rho[0], rho[1]) + ((grad[0], grad[1]) if fam == 2 else ())
+    e_ref, (vu, vd), vg_ref = xc_ref.eval_pol(xcstr, *args)
+    e, vr, vg = _lib.xc_pol(xc_ref.parse(xcstr), rho.to(cuda).contiguous(),
+                            grad.to(cuda).contiguous() if fam == 2 else None)
+    rel = lambda a, b: float(((a.cpu() - b).abs() / (b.abs() + 1e-12 * b.abs().max())).max())
+    assert rel(e, e_ref) < 1e-11
+    assert rel(vr[0], vu) < 1e-9 and rel(vr[1], vd) < 1e-9
+    if fam == 2:
+        for s in range(2):
+            assert float((vg[s].cpu() - vg_ref[s]).abs().max() / vg_ref[s].abs().max()) < 1e-10
+
+
+def test_xc_pol_reduces_to_unpol(cuda):
+    from dqc_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    n = 999
+    rho = 10 ** (torch.rand(n, dtype=torch.float64, generator=g) * 6 - 4)
+    grad = torch.randn(3, n, dtype=torch.float64, generator=g) * rho
+    terms = [(1.0, "gga_x_pbe"), (1.0, "gga_c_pbe"), (0.5, "lda_c_pw")]
+    e, vr, vg = _lib.xc_unpol(terms, rho.to(cuda), grad.to(cuda))
+    rp = torch.stack([rho / 2, rho / 2]).to(cuda)
+    gp = torch.stack([grad / 2, grad / 2]).to(cuda)
+    e2, vr2, vg2 = _lib.xc_pol(terms, rp, gp)
+    assert torch.allclose(e, e2, rtol=1e-12, atol=0)
+    assert torch.allclose(vr, vr2[0], rtol=1e-11, atol=1e-300)
+    assert torch.allclose(vg, vg2[0], rtol=1e-10, atol=1e-14)
+
+
+@pytest.mark.parametrize("which,xcstr", [("h2o-def2svp", "lda_x + lda_c_pw"), ("h2o-def2svp", "gga_x_pbe + gga_c_pbe"),
+                                         ("highl", "gga_x_pbe")])
+def test_rho_and_vxc_match_oracle(cuda, which, xcstr):
+    """K2 + K3 + K4 against oracle/fock_ref.py on a few thousand points (identity orthogonaliser so
+    that the kernels themselves are compared; the basis change is plain torch on both sides)."""
+    from dqc_b200 import _lib
+    from oracle import fock_ref, xc_ref
+    w, _ = util.make_wrapper(*util.H2O, "def2-svp") if which == "h2o-def2svp" else util.highl_wrapper()
+    ngrid = 3000
+    pts = util.random_points(ngrid, seed=11, span=2.5)
+    wts = np.random.RandomState(5).uniform(0.0, 0.3, ngrid)
+    h = fock_ref.RefHamilton(w, orthozer=False)
+    h.setup_grid(pts, wts, xcstr)
+    nao = w.nao()
+    dm = util.seeded_dm(nao, max(1, nao // 4), seed=3)
+    rho_ref, grad_ref = h.dm2densinfo(dm)
+    fam = xc_ref.family(xcstr)
+
+    db = w.device_basis(cuda)
+    ao = _lib.eval_gto(db, 0, len(w), torch.tensor(pts, device=cuda), 1 if fam == 2 else 0)
+    ld = ao.shape[2]
+    rho, grad = _lib.rho(ao, _pad_dm(dm, ld, cuda), fam == 2)
+    assert float((rho[:ngrid].cpu() - rho_ref).abs().max()) < 1e-11 * max(1.0, float(rho_ref.abs().max()))
+    if fam == 2:
+        assert float((grad[:, :ngrid].cpu() - grad_ref).abs().max()) < 1e-10 * max(1.0, float(grad_ref.abs().max()))
+    # potentials from the oracle densities (so K4 is tested in isolation), then the full chain
+    _, vrho_ref, vgrad_ref = xc_ref.eval_unpol(xcstr, rho_ref, grad_ref)
+    mat_ref = h.vxc_from_potinfo(vrho_ref, vgrad_ref)   # includes (M + M^T)/2
+    ngl = ao.shape[1]
+    wpad = torch.zeros(ngl, dtype=torch.float64, device=cuda)
+    wpad[:ngrid] = torch.tensor(wts, device=cuda)
+    vr = torch.zeros(ngl, dtype=torch.float64, device=cuda)
+    vr[:ngrid] = vrho_ref.to(cuda)
+    vg = None
+    if fam == 2:
+        vg = torch.zeros(3, ngl, dtype=torch.float64, device=cuda)
+        vg[:, :ngrid] = vgrad_ref.to(cuda)
+    mat = _lib.vxc_mat(ao, wpad, vr, vg)[:nao, :nao]
+    mat = 0.5 * (mat + mat.T)
+    assert float((mat.cpu() - mat_ref).abs().max()) < 1e-10
+    # full chain on the device
+    e, vr2, vg2 = _lib.xc_unpol(xc_ref.parse(xcstr), rho, grad)
+    mat2 = _lib.vxc_mat(ao, wpad, vr2, vg2)[:nao, :nao]
+    mat2 = 0.5 * (mat2 + mat2.T)
+    assert float((mat2.cpu() - mat_ref).abs().max()) < 1e-9
+    exc = float((e * wpad).sum())
+    exc_ref = float((xc_ref.eval_unpol(xcstr, rho_ref, grad_ref)[0] * torch.tensor(wts)).sum())
+    assert abs(exc - exc_ref) < 1e-10
+
+
+def test_gemm_engine_large_random(cuda):
+    """K2/K4 at a size with many tiles and odd padding, against torch fp64 matmul on the device
+    (plain library GEMM used only as a checker here)."""
+    from dqc_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(0)
+    ngl, ld, nao = 128 * 37, 64 * 5, 300
+    ao = torch.zeros(4, ngl, ld, dtype=torch.float64)
+    ao[:, :, :nao] = torch.randn(4, ngl, nao, dtype=torch.float64, generator=g)
+    ao = ao.to(cuda)
+    dm = torch.zeros(ld, ld, dtype=torch.float64)
+    d0 = torch.randn(nao, nao, dtype=torch.float64, generator=g)
+    dm[:nao, :nao] = d0 + d0.T
+    dm = dm.to(cuda)
+    rho, grad = _lib.rho(ao, dm, True)
+    x = ao[0] @ dm
+    assert torch.allclose(rho, (x * ao[0]).sum(-1), rtol=1e-12, atol=1e-9)
+    for d in range(3):
+        assert torch.allclose(grad[d], 2 * (x * ao[d + 1]).sum(-1), rtol=1e-12, atol=1e-9)
+    w = torch.rand(ngl, dtype=torch.float64, device=cuda)
+    vr = torch.randn(ngl, dtype=torch.float64, device=cuda)
+    vg = torch.randn(3, ngl, dtype=torch.float64, device=cuda)
+    mat = _lib.vxc_mat(ao, w, vr, vg)
+    vb = vr[:, None] * ao[0] + 2 * (vg[0][:, None] * ao[1] + vg[1][:, None] * ao[2] + vg[2][:, None] * ao[3])
+    ref = (ao[0] * w[:, None]).T @ vb
+    assert float((mat - ref).abs().max() / ref.abs().max()) < 1e-13
+    mat1 = _lib.vxc_mat(ao[:1].contiguous(), w, vr, None)
+    ref1 = (ao[0] * w[:, None]).T @ (vr[:, None] * ao[0])
+    assert float((mat1 - ref1).abs().max() / ref1.abs().max()) < 1e-13
