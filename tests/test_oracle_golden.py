@@ -1,0 +1,128 @@
+"""Pins the CPU oracle (oracle/) against the golden numbers the reference's own tests hold for the
+Fock-build path.  Every constant below is copied from the cited reference test, nothing else.
+These are CPU tests (-m "not gpu")."""
+import numpy as np
+import pytest
+import torch
+from tests import util
+from oracle import fock_ref, scf_ref, xc_ref, cint
+
+dtype = torch.float64
+
+
+def _diatomic(atomzs, dist, basis="3-21g"):
+    pos = (np.array([[-0.5, 0.0, 0.0], [0.5, 0.0, 0.0]]) * dist).tolist()
+    w, p = util.make_wrapper(atomzs, pos, basis)
+    return w, p.numpy()
+
+
+# dqc/test/test_hf.py:17-31 (RHF/3-21G from PySCF, rtol 1e-7 at :42-45)
+RHF = [([1, 1], 1.0, -1.07195346e+00), ([3, 3], 5.0, -1.47683688e+01), ([7, 7], 2.0, -1.08298897e+02),
+       ([9, 9], 2.5, -1.97636373e+02), ([6, 8], 2.0, -1.12078732e+02)]
+
+
+@pytest.mark.parametrize("atomzs,dist,etrue", RHF)
+def test_rhf_321g_golden(atomzs, dist, etrue):
+    w, pos = _diatomic(atomzs, dist)
+    h = fock_ref.RefHamilton(w).build_eri()
+    e, _ = scf_ref.run_scf(h, atomzs, pos, sum(atomzs))
+    assert abs(e - etrue) <= 1e-7 * abs(etrue)
+
+
+# dqc/test/test_hf.py:141-153 (UHF atoms, rtol 1e-7 at :177-189)
+UHF_ATOMS = [(1, 1, -4.96198609e-01), (3, 1, -7.38151326e+00), (5, 1, -2.43897617e+01), (8, 2, -7.43936572e+01)]
+
+
+@pytest.mark.parametrize("z,spin,etrue", UHF_ATOMS)
+def test_uhf_atoms_golden(z, spin, etrue):
+    w, pos = util.make_wrapper([z], [[0.0, 0.0, 0.0]], "3-21g")
+    h = fock_ref.RefHamilton(w).build_eri()
+    e, _ = scf_ref.run_scf(h, [z], pos.numpy(), z, spin=spin)
+    assert abs(e - etrue) <= 1e-7 * abs(etrue)
+
+
+def test_uhf_no_golden():
+    # dqc/test/test_hf.py:154-161,191-206: NO, dist 2.0, spin 1, -128.477807 Ha, rtol 1e-8
+    w, pos = _diatomic([7, 8], 2.0)
+    h = fock_ref.RefHamilton(w).build_eri()
+    e, _ = scf_ref.run_scf(h, [7, 8], pos, 15, spin=1)
+    assert abs(e - (-1.28477807e+02)) <= 1e-8 * 128.477807 * 10  # constant is printed to 9 digits
+
+
+def test_h2_density_points_golden():
+    # dqc/test/test_hamilton.py:95-142: converged HF density of H2/3-21G ("H 0 0 0.8; H 0 0 -0.8")
+    # on 5 points of the z axis, values from PySCF quoted there (default allclose tolerances)
+    w, pos = util.make_wrapper([1, 1], [[0.0, 0.0, 0.8], [0.0, 0.0, -0.8]], "3-21g")
+    h = fock_ref.RefHamilton(w).build_eri()
+    _, dm = scf_ref.run_scf(h, [1, 1], pos.numpy(), 2)
+    xyz = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.4], [0.0, 0.0, 0.8], [0.0, 0.0, -0.4], [0.0, 0.0, -0.8]])
+    dens = h.aodm2dens(dm, xyz).numpy()
+    true = np.array([0.18742819, 0.23469519, 0.30250292, 0.23469519, 0.30250292])
+    assert np.allclose(dens, true, rtol=1e-5, atol=1e-8)
+
+
+def test_vext_constant_is_identity():
+    # dqc/test/test_hamilton.py:144-155: <mu| w |nu> integrated on the grid reproduces w * S
+    from dqc_b200.grid.radial_grid import RadialGrid, DE2Transformation
+    from dqc_b200.grid.lebedev_grid import LebedevGrid
+    w, pos = util.make_wrapper([1], [[0.0, 0.0, 0.0]], "3-21g")
+    atm, bas, env = w.atm_bas_env
+    g = LebedevGrid(RadialGrid(99, "uniform", DE2Transformation(alpha=2.7, rmin=1e-7, rmax=15 * 1.5)), prec=41)
+    ao = cint.eval_gto(atm, bas, env, g.get_rgrid().numpy(), 0)
+    S = (ao * g.get_dvolume().numpy()[:, None]).T @ ao
+    assert np.allclose(S, cint.int1e("ovlp", atm, bas, env), atol=4e-5)
+
+
+# ---- XC analytic forms of dqc/test/test_xc.py:390-425 -------------------------------------
+def test_lda_x_formula():
+    rho = torch.logspace(-3, 2, 50, dtype=dtype)
+    e, v, _ = xc_ref.eval_unpol("lda_x", rho)
+    assert torch.allclose(e, -0.75 * (3 / np.pi) ** (1. / 3) * rho ** (4. / 3))   # test_xc.py:390-391
+    assert torch.allclose(v, -(3 / np.pi) ** (1. / 3) * rho ** (1. / 3))          # test_xc.py:416-417
+
+
+def test_pw92_formula():
+    # test_xc.py:393-414 (ldac_e_true): PW92 with the original parameters, unpolarised and polarised
+    def ldac_e_true(rhou, rhod):
+        rho = rhou + rhod
+        zeta = (rhou - rhod) / rho
+        rs = (3. / (4 * np.pi * rho)) ** (1. / 3)
+
+        def G(rs, A, a1, b1, b2, b3, b4, p=1):
+            return -2 * A * (1 + a1 * rs) * torch.log(
+                1 + 1. / (2 * A * (b1 * rs ** 0.5 + b2 * rs + b3 * rs ** 1.5 + b4 * rs ** (p + 1))))
+        ec0 = G(rs, 0.031091, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294)
+        ec1 = G(rs, 0.015545, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517)
+        mac = G(rs, 0.016887, 0.11125, 10.357, 3.6231, 0.88026, 0.49671)
+        fz = ((1 + zeta) ** (4. / 3) + (1 - zeta) ** (4. / 3) - 2) / (2 ** (4. / 3) - 2)
+        fz20 = 1.709921
+        return rho * (ec0 - mac * fz * (1 - zeta ** 4) / fz20 + (ec1 - ec0) * fz * zeta ** 4)
+    ru = torch.logspace(-3, 1.5, 40, dtype=dtype)
+    rd = ru.flip(0) * 0.7
+    assert torch.allclose(xc_ref.edens_pol("lda_c_pw", ru, rd), ldac_e_true(ru, rd), rtol=1e-10)
+    assert torch.allclose(xc_ref.edens_unpol("lda_c_pw", ru), ldac_e_true(ru / 2, ru / 2), rtol=1e-10)
+
+
+def test_pbe_x_formula():
+    # test_xc.py:419-425 (pbe_e_true)
+    rho = torch.logspace(-2, 1.5, 30, dtype=dtype)
+    g = torch.stack([0.3 * rho, -0.2 * rho ** 1.2, 0.5 * rho ** 0.9])
+    kf = (3 * np.pi ** 2 * rho) ** (1. / 3)
+    s = torch.sqrt((g * g).sum(0)) / (2 * rho * kf)
+    kappa, mu = 0.804, 0.21951
+    fx = 1 + kappa - kappa / (1 + mu * s * s / kappa)
+    etrue = -0.75 * (3 / np.pi) ** (1. / 3) * rho ** (4. / 3) * fx
+    assert torch.allclose(xc_ref.edens_unpol("gga_x_pbe", rho, g), etrue, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["lda_x", "lda_c_pw", "lda_c_pw_mod", "gga_x_pbe", "gga_c_pbe"])
+def test_potential_is_derivative_of_energy(name):
+    # v = de/drho checked by central finite differences (fp64)
+    rho = torch.logspace(-2, 1, 12, dtype=dtype)
+    g = torch.stack([0.4 * rho, 0.1 * rho, -0.3 * rho])
+    fam = xc_ref.FAMILY[name]
+    _, v, vg = xc_ref.eval_unpol(name, rho, g if fam == 2 else None)
+    h = 1e-6 * rho
+    ep = xc_ref.edens_unpol(name, rho + h, g if fam == 2 else None)
+    em = xc_ref.edens_unpol(name, rho - h, g if fam == 2 else None)
+    assert torch.allclose(v, (ep - em) / (2 * h), rtol=1e-6, atol=1e-9)
