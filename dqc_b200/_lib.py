@@ -54,13 +54,25 @@ _SIGS = {
     "b200qc_int2c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int3c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_int3c2e_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                             ctypes.c_void_p]),
+    "b200qc_jkplan_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_jkplan_nquartets": (ctypes.c_int64, [ctypes.c_void_p]),
+    "b200qc_jkplan_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200qc_jkplan_free": (ctypes.c_int, [ctypes.c_void_p]),
     "b200qc_jk_direct": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_dfj_worksize": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int64]),
-    "b200qc_dfj": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+    "b200qc_dfj": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "b200qc_pack_tril": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
-                                        ctypes.c_void_p]),
+    "b200qc_dfj_pass1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_dfj_pass2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_pack_tril": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 
@@ -309,8 +321,55 @@ def int2e(basis: DeviceBasis, shls):
     return out
 
 
+def int3c2e_packed(basis: DeviceBasis, shls, ld: Optional[int] = None):
+    """(ij|P) for AO pairs i >= j: (npair, ld) with ld = naux rounded up to even, zero padded."""
+    lib = load()
+    ensure_rys_table()
+    sl = np.array(shls, dtype=np.int32)
+    nao, naux = basis.nao(sl[0], sl[1]), basis.nao(sl[4], sl[5])
+    ld = round_up(naux, 2) if ld is None else ld
+    out = torch.zeros((nao * (nao + 1) // 2, ld), dtype=torch.float64, device=basis.device)
+    _check(lib.b200qc_int3c2e_packed(basis.handle, _np(sl), _ptr(out), ld, _stream()), "int3c2e_packed")
+    return out
+
+
+class JKPlan(object):
+    """Schwarz-screened direct J/K plan of shells [sh0, sh1) (b200qc_jkplan_*)."""
+
+    def __init__(self, basis: DeviceBasis, sh0: int, sh1: int, thresh: float = 1e-13):
+        lib = load()
+        ensure_rys_table()
+        self.basis = basis  # keeps the device basis alive
+        self.nao = basis.nao(sh0, sh1)
+        h = ctypes.c_void_p(0)
+        with torch.cuda.device(basis.device):
+            _check(lib.b200qc_jkplan_create(basis.handle, sh0, sh1, float(thresh), ctypes.byref(h), _stream()),
+                   "jkplan_create")
+        self.handle = h
+        self.nquartets = int(lib.b200qc_jkplan_nquartets(h))
+
+    def run(self, dm: torch.Tensor, with_j=True, with_k=True, rank=0, world=1):
+        """dm (nset, nao, nao) symmetric -> vj, vk (nset, nao, nao); partial sums when world > 1."""
+        lib = load()
+        dm = dm.contiguous()
+        assert dm.ndim == 3 and dm.shape[1] == self.nao
+        vj = torch.empty_like(dm) if with_j else None
+        vk = torch.empty_like(dm) if with_k else None
+        _check(lib.b200qc_jkplan_run(self.handle, _ptr(dm), dm.shape[0], _ptr(vj), _ptr(vk), rank, world,
+                                     _stream()), "jkplan_run")
+        return vj, vk
+
+    def __del__(self):
+        try:
+            if self.handle:
+                load(False).b200qc_jkplan_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
 def jk_direct(basis: DeviceBasis, sh0, sh1, dm, with_j=True, with_k=True):
-    """dm (nset, nao, nao) AO basis -> vj, vk (nset, nao, nao) (either may be None)."""
+    """dm (nset, nao, nao) symmetric AO basis -> vj, vk (nset, nao, nao) (either may be None)."""
     lib = load()
     ensure_rys_table()
     dm = dm.contiguous()
@@ -321,19 +380,41 @@ def jk_direct(basis: DeviceBasis, sh0, sh1, dm, with_j=True, with_k=True):
     return vj, vk
 
 
-def pack_tril(full):
+def pack_tril(full, ld=None):
     lib = load()
     nao, _, naux = full.shape
-    out = torch.empty((nao * (nao + 1) // 2, naux), dtype=torch.float64, device=full.device)
-    _check(lib.b200qc_pack_tril(_ptr(full.contiguous()), nao, naux, _ptr(out), _stream()), "pack_tril")
+    ld = round_up(naux, 2) if ld is None else ld
+    out = torch.empty((nao * (nao + 1) // 2, ld), dtype=torch.float64, device=full.device)
+    _check(lib.b200qc_pack_tril(_ptr(full.contiguous()), nao, naux, ld, _ptr(out), _stream()), "pack_tril")
     return out
 
 
-def dfj(j3c_packed, nao, inv_j2c, dm):
+def dfj(j3c_packed, nao, naux, inv_j2c, dm):
+    """One-GPU density-fitted J: (nao, nao) from the packed (npair, ld) tensor."""
     lib = load()
-    naux = j3c_packed.shape[1]
-    work = _workspace(int(lib.b200qc_dfj_worksize(nao, naux)), dm.device)
+    ld = j3c_packed.shape[1]
+    work = _workspace(int(lib.b200qc_dfj_worksize(nao, ld)), dm.device)
     vj = torch.empty((nao, nao), dtype=torch.float64, device=dm.device)
-    _check(lib.b200qc_dfj(_ptr(j3c_packed), nao, naux, _ptr(inv_j2c.contiguous()), _ptr(dm.contiguous()), _ptr(vj),
-                          _ptr(work), _stream()), "dfj")
+    _check(lib.b200qc_dfj(_ptr(j3c_packed), nao, naux, ld, _ptr(inv_j2c.contiguous()), _ptr(dm.contiguous()),
+                          _ptr(vj), _ptr(work), _stream()), "dfj")
+    return vj
+
+
+def dfj_pass1(j3c_packed, nao, naux, dm):
+    lib = load()
+    ld = j3c_packed.shape[1]
+    work = _workspace(int(lib.b200qc_dfj_worksize(nao, ld)), dm.device)
+    temp = torch.empty(naux, dtype=torch.float64, device=dm.device)
+    _check(lib.b200qc_dfj_pass1(_ptr(j3c_packed), nao, naux, ld, _ptr(dm.contiguous()), _ptr(temp), _ptr(work),
+                                _stream()), "dfj_pass1")
+    return temp
+
+
+def dfj_pass2(j3c_packed, nao, naux, coef):
+    lib = load()
+    ld = j3c_packed.shape[1]
+    cpad = torch.zeros(ld, dtype=torch.float64, device=coef.device)
+    cpad[:naux] = coef
+    vj = torch.empty((nao, nao), dtype=torch.float64, device=coef.device)
+    _check(lib.b200qc_dfj_pass2(_ptr(j3c_packed), nao, naux, ld, _ptr(cpad), _ptr(vj), _stream()), "dfj_pass2")
     return vj

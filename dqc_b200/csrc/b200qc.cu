@@ -8,9 +8,7 @@
 #include "gemm_f64.cuh"
 #include "rho.cuh"
 #include "vxc.cuh"
-#ifdef B200QC_WITH_INTS
 #include "rys.cuh"
 #include "ints.cuh"
+#include "jk.cuh"
 #include "dfj.cuh"
-#endif
-#include "stubs_tmp.cuh"

@@ -98,21 +98,48 @@ int b200qc_int3c2e(const b200qc_basis *basis, const int *h_shls_slice /*6*/, dou
 /* (ij|kl) dense: replaces GTOnr2e_fill_drv + fills4 (molintor.py:667-688, symmetry.py:55-64).
  * out (ni, nj, nk, nl) row-major.  Meant for small systems / tests. */
 int b200qc_int2e(const b200qc_basis *basis, const int *h_shls_slice /*8*/, double *out, void *stream);
-/* K8: direct J/K -- replaces the dense-ERI einsums of hcgto.py:204-241 without storing (ij|kl).
- * dm: (nset, nao, nao) AO basis; vj/vk: (nset, nao, nao) or NULL;
- *   vj[kl] = sum_ij dm[ij] (ij|kl),  vk[jk] = sum_il dm[il] (ij|kl)   (no -1/2 factor). */
+/* Same integrals stored once per AO pair i >= j: out[(i(i+1)/2 + j) * ld + P] (ld >= naux; the
+ * caller zero-fills the padding).  This is the resident DF tensor of K9: half the bytes of the
+ * reference's (nao, nao, naux) j3c (dqc/df/dfmol.py:33-39).  i and j slices must be identical. */
+int b200qc_int3c2e_packed(const b200qc_basis *basis, const int *h_shls_slice /*6*/, double *out, int64_t ld,
+                          void *stream);
+
+/* ---- K8: direct J/K -- replaces the dense-ERI einsums of hcgto.py:204-241 ---------------- */
+/* without ever storing (ij|kl) (the reference holds nao^4 doubles, hcgto.py:129).
+ * dm: (nset, nao, nao) SYMMETRIC, AO basis of shells [sh0, sh1); vj / vk: (nset, nao, nao) or NULL;
+ *   vj[kl] = sum_ij dm[ij] (ij|kl),  vk[jk] = sum_il dm[il] (ij|kl)   (no -1/2 factor).
+ * A plan = Schwarz-sorted shell-pair lists + work-item tables, built once per geometry
+ * (plays the role of the `int2e_optimizer` pair cache, molintor.py:695-708).  Quartets with
+ * Q_ij Q_kl < thresh are skipped (the reference skips nothing: use thresh <= 1e-12 for parity).
+ * rank / world: this process digests work items rank, rank + world, ... and returns PARTIAL
+ * matrices (multi-GPU: all-reduce them); rank = 0, world = 1 for the complete result. */
+typedef struct b200qc_jkplan b200qc_jkplan;
+int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1, double thresh, b200qc_jkplan **out,
+                         void *stream);
+int64_t b200qc_jkplan_nquartets(const b200qc_jkplan *plan);
+int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, int nset, double *vj, double *vk, int rank,
+                      int world, void *stream);
+int b200qc_jkplan_free(b200qc_jkplan *plan);
+/* one-shot convenience: plan (thresh 1e-13) + run + free */
 int b200qc_jk_direct(const b200qc_basis *basis, int sh0, int sh1, const double *dm, int nset,
                      double *vj, double *vk, void *stream);
 
 /* ---- K9: density-fitted J -- replaces dfmol.py:60-79 ----------------------------------- */
-/* j3c: (npair, naux) packed lower-triangular AO pairs (i >= j, pair = i(i+1)/2 + j);
- * dm: (nao, nao) AO basis; inv_j2c: (naux, naux); vj: (nao, nao) = sum_P (ij|P) c_P with
- * c = inv_j2c . (sum_ij dm_ij (ij|P)).  work: 2*naux + nblock*naux doubles (see worksize). */
-int64_t b200qc_dfj_worksize(int64_t nao, int64_t naux);
-int b200qc_dfj(const double *j3c_packed, int64_t nao, int64_t naux, const double *inv_j2c,
+/* j3c: (npair, ld) packed AO pairs (b200qc_int3c2e_packed), ld even, padding zero;
+ * dm: (nao, nao) AO basis (need not be symmetric); inv_j2c: (naux, naux);
+ *   temp_P = sum_ij dm_ij (ij|P);  c = temp . inv_j2c;  vj_ij = sum_P (ij|P) c_P   (nao, nao).
+ * work: b200qc_dfj_worksize(nao, ld) doubles.  pass1 / pass2 are the two halves for the
+ * aux-sharded multi-GPU layout (each rank holds a column slice of j3c; temp is all-gathered,
+ * the partial vj all-reduced); coef must be zero beyond naux up to ld. */
+int64_t b200qc_dfj_worksize(int64_t nao, int64_t ld);
+int b200qc_dfj(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, const double *inv_j2c,
                const double *dm, double *vj, double *work, void *stream);
-/* pack (nao, nao, naux) -> (npair, naux) */
-int b200qc_pack_tril(const double *full, int64_t nao, int64_t naux, double *packed, void *stream);
+int b200qc_dfj_pass1(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, const double *dm,
+                     double *temp, double *work, void *stream);
+int b200qc_dfj_pass2(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, const double *coef,
+                     double *vj, void *stream);
+/* pack (nao, nao, naux) -> (npair, ld) */
+int b200qc_pack_tril(const double *full, int64_t nao, int64_t naux, int64_t ld, double *packed, void *stream);
 
 #ifdef __cplusplus
 }

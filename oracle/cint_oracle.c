@@ -334,6 +334,10 @@ void orc_int1e(int kind, double *out, const int *shls_slice, const int *ao_loc, 
  * Generic (AB|CD); a missing centre is a Shell with l=0, one primitive, exponent 0, coef 1 placed
  * on its partner's centre.  Result: cartesian block [nca][ncb][ncc][ncd]. */
 static const double ZERO_EX = 0.0, ONE_CO = 1.0;
+/* libcint applies the s/p solid-harmonic constants only to the shells that exist (int2c2e: two
+ * CINTcommon_fac_sp factors, int3c2e: three); quartet_sph() pushes the dummy s shells through
+ * the same c2s table, so that 1/sqrt(4 pi) is taken out again per dummy. */
+static const double UNDO_DUMMY_S = 1.0 / 0.282094791773878143;
 
 static void dummy_shell(Shell *s, const Shell *partner) {
     s->l = 0;
@@ -473,7 +477,8 @@ void orc_int2c2e(double *out, const int *shls_slice, const int *ao_loc, const in
             quartet_sph(&A, &B, &C, &D, sph);
             int i0 = ao_loc[ish] - ao_loc[i0s], j0 = ao_loc[jsh] - ao_loc[j0s];
             for (int i = 0; i < nsa; i++)
-                for (int j = 0; j < nsc; j++) out[(size_t)(i0 + i) * nj + j0 + j] = sph[i * nsc + j];
+                for (int j = 0; j < nsc; j++)
+                    out[(size_t)(i0 + i) * nj + j0 + j] = sph[i * nsc + j] * UNDO_DUMMY_S * UNDO_DUMMY_S;
             free(sph);
         }
 }
@@ -505,7 +510,8 @@ void orc_int3c2e(double *out, const int *shls_slice, const int *ao_loc, const in
                 for (int i = 0; i < nsa; i++)
                     for (int j = 0; j < nsb; j++)
                         for (int k = 0; k < nsc; k++)
-                            out[((size_t)(i0 + i) * nj + j0 + j) * nk + k0 + k] = sph[(i * nsb + j) * nsc + k];
+                            out[((size_t)(i0 + i) * nj + j0 + j) * nk + k0 + k] =
+                                sph[(i * nsb + j) * nsc + k] * UNDO_DUMMY_S;
                 free(sph);
             }
         }

@@ -1,0 +1,195 @@
+"""GPU parity of the Rys integral engine (int1e / int2c2e / int3c2e / int2e), the direct J/K
+digestion and the density-fitted J against the CPU oracle (McMurchie-Davidson, a different
+algorithm), all through the C-ABI.  Tolerance 1e-11 abs on integrals."""
+import numpy as np
+import pytest
+import torch
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _wrapper(which):
+    if which == "h2o-def2svp":
+        return util.make_wrapper(*util.H2O, "def2-svp")[0]
+    if which == "highl":
+        return util.highl_wrapper()[0]
+    if which == "ch4ish-321g":
+        return util.make_wrapper(*util.CH4ISH, "3-21g")[0]
+    raise KeyError(which)
+
+
+@pytest.mark.parametrize("which", ["h2o-def2svp", "highl", "ch4ish-321g"])
+@pytest.mark.parametrize("kind", ["ovlp", "kin", "nuc"])
+def test_int1e_matches_oracle(cuda, which, kind):
+    from dqc_b200 import _lib
+    from oracle import cint
+    w = _wrapper(which)
+    atm, bas, env = w.atm_bas_env
+    nb = len(w)
+    ref = cint.int1e(kind, atm, bas, env)
+    got = _lib.int1e(w.device_basis(cuda), kind, (0, nb, 0, nb)).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+    # sub-blocks come out in the right place (dqc/test/test_libcint.py:145-199 subset consistency)
+    if nb > 3:
+        sub = _lib.int1e(w.device_basis(cuda), kind, (1, nb - 1, 2, nb)).cpu().numpy()
+        loc = w.full_shell_to_aoloc
+        assert np.abs(sub - ref[loc[1]:loc[nb - 1], loc[2]:loc[nb]]).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def test_int1e_rinv_matches_oracle(cuda):
+    from dqc_b200 import _lib
+    from oracle import cint
+    w = _wrapper("h2o-def2svp")
+    atm, bas, env = w.atm_bas_env
+    nb = len(w)
+    orig = np.array([0.3, -0.4, 0.5])
+    env2 = env.copy()
+    env2[4:7] = orig
+    ref = cint.int1e("rinv", atm, bas, env2)
+    got = _lib.int1e(w.device_basis(cuda), "rinv", (0, nb, 0, nb), orig).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-11
+
+
+def test_overlap_diagonal_is_one(cuda):
+    from dqc_b200 import _lib
+    w = _wrapper("highl")
+    nb = len(w)
+    s = _lib.int1e(w.device_basis(cuda), "ovlp", (0, nb, 0, nb))
+    assert torch.allclose(torch.diagonal(s), torch.ones(w.nao(), dtype=torch.float64, device=cuda), atol=1e-12)
+
+
+@pytest.mark.parametrize("which", ["c-etbjfit", "highl"])
+def test_int2c2e_matches_oracle(cuda, which):
+    from dqc_b200 import _lib
+    from oracle import cint
+    w = util.make_wrapper([6, 1], [[0.1, 0.2, -0.3], [1.2, -0.8, 0.9]], "etb-jfit")[0] if which == "c-etbjfit" \
+        else _wrapper("highl")
+    atm, bas, env = w.atm_bas_env
+    nb = len(w)
+    ref = cint.int2c2e(atm, bas, env)
+    got = _lib.int2c2e(w.device_basis(cuda), (0, nb, 0, nb)).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def _df_wrappers(basis="def2-svp"):
+    from dqc_b200.hamilton.intor.lcintwrap import LibcintWrapper
+    w = util.make_wrapper(*util.H2O, basis)[0]
+    aux = util.make_wrapper(*util.H2O, "etb-jfit")[0]
+    return LibcintWrapper.concatenate(w, aux)
+
+
+def test_int3c2e_matches_oracle_dense_and_packed(cuda):
+    from dqc_b200 import _lib
+    from oracle import cint
+    bw, aw = _df_wrappers()
+    atm, bas, env = aw.atm_bas_env
+    b0, b1 = bw.shell_idxs
+    a0, a1 = aw.shell_idxs
+    sl = (b0, b1, b0, b1, a0, a1)
+    ref = cint.int3c2e(atm, bas, env, sl)
+    db = aw.device_basis(cuda)
+    got = _lib.int3c2e(db, sl).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+    packed = _lib.int3c2e_packed(db, sl)
+    nao, naux = ref.shape[0], ref.shape[2]
+    ii, jj = np.tril_indices(nao)
+    assert np.abs(packed[:, :naux].cpu().numpy() - ref[ii, jj]).max() < 1e-11 * max(1.0, np.abs(ref).max())
+    assert float(packed[:, naux:].abs().max()) == 0.0 if packed.shape[1] > naux else True
+    # pack_tril of the dense tensor gives the same thing
+    p2 = _lib.pack_tril(torch.tensor(ref, device=cuda))
+    assert torch.allclose(p2, packed, atol=1e-11)
+
+
+@pytest.mark.parametrize("which", ["h2o-def2svp", "ch4ish-321g"])
+def test_int2e_matches_oracle(cuda, which):
+    from dqc_b200 import _lib
+    from oracle import cint
+    w = _wrapper(which)
+    atm, bas, env = w.atm_bas_env
+    nb = len(w)
+    ref = cint.int2e(atm, bas, env)
+    got = _lib.int2e(w.device_basis(cuda), (0, nb) * 4).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def test_int2e_high_l_subset(cuda):
+    """(ij|kl) with f and g functions on a shell subset (4 roots and more)."""
+    from dqc_b200 import _lib
+    from oracle import cint
+    w = _wrapper("highl")
+    atm, bas, env = w.atm_bas_env
+    sl = (2, 4, 0, 2, 7, 8, 5, 6)   # (d f | s p | d' | s')
+    ref = cint.int2e(atm, bas, env, sl)
+    got = _lib.int2e(w.device_basis(cuda), sl).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("which,nset", [("h2o-def2svp", 1), ("ch4ish-321g", 2)])
+def test_jk_direct_matches_dense_contraction(cuda, which, nset):
+    """K8 against the reference's dense einsums (hcgto.py:209,234) on oracle integrals."""
+    from dqc_b200 import _lib
+    from oracle import cint
+    w = _wrapper(which)
+    atm, bas, env = w.atm_bas_env
+    nb, nao = len(w), w.nao()
+    eri = torch.as_tensor(cint.int2e(atm, bas, env))
+    dms = torch.stack([util.seeded_dm(nao, max(1, nao // 3), seed=s) for s in range(nset)])
+    jref = torch.einsum("sij,ijkl->skl", dms, eri)
+    kref = torch.einsum("sil,ijkl->sjk", dms, eri)
+    vj, vk = _lib.jk_direct(w.device_basis(cuda), 0, nb, dms.to(cuda))
+    assert float((vj.cpu() - jref).abs().max()) < 1e-10
+    assert float((vk.cpu() - kref).abs().max()) < 1e-10
+    # plan API with two "ranks": partial results add up
+    plan = _lib.JKPlan(w.device_basis(cuda), 0, nb, 1e-14)
+    assert plan.nquartets > 0
+    j0, k0 = plan.run(dms.to(cuda), rank=0, world=2)
+    j1, k1 = plan.run(dms.to(cuda), rank=1, world=2)
+    assert float((j0 + j1 - jref.to(cuda)).abs().max()) < 1e-10
+    assert float((k0 + k1 - kref.to(cuda)).abs().max()) < 1e-10
+
+
+def test_dfj_matches_oracle(cuda):
+    """K9 against the reference's DF-J ops (dfmol.py:66-76) on oracle integrals."""
+    from dqc_b200 import _lib
+    from oracle import cint
+    bw, aw = _df_wrappers()
+    atm, bas, env = aw.atm_bas_env
+    b0, b1 = bw.shell_idxs
+    a0, a1 = aw.shell_idxs
+    j3c = torch.as_tensor(cint.int3c2e(atm, bas, env, (b0, b1, b0, b1, a0, a1)))
+    j2c = torch.as_tensor(cint.int2c2e(atm, bas, env, (a0, a1, a0, a1)))
+    inv = torch.inverse(j2c)
+    nao, naux = j3c.shape[0], j3c.shape[2]
+    g = torch.Generator().manual_seed(3)
+    dm = torch.randn(nao, nao, dtype=torch.float64, generator=g)   # deliberately not symmetric
+    temp = torch.einsum("ij,ijl->l", dm, j3c)
+    coef = torch.einsum("l,lk->k", temp, inv)
+    jref = torch.einsum("k,ijk->ij", coef, j3c)
+    db = aw.device_basis(cuda)
+    packed = _lib.int3c2e_packed(db, (b0, b1, b0, b1, a0, a1))
+    vj = _lib.dfj(packed, nao, naux, inv.to(cuda), dm.to(cuda))
+    scale = float(jref.abs().max())
+    assert float((vj.cpu() - jref).abs().max()) < 1e-10 * scale
+    t1 = _lib.dfj_pass1(packed, nao, naux, dm.to(cuda))
+    assert float((t1.cpu() - temp).abs().max()) < 1e-10 * float(temp.abs().max())
+    vj2 = _lib.dfj_pass2(packed, nao, naux, coef.to(cuda))
+    assert float((vj2.cpu() - jref).abs().max()) < 1e-10 * scale
+
+
+def test_dfj_large_random(cuda):
+    """K9 at a size with many row slabs / column blocks and an odd naux, against torch on the device."""
+    from dqc_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    nao, naux = 150, 4099
+    full = torch.randn(nao, nao, naux, dtype=torch.float64, generator=g)
+    full = (full + full.transpose(0, 1)).to(cuda)
+    inv = torch.randn(naux, naux, dtype=torch.float64, generator=g).to(cuda) / naux
+    dm = torch.randn(nao, nao, dtype=torch.float64, generator=g).to(cuda)
+    packed = _lib.pack_tril(full)
+    assert packed.shape[1] == 4100
+    vj = _lib.dfj(packed, nao, naux, inv, dm)
+    temp = torch.einsum("ij,ijl->l", dm, full)
+    ref = torch.einsum("k,ijk->ij", temp @ inv, full)
+    assert float((vj - ref).abs().max() / ref.abs().max()) < 1e-12
