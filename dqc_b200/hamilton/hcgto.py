@@ -1,0 +1,385 @@
+"""Molecular CGTO Hamiltonian whose Fock-build path runs on a B200.
+
+Drop-in for the reference's ``HamiltonCGTO`` (dqc/hamilton/hcgto.py:19-558): same constructor
+arguments, same ``build`` / ``setup_grid`` / ``get_*`` members, operators returned as Hermitian
+LinearOperators in the orthogonalised basis X = U s^-1/2, explicitly symmetrised.  What differs is
+where the numbers come from:
+
+  reference (CPU)                                     here (sm_100a kernels through libb200qc.so)
+  -------------------------------------------------   -------------------------------------------------
+  S, T, V from libcint, :107-114                      Rys / Obara-Saika kernel  b200qc_int1e
+  dense (ij|kl) nao^4 + convert4, :129-132            never stored: Schwarz-screened direct J/K plan
+  J, K einsums over nao^4, :204-241                   b200qc_jkplan_run (quartets digested on the fly)
+  DF: dfmol.py                                        dqc_b200/df/dfmol.py (packed (ij|P), two GEMV passes)
+  AO / grad AO on the grid, :168-186                  b200qc_eval_gto into one padded resident buffer
+  _dm2densinfo chunk loop, :371-443                   b200qc_rho (fp64 tensor-pipe tiles, fused row dots)
+  libxc, dqc/xc/libxc.py                              b200qc_xc_unpol / _pol
+  _get_vxc_from_potinfo chunk loop, :445-495          b200qc_vxc_mat (split-K tensor-pipe GEMM)
+
+Multi-GPU (one process per GPU): each rank keeps the AO values of a contiguous slice of the grid,
+every n-th J/K work item and a slice of the aux shells; the partial AO-basis matrices are summed by
+one packed all-reduce in ``get_fock_2e`` (or one per call of the individual ``get_*`` members).
+There is no CPU fallback: constructing this class without a CUDA device raises.
+"""
+from typing import List, Optional, Tuple, Union
+import torch
+from dqc_b200 import _lib
+from dqc_b200.df.dfmol import DFMol
+from dqc_b200.grid.base_grid import BaseGrid
+from dqc_b200.hamilton.base_hamilton import BaseHamilton
+from dqc_b200.hamilton.intor import molintor as intor
+from dqc_b200.hamilton.intor import gtoeval
+from dqc_b200.hamilton.intor.lcintwrap import LibcintWrapper
+from dqc_b200.hamilton.orbconverter import OrbitalOrthogonalizer, IdentityOrbConverter
+from dqc_b200.utils.datastruct import AtomCGTOBasis, ValGrad, SpinParam, DensityFitInfo
+from dqc_b200.utils.dist import ParallelContext, get_context, split_rows
+from dqc_b200.utils.linop import LinearOperator
+from dqc_b200.utils.misc import logger
+from dqc_b200.xc.base_xc import BaseXC
+from dqc_b200.xc.b200xc import B200XC
+
+__all__ = ["HamiltonCGTO"]
+
+
+def _symm(mat: torch.Tensor) -> torch.Tensor:
+    return (mat + mat.transpose(-2, -1)) * 0.5
+
+
+class HamiltonCGTO(BaseHamilton):
+    def __init__(self, atombases: List[AtomCGTOBasis], spherical: bool = True,
+                 df: Optional[DensityFitInfo] = None,
+                 efield: Optional[Tuple[torch.Tensor, ...]] = None,
+                 vext: Optional[torch.Tensor] = None,
+                 cache=None,
+                 orthozer: bool = True,
+                 aoparamzer: str = "qr",
+                 device: Optional[torch.device] = None,
+                 jk_thresh: float = 1e-13,
+                 ctx: Optional[ParallelContext] = None) -> None:
+        _lib.load()  # raises without the CUDA library or without a device
+        if efield is not None:
+            raise NotImplementedError("electric-field terms (int1e_r*) are outside the Fock-build path")
+        if aoparamzer not in ("qr", "matexp"):
+            raise RuntimeError("Unknown ao parameterizer: %s. Available options are: ['qr', 'matexp']" % aoparamzer)
+        self.atombases = atombases
+        self.spherical = spherical
+        self.libcint_wrapper = LibcintWrapper(atombases, spherical)
+        self.dtype = self.libcint_wrapper.dtype
+        dev = device if device is not None else self.libcint_wrapper.device
+        if dev.type != "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self._ctx = ctx if ctx is not None else get_context()
+        self._jk_thresh = jk_thresh
+
+        with torch.cuda.device(self.device):
+            self._devbasis = self.libcint_wrapper.device_basis(self.device)
+            ovlp = intor.overlap(self.libcint_wrapper)
+        self._ovlp_ao = ovlp
+        self._orthozer = OrbitalOrthogonalizer(ovlp) if orthozer else IdentityOrbConverter(ovlp)
+        self._nao_ao = self.libcint_wrapper.nao()
+
+        self._dfoptions = df
+        self._df: Optional[DFMol] = None if df is None else \
+            DFMol(df, wrapper=self.libcint_wrapper, orthozer=self._orthozer, ctx=self._ctx)
+        self._vext = vext
+        self.is_grid_set = False
+        self.is_ao_set = False
+        self.is_grad_ao_set = False
+        self.is_lapl_ao_set = False
+        self.xc: Optional[BaseXC] = None
+        self.xcfamily = 1
+        self.is_built = False
+        self._jkplan = None
+
+    # ---- properties ----
+    @property
+    def nao(self) -> int:
+        return self._orthozer.nao()
+
+    @property
+    def kpts(self) -> torch.Tensor:
+        raise TypeError("Isolated molecule Hamiltonian does not have kpts property")
+
+    @property
+    def df(self):
+        return self._df
+
+    # ---- setups ----
+    def build(self) -> BaseHamilton:
+        with torch.cuda.device(self.device):
+            logger.log("Calculating the overlap matrix")
+            self.olp_mat = self._ovlp_ao
+            logger.log("Calculating the kinetic matrix")
+            kin_mat = intor.kinetic(self.libcint_wrapper)
+            logger.log("Calculating the nuclear attraction matrix")
+            nucl_mat = intor.nuclattr(self.libcint_wrapper)
+            self.nucl_mat = nucl_mat
+            self.kinnucl_mat = kin_mat + nucl_mat
+            if self._df is None:
+                logger.log("Planning the direct electron-repulsion build")
+                s0, s1 = self.libcint_wrapper.shell_idxs
+                self._jkplan = _lib.JKPlan(self._devbasis, s0, s1, self._jk_thresh)
+            else:
+                logger.log("Building the density fitting matrices")
+                self._df.build()
+            self.is_built = True
+            self.olp_mat = self._orthozer.convert2(self.olp_mat)
+            self.kinnucl_mat = self._orthozer.convert2(self.kinnucl_mat)
+            self.nucl_mat = self._orthozer.convert2(self.nucl_mat)
+            if self._vext is not None:
+                self.kinnucl_mat = self.kinnucl_mat + self.get_vext(self._vext).fullmatrix()
+            logger.log("Setting up the Hamiltonian done")
+        return self
+
+    def setup_grid(self, grid: BaseGrid, xc: Optional[BaseXC] = None) -> None:
+        self.xc = xc
+        self.xcfamily = 1 if xc is None else xc.family
+        if self.xcfamily not in (1, 2):
+            raise NotImplementedError("meta-GGA functionals are not on the B200 Fock-build path yet")
+        self.grid = grid
+        assert grid.coord_type == "cart"
+        rgrid_all = grid.get_rgrid().to(self.device)
+        dvol_all = grid.get_dvolume().to(self.device)
+        self._ngrid_total = rgrid_all.shape[0]
+        # this rank's contiguous slice of the grid (boundaries on the 128-point CTA tile)
+        g0, g1 = split_rows(self._ngrid_total, self._ctx.world, self._ctx.rank, _lib.GRID_ALIGN)
+        self._grid_slice = (g0, g1)
+        self.rgrid = rgrid_all[g0:g1].contiguous()
+        self.dvolume = dvol_all[g0:g1].contiguous()
+        ng = g1 - g0
+        logger.log("Calculating the basis values in the grid")
+        with torch.cuda.device(self.device):
+            # one buffer (ncomp, ngrid_ld, ao_ld): component 0 = values, 1..3 = gradient (GGA)
+            self._ao = gtoeval.eval_gto_padded(self.libcint_wrapper, self.rgrid, 1 if self.xcfamily == 2 else 0)
+        self._ngl, self._ld = self._ao.shape[1], self._ao.shape[2]
+        self._wpad = torch.zeros(self._ngl, dtype=torch.float64, device=self.device)
+        self._wpad[:ng] = self.dvolume
+        self.is_grid_set = True
+        self.is_ao_set = True
+        self.is_grad_ao_set = self.xcfamily == 2
+
+    # the reference's attribute names, materialised on demand (views of the padded buffer)
+    @property
+    def basis(self) -> torch.Tensor:
+        return self._ao[0, :self.rgrid.shape[0], :self._nao_ao]
+
+    @property
+    def grad_basis(self) -> torch.Tensor:
+        return self._ao[1:, :self.rgrid.shape[0], :self._nao_ao]
+
+    @property
+    def basis_dvolume(self) -> torch.Tensor:
+        return self.basis * self.dvolume.unsqueeze(-1)
+
+    # ---- Fock components ----
+    def get_nuclattr(self) -> LinearOperator:
+        return LinearOperator.m(self.nucl_mat, is_hermitian=True)
+
+    def get_kinnucl(self) -> LinearOperator:
+        return LinearOperator.m(self.kinnucl_mat, is_hermitian=True)
+
+    def get_overlap(self) -> LinearOperator:
+        return LinearOperator.m(self.olp_mat, is_hermitian=True)
+
+    def _jk_ao_partial(self, dmao: torch.Tensor, with_j: bool, with_k: bool):
+        """dmao (nset, nao, nao) symmetric AO-basis densities -> this rank's partial (J, K)."""
+        return self._jkplan.run(dmao, with_j, with_k, self._ctx.rank, self._ctx.world)
+
+    def _flat(self, dm: torch.Tensor):
+        bshape = dm.shape[:-2]
+        return bshape, dm.reshape(-1, *dm.shape[-2:])
+
+    def get_elrep(self, dm: torch.Tensor) -> LinearOperator:
+        # dm: (*BD, nao, nao) -> (*BD, nao, nao)
+        if self._df is not None:
+            return self._df.get_elrep(dm)
+        bshape, dm2 = self._flat(dm)
+        dmao = self._orthozer.unconvert_dm(_symm(dm2))   # J only sees the symmetric part of dm
+        outs = []
+        for b0 in range(0, dmao.shape[0], 2):
+            vj, _ = self._jk_ao_partial(dmao[b0:b0 + 2].contiguous(), True, False)
+            outs.append(vj)
+        mat = self._ctx.allreduce_(torch.cat(outs))
+        mat = self._orthozer.convert2(mat).reshape(*bshape, self.nao, self.nao)
+        return LinearOperator.m(_symm(mat), is_hermitian=True)
+
+    def get_exchange(self, dm):
+        if self._df is not None:
+            raise RuntimeError("Exact exchange cannot be computed with density fitting")
+        if isinstance(dm, torch.Tensor):
+            bshape, dm2 = self._flat(dm)
+            # symmetrised K[dm] == K[sym(dm)] (hcgto.py:234-236): the kernel needs a symmetric density
+            dmao = self._orthozer.unconvert_dm(_symm(dm2))
+            outs = []
+            for b0 in range(0, dmao.shape[0], 2):
+                _, vk = self._jk_ao_partial(dmao[b0:b0 + 2].contiguous(), False, True)
+                outs.append(vk)
+            mat = self._ctx.allreduce_(torch.cat(outs))
+            mat = -0.5 * self._orthozer.convert2(mat).reshape(*bshape, self.nao, self.nao)
+            return LinearOperator.m(_symm(mat), is_hermitian=True)
+        return SpinParam(u=self.get_exchange(2 * dm.u), d=self.get_exchange(2 * dm.d))
+
+    def _vmat_ao_partial(self, vrho: torch.Tensor, vgrad: Optional[torch.Tensor]) -> torch.Tensor:
+        """sum_g w phi^T (vrho phi + 2 vgrad . grad phi) over this rank's grid slice, (nao_ao, nao_ao)."""
+        ng, ngl = self.rgrid.shape[0], self._ngl
+        vr = torch.zeros(ngl, dtype=torch.float64, device=self.device)
+        vr[:ng] = vrho
+        vg = None
+        if vgrad is not None:
+            vg = torch.zeros(3, ngl, dtype=torch.float64, device=self.device)
+            vg[:, :ng] = vgrad
+        ao = self._ao if vg is not None else self._ao[:1]
+        mat = _lib.vxc_mat(ao, self._wpad, vr, vg)
+        return mat[:self._nao_ao, :self._nao_ao]
+
+    def get_vext(self, vext: torch.Tensor) -> LinearOperator:
+        # vext: (*BR, ngrid) sampled on the FULL grid
+        if not self.is_ao_set:
+            raise RuntimeError("Please call `setup_grid(grid, xc)` to call this function")
+        g0, g1 = self._grid_slice
+        v2 = vext.to(self.device).reshape(-1, vext.shape[-1])
+        mats = torch.stack([self._vmat_ao_partial(v2[b, g0:g1], None) for b in range(v2.shape[0])])
+        mats = self._ctx.allreduce_(mats)
+        mat = self._orthozer.convert2(mats).reshape(*vext.shape[:-1], self.nao, self.nao)
+        return LinearOperator.m(_symm(mat), is_hermitian=True)
+
+    def get_vxc(self, dm):
+        assert self.xc is not None, "Please call .setup_grid with the xc object"
+        parts = self._vxc_ao_partial(dm)
+        if isinstance(dm, SpinParam):
+            u, d = self._ctx.allreduce_packed([parts.u, parts.d])
+            return SpinParam(u=self._finish_ao_operator(u), d=self._finish_ao_operator(d))
+        return self._finish_ao_operator(self._ctx.allreduce_(parts))
+
+    def _finish_ao_operator(self, mat_ao: torch.Tensor) -> LinearOperator:
+        return LinearOperator.m(_symm(self._orthozer.convert2(mat_ao)), is_hermitian=True)
+
+    def _vxc_ao_partial(self, dm):
+        """AO-basis Vxc matrix summed over this rank's grid slice: (*BD, nao_ao, nao_ao) or SpinParam."""
+        densinfo = SpinParam.apply_fcn(lambda dm_: self._dm2densinfo(dm_), dm)
+        potinfo = self.xc.get_vxc(densinfo)
+        return SpinParam.apply_fcn(lambda p: self._potinfo2mat(p), potinfo)
+
+    def _potinfo2mat(self, potinfo: ValGrad) -> torch.Tensor:
+        bshape = potinfo.value.shape[:-1]
+        n = potinfo.value.shape[-1]
+        v2 = potinfo.value.reshape(-1, n)
+        g2 = potinfo.grad.reshape(-1, 3, n) if (self.xcfamily == 2 and potinfo.grad is not None) else None
+        mats = [self._vmat_ao_partial(v2[b], None if g2 is None else g2[b]) for b in range(v2.shape[0])]
+        return torch.stack(mats).reshape(*bshape, self._nao_ao, self._nao_ao)
+
+    # ---- combined two-electron + xc build with ONE collective (used by the SCF engines) ----
+    def get_fock_2e(self, dm, exx: float = 0.0, with_xc: bool = True):
+        """J[D_total] + exx * K'[D] (+ Vxc[D]) as LinearOperator (SpinParam in -> SpinParam out),
+        K' being ``get_exchange``.  All partial AO matrices travel in one packed all-reduce."""
+        polarized = isinstance(dm, SpinParam)
+        dmtot = dm.u + dm.d if polarized else dm
+        assert dmtot.ndim == 2, "get_fock_2e handles one density at a time"
+        parts: List[torch.Tensor] = []
+        if self._df is not None:
+            if exx != 0.0:
+                raise RuntimeError("Exact exchange cannot be computed with density fitting")
+            parts.append(self._df.elrep_ao_partial(self._orthozer.unconvert_dm(dmtot).contiguous()))
+        else:
+            dmao = self._orthozer.unconvert_dm(_symm(dmtot)).unsqueeze(0)
+            vj, _ = self._jk_ao_partial(dmao.contiguous(), True, False)
+            parts.append(vj[0])
+            if exx != 0.0:
+                # K'[D] = -1/2 K[D] restricted; per spin -1/2 K[2 D_s] (hcgto.py:238-241)
+                ds = torch.stack([2 * dm.u, 2 * dm.d]) if polarized else dmtot.unsqueeze(0)
+                _, vk = self._jk_ao_partial(self._orthozer.unconvert_dm(_symm(ds)).contiguous(), False, True)
+                parts.extend(list(vk))
+        nk = len(parts) - 1
+        if with_xc and self.xc is not None:
+            vx = self._vxc_ao_partial(dm)
+            parts.extend([vx.u, vx.d] if polarized else [vx])
+        parts = self._ctx.allreduce_packed(parts)
+        j_ao = _symm(parts[0])
+        xcs = parts[1 + nk:]
+
+        def total(spin_idx: int) -> LinearOperator:
+            m = j_ao
+            if nk:
+                m = m + (-0.5 * exx) * parts[1 + (spin_idx if polarized else 0)]
+            if xcs:
+                m = m + xcs[spin_idx if polarized else 0]
+            return self._finish_ao_operator(m)
+        if polarized:
+            return SpinParam(u=total(0), d=total(1))
+        return total(0)
+
+    # ---- density-matrix interface ----
+    def ao_orb2dm(self, orb: torch.Tensor, orb_weight: torch.Tensor) -> torch.Tensor:
+        orb_w = orb * orb_weight.unsqueeze(-2)
+        return torch.matmul(orb, orb_w.transpose(-2, -1))
+
+    def aodm2dens(self, dm: torch.Tensor, xyz: torch.Tensor) -> torch.Tensor:
+        # xyz: (*BR, ndim), dm: (*BD, nao, nao) -> (*BRD)
+        dmao = self._orthozer.unconvert_dm(dm.to(self.device))
+        pts = xyz.reshape(-1, xyz.shape[-1]).to(self.device)
+        ao = gtoeval.eval_gto_padded(self.libcint_wrapper, pts, 0)
+        bshape, d2 = self._flat(dmao)
+        ld = ao.shape[2]
+        outs = []
+        for b in range(d2.shape[0]):
+            dpad = torch.zeros(ld, ld, dtype=torch.float64, device=self.device)
+            dpad[:self._nao_ao, :self._nao_ao] = _symm(d2[b])
+            outs.append(_lib.rho(ao, dpad, False)[0][:pts.shape[0]])
+        dens = torch.stack(outs).reshape(*bshape, *xyz.shape[:-1])
+        # (*BD, *BR) -> broadcast shape (*BRD) as the reference's matmul broadcasting gives for the
+        # common cases (no batch on one side, or equal leading dims handled by the caller)
+        return dens if len(bshape) else dens.reshape(*xyz.shape[:-1])
+
+    # ---- energies ----
+    def get_e_hcore(self, dm: torch.Tensor) -> torch.Tensor:
+        return torch.einsum("...ij,...ji->...", self.kinnucl_mat, dm)
+
+    def get_e_elrep(self, dm: torch.Tensor) -> torch.Tensor:
+        elrep_mat = self.get_elrep(dm).fullmatrix()
+        return 0.5 * torch.einsum("...ij,...ji->...", elrep_mat, dm)
+
+    def get_e_exchange(self, dm: Union[torch.Tensor, SpinParam[torch.Tensor]]) -> torch.Tensor:
+        exc_mat = self.get_exchange(dm)
+        ene = SpinParam.apply_fcn(
+            lambda exc_mat, dm: 0.5 * torch.einsum("...ij,...ji->...", exc_mat.fullmatrix(), dm), exc_mat, dm)
+        return SpinParam.sum(ene)
+
+    def get_e_xc(self, dm: Union[torch.Tensor, SpinParam[torch.Tensor]]) -> torch.Tensor:
+        assert self.xc is not None, "Please call .setup_grid with the xc object"
+        densinfo = SpinParam.apply_fcn(lambda dm_: self._dm2densinfo(dm_), dm)
+        edens = self.xc.get_edensityxc(densinfo)          # (*BD, nr_local)
+        e = torch.sum(self.dvolume * edens, dim=-1)
+        return self._ctx.allreduce_(e.reshape(-1).clone()).reshape(e.shape)
+
+    # ---- density on (this rank's slice of) the grid ----
+    def _dm2densinfo(self, dm: torch.Tensor) -> ValGrad:
+        # dm: (*BD, nao, nao) -> value (*BD, nr), grad (*BD, 3, nr)   (hcgto.py:371-443)
+        if not self.is_ao_set:
+            raise RuntimeError("Please call `setup_grid(grid, xc)` to call this function")
+        bshape, dm2 = self._flat(dm)
+        dmdmt = self._orthozer.unconvert_dm(_symm(dm2))
+        ng, ld, gga = self.rgrid.shape[0], self._ld, self.xcfamily == 2
+        vals, grads = [], []
+        for b in range(dmdmt.shape[0]):
+            dpad = torch.zeros(ld, ld, dtype=torch.float64, device=self.device)
+            dpad[:self._nao_ao, :self._nao_ao] = dmdmt[b]
+            rho, grad = _lib.rho(self._ao, dpad, gga)
+            vals.append(rho[:ng])
+            if gga:
+                grads.append(grad[:, :ng])
+        value = torch.stack(vals).reshape(*bshape, ng)
+        grad = torch.stack(grads).reshape(*bshape, 3, ng) if gga else None
+        return ValGrad(value=value, grad=grad)
+
+    def getparamnames(self, methodname: str, prefix: str = "") -> List[str]:
+        if methodname in ("get_kinnucl",):
+            return [prefix + "kinnucl_mat"]
+        if methodname == "get_nuclattr":
+            return [prefix + "nucl_mat"]
+        if methodname == "get_overlap":
+            return [prefix + "olp_mat"]
+        if methodname in ("get_elrep", "get_exchange", "get_vxc", "get_vext", "get_e_hcore", "get_e_elrep",
+                          "get_e_exchange", "get_e_xc", "ao_orb2dm", "aodm2dens"):
+            return []
+        raise KeyError("getparamnames has no %s method" % methodname)

@@ -1,0 +1,32 @@
+"""AO values on a grid with the reference's names (dqc/hamilton/intor/gtoeval.py:60-73):
+``eval_gto`` / ``eval_gradgto`` return (nao, ngrid) / (3, nao, ngrid), or (ngrid, nao) /
+(3, ngrid, nao) with ``to_transpose=True``; ``eval_gto_padded`` hands out the padded buffer the
+Fock-build kernels read in place."""
+import torch
+from dqc_b200 import _lib
+from dqc_b200.hamilton.intor.lcintwrap import LibcintWrapper
+from dqc_b200.hamilton.intor.molintor import _device
+
+__all__ = ["eval_gto", "eval_gradgto", "eval_laplgto", "eval_gto_padded"]
+
+
+def eval_gto_padded(wrapper: LibcintWrapper, rgrid: torch.Tensor, deriv: int) -> torch.Tensor:
+    """(ncomp, ngrid_ld, ao_ld) zero-padded; ncomp = 1 (values) or 4 (values, d/dx, d/dy, d/dz)."""
+    dev = rgrid.device if rgrid.is_cuda else _device(wrapper)
+    db = wrapper.device_basis(dev)
+    s0, s1 = wrapper.shell_idxs
+    return _lib.eval_gto(db, s0, s1, rgrid.to(dev).to(torch.float64), deriv)
+
+
+def eval_gto(wrapper: LibcintWrapper, rgrid: torch.Tensor, *, to_transpose: bool = False) -> torch.Tensor:
+    ao = eval_gto_padded(wrapper, rgrid, 0)[0, :rgrid.shape[0], :wrapper.nao()]
+    return ao.contiguous() if to_transpose else ao.transpose(-2, -1).contiguous()
+
+
+def eval_gradgto(wrapper: LibcintWrapper, rgrid: torch.Tensor, *, to_transpose: bool = False) -> torch.Tensor:
+    ao = eval_gto_padded(wrapper, rgrid, 1)[1:, :rgrid.shape[0], :wrapper.nao()]
+    return ao.contiguous() if to_transpose else ao.transpose(-2, -1).contiguous()
+
+
+def eval_laplgto(wrapper: LibcintWrapper, rgrid: torch.Tensor, *, to_transpose: bool = False) -> torch.Tensor:
+    raise NotImplementedError("Laplacian AOs (meta-GGA) are not on the LDA/GGA Fock-build path (SURVEY 8f rank 4)")

@@ -1,0 +1,181 @@
+"""SCF driver: the CALLER of the Fock-build path.  Mirrors the reference's surface
+(dqc/qccalc/scf_qccalc.py:18-316, hf.py:14-316, ks.py:15-238): ``HF(system).run().energy()``,
+``KS(system, xc).run()``, ``aodm()``, ``dm2energy(dm)``, engines with ``dm2scp / scp2dm / scp2scp /
+dm2energy``; the self-consistent parameter is the Fock matrix, the initial guess ``dm0="1e"`` is
+zero density -> core Fock -> density (:88-91).
+
+The reference hands ``scp2scp`` to ``xitorch.optimize.equilibrium`` (Broyden's good method,
+alpha=-0.5, maxiter=50, :48-53, :109-113); xitorch is absent here, so the fixed point is found by
+the two solvers below (device-resident, no host round trip except the convergence scalar).  The
+fixed point -- hence the energy -- is the same; only the path differs."""
+from abc import abstractmethod
+from typing import Any, Dict, Optional, Union
+import torch
+from dqc_b200.utils.config import config
+from dqc_b200.utils.datastruct import SpinParam
+from dqc_b200.utils.linop import EditableModule
+
+__all__ = ["SCF_QCCalc", "BaseSCFEngine", "equilibrium"]
+
+
+def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, f_tol: float = 1e-9,
+                alpha: float = -0.5, history: int = 8, verbose: bool = False, **unused) -> torch.Tensor:
+    """Solve y = fcn(y).  method "diis": Anderson/Pulay mixing of the last `history` iterates on the
+    residual fcn(y) - y; "broyden1": Broyden's good method with J0 = alpha^-1 I like the reference's
+    default; "simple": y <- fcn(y).  Stops when max|fcn(y) - y| < f_tol."""
+    y = y0
+    shape = y0.shape
+    if method == "simple":
+        for _ in range(maxiter):
+            fy = fcn(y)
+            if float((fy - y).abs().max()) < f_tol:
+                return fy
+            y = fy
+        return y
+    if method == "broyden1":
+        x = y0.reshape(-1)
+        f = (fcn(x.reshape(shape)).reshape(-1) - x)
+        us, vs = [], []          # B^-1 = alpha I + sum_k u_k v_k^T  (Sherman-Morrison updates)
+
+        def binv(v):
+            out = alpha * v
+            for u, w in zip(us, vs):
+                out = out + u * torch.dot(w, v)
+            return out
+
+        def binv_t(v):
+            out = alpha * v
+            for u, w in zip(us, vs):
+                out = out + w * torch.dot(u, v)
+            return out
+        for it in range(maxiter):
+            if float(f.abs().max()) < f_tol:
+                break
+            dx = -binv(f)
+            xn = x + dx
+            fn = fcn(xn.reshape(shape)).reshape(-1) - xn
+            df = fn - f
+            bdf = binv(df)
+            denom = torch.dot(dx, bdf)
+            us.append((dx - bdf) / denom)
+            vs.append(binv_t(dx))
+            x, f = xn, fn
+            if verbose:
+                print("broyden1 iter %3d  max|f| = %.3e" % (it, float(f.abs().max())))
+        return x.reshape(shape)
+    if method != "diis":
+        raise RuntimeError("Unknown equilibrium method: %s (available: diis, broyden1, simple)" % method)
+    ys, rs = [], []
+    for it in range(maxiter):
+        fy = fcn(y)
+        r = (fy - y).reshape(-1)
+        err = float(r.abs().max())
+        if verbose:
+            print("diis iter %3d  max|f| = %.3e" % (it, err))
+        if err < f_tol:
+            return fy
+        ys.append(fy.reshape(-1))
+        rs.append(r)
+        ys, rs = ys[-history:], rs[-history:]
+        n = len(rs)
+        if n == 1:
+            y = fy
+            continue
+        R = torch.stack(rs)
+        B = torch.zeros(n + 1, n + 1, dtype=R.dtype, device=R.device)
+        B[:n, :n] = R @ R.T
+        B[n, :n] = B[:n, n] = -1.0
+        rhs = torch.zeros(n + 1, dtype=R.dtype, device=R.device)
+        rhs[n] = -1.0
+        try:
+            c = torch.linalg.solve(B, rhs)[:n]
+        except Exception:
+            ys, rs = ys[-1:], rs[-1:]
+            y = fy
+            continue
+        y = (c.unsqueeze(-1) * torch.stack(ys)).sum(0).reshape(shape)
+    return y
+
+
+class BaseSCFEngine(EditableModule):
+    @abstractmethod
+    def get_system(self):
+        pass
+
+    @abstractmethod
+    def dm2scp(self, dm):
+        pass
+
+    @abstractmethod
+    def scp2dm(self, scp):
+        pass
+
+    @abstractmethod
+    def scp2scp(self, scp):
+        pass
+
+    @abstractmethod
+    def dm2energy(self, dm):
+        pass
+
+    @abstractmethod
+    def set_eigen_options(self, eigen_options: Dict[str, Any]) -> None:
+        pass
+
+
+class SCF_QCCalc(object):
+    def __init__(self, engine: BaseSCFEngine, variational: bool = False):
+        if variational:
+            raise NotImplementedError("variational (direct-minimisation) SCF is outside the Fock-build path "
+                                      "(SURVEY section 2, component 14); use variational=False")
+        self._engine = engine
+        self._polarized = engine.polarized
+        self._shape = engine.shape
+        self.dtype = engine.dtype
+        self.device = engine.device
+        self._has_run = False
+        self._variational = variational
+
+    def get_system(self):
+        return self._engine.get_system()
+
+    def run(self, dm0="1e", eigen_options: Optional[Dict[str, Any]] = None,
+            fwd_options: Optional[Dict[str, Any]] = None, bck_options: Optional[Dict[str, Any]] = None):
+        fwd = {"method": "diis", "alpha": -0.5, "maxiter": 50, "verbose": config.VERBOSE > 0}
+        fwd.update(fwd_options or {})
+        self._engine.set_eigen_options(eigen_options or {"method": "exacteig"})
+        if dm0 is None:
+            dm = self._get_zero_dm()
+        elif isinstance(dm0, str):
+            if dm0 != "1e":
+                raise RuntimeError("Unknown dm0: %s" % dm0)
+            dm = self._engine.scp2dm(self._engine.dm2scp(self._get_zero_dm()))
+        else:
+            dm = SpinParam.apply_fcn(lambda d: d.detach().to(self.device), dm0)
+        if isinstance(dm, torch.Tensor) and self._polarized:
+            dm = SpinParam(u=dm * 0.5, d=dm * 0.5)
+        elif isinstance(dm, SpinParam) and not self._polarized:
+            dm = dm.u + dm.d
+        scp0 = self._engine.dm2scp(dm)
+        scp = equilibrium(self._engine.scp2scp, scp0, **fwd)
+        self._dm = self._engine.scp2dm(scp)
+        self._has_run = True
+        return self
+
+    def energy(self) -> torch.Tensor:
+        assert self._has_run, "run() must be called first"
+        return self.dm2energy(self._dm)
+
+    def aodm(self):
+        assert self._has_run, "run() must be called first"
+        return self._dm
+
+    def dm2energy(self, dm) -> torch.Tensor:
+        assert (isinstance(dm, torch.Tensor) and not self._polarized) or \
+            (isinstance(dm, SpinParam) and self._polarized), \
+            "The dm must be a Tensor for unpolarized case and SpinParam of Tensor for polarized case"
+        return self._engine.dm2energy(dm)
+
+    def _get_zero_dm(self):
+        z = torch.zeros(self._shape, dtype=self.dtype, device=self.device)
+        return SpinParam(u=z, d=z.clone()) if self._polarized else z

@@ -1,0 +1,206 @@
+"""Molecule description -> basis, occupations, nuclear repulsion, grid and Hamiltonian factory.
+Same constructor and members as the reference's ``Mol`` (dqc/system/mol.py:77-473); the Hamiltonian
+it hands out is the B200 one (dqc_b200/hamilton/hcgto.py), so ``device`` defaults to the current
+CUDA device."""
+from typing import Dict, List, Optional, Tuple, Union
+import warnings
+import torch
+from dqc_b200.api.loadbasis import loadbasis
+from dqc_b200.api.parser import parse_moldesc
+from dqc_b200.grid.base_grid import BaseGrid
+from dqc_b200.grid.factory import get_predefined_grid
+from dqc_b200.hamilton.hcgto import HamiltonCGTO
+from dqc_b200.system.base_system import BaseSystem
+from dqc_b200.utils.datastruct import CGTOBasis, AtomCGTOBasis, SpinParam, DensityFitInfo, ZType, is_z_float
+from dqc_b200.utils.misc import logger, occnumber
+from dqc_b200.utils.periodictable import get_atomz
+
+__all__ = ["Mol"]
+
+BasisInpType = Union[str, List[CGTOBasis], List[str], List[List[CGTOBasis]], Dict[Union[str, int], Union[List[CGTOBasis], str]]]
+
+
+class Mol(BaseSystem):
+    def __init__(self, moldesc, basis: BasisInpType, *, orthogonalize_basis: bool = True,
+                 ao_parameterizer: str = "qr", grid: Union[int, str] = "sg3", spin: Optional[ZType] = None,
+                 charge: ZType = 0, orb_weights: Optional[SpinParam[torch.Tensor]] = None,
+                 efield=None, vext: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.float64,
+                 device: Optional[torch.device] = None, jk_thresh: float = 1e-13, ctx=None):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+                else torch.device("cpu")
+        self._dtype = dtype
+        self._device = torch.device(device)
+        self._grid_inp = grid
+        self._basis_inp = basis
+        self._grid: Optional[BaseGrid] = None
+        self._vext = vext
+        self._efield = efield
+        self._jk_thresh = jk_thresh
+        self._ctx = ctx
+
+        # basis parameters stay on the host (they are packed into the libcint layout and uploaded once)
+        atomzs, atompos = parse_moldesc(moldesc, dtype=dtype, device=torch.device("cpu"))
+        atomzs_int = torch.round(atomzs).to(torch.int) if atomzs.is_floating_point() else atomzs
+        allbases = _parse_basis(atomzs_int, basis)
+        atombases = [AtomCGTOBasis(atomz=(float(z) if atomzs.is_floating_point() else int(z)), bases=b, pos=p)
+                     for (z, b, p) in zip(atomzs, allbases, atompos)]
+        self._atombases = atombases
+        self._orthogonalize_basis = orthogonalize_basis
+        self._aoparamzer = ao_parameterizer
+        self._atompos = atompos.to(self._device)
+        self._atomzs = atomzs.to(self._device)
+        self._atomzs_int = atomzs_int
+        self._hamilton = self._make_hamiltonian(None)
+        nelecs_tot = torch.sum(atomzs)
+
+        if orb_weights is None:
+            nelecs, spin, frac_mode = _get_nelecs_spin(nelecs_tot, spin, charge)
+            ow, owu, owd = _get_orb_weights(nelecs, spin, frac_mode, dtype, self._device)
+            self._spin, self._charge, self._numel = spin, charge, nelecs
+            self._orb_weights, self._orb_weights_u, self._orb_weights_d = ow, owu, owd
+        else:
+            if not isinstance(orb_weights, SpinParam):
+                raise TypeError("Specifying orb_weights must be in SpinParam type")
+            assert orb_weights.u.ndim == 1 and orb_weights.d.ndim == 1
+            assert len(orb_weights.u) == len(orb_weights.d)
+            dec_u = torch.all(orb_weights.u[:-1] - orb_weights.u[1:] > -1e-4)
+            dec_d = torch.all(orb_weights.d[:-1] - orb_weights.d[1:] > -1e-4)
+            if not (dec_u and dec_d):
+                warnings.warn("The orbitals should be ordered in a non-increasing manner. "
+                              "Otherwise, some calculations might be wrong.")
+            utot, dtot = orb_weights.u.sum(), orb_weights.d.sum()
+            self._numel = utot + dtot
+            self._spin = utot - dtot
+            self._charge = nelecs_tot - self._numel
+            self._orb_weights_u = orb_weights.u.to(self._device)
+            self._orb_weights_d = orb_weights.d.to(self._device)
+            self._orb_weights = self._orb_weights_u + self._orb_weights_d
+
+    def _make_hamiltonian(self, df: Optional[DensityFitInfo]) -> HamiltonCGTO:
+        return HamiltonCGTO(self._atombases, df=df, efield=self._efield, vext=self._vext,
+                            orthozer=self._orthogonalize_basis, aoparamzer=self._aoparamzer,
+                            device=self._device, jk_thresh=self._jk_thresh, ctx=self._ctx)
+
+    def densityfit(self, method: Optional[str] = None, auxbasis: Optional[BasisInpType] = None) -> BaseSystem:
+        if method is None:
+            method = "coulomb"
+        if auxbasis is None:
+            auxbasis = "cc-pvtz-jkfit"   # the reference's default (mol.py:190-192); must be embedded to be used
+        auxbasis_lst = _parse_basis(self._atomzs_int, auxbasis)
+        atomaux = [AtomCGTOBasis(atomz=ab.atomz, bases=bas, pos=ab.pos)
+                   for (ab, bas) in zip(self._atombases, auxbasis_lst)]
+        self._hamilton = self._make_hamiltonian(DensityFitInfo(method=method, auxbases=atomaux))
+        return self
+
+    def get_hamiltonian(self) -> HamiltonCGTO:
+        return self._hamilton
+
+    def set_cache(self, fname: str, paramnames=None) -> BaseSystem:
+        raise NotImplementedError("the h5py integral cache is outside the Fock-build path (DESIGN.md)")
+
+    def get_orbweight(self, polarized: bool = False):
+        if not polarized:
+            return self._orb_weights
+        return SpinParam(u=self._orb_weights_u, d=self._orb_weights_d)
+
+    def get_nuclei_energy(self) -> torch.Tensor:
+        # 1/2 sum_{A != B} Z_A Z_B / R_AB  (mol.py:252-260)
+        pos = self._atompos
+        z = self._atomzs.to(pos.dtype)
+        r12 = torch.cdist(pos, pos)
+        r12 = r12 + torch.diag(torch.full((pos.shape[0],), float("inf"), dtype=pos.dtype, device=pos.device))
+        return (z.unsqueeze(-2) * z.unsqueeze(-1) / r12).sum() * 0.5
+
+    def setup_grid(self) -> None:
+        logger.log("Constructing the integration grid")
+        self._grid = get_predefined_grid(self._grid_inp, self._atomzs_int, self._atompos,
+                                         dtype=self._dtype, device=self._device)
+        logger.log("Constructing the integration grid: done")
+
+    def get_grid(self) -> BaseGrid:
+        if self._grid is None:
+            raise RuntimeError("Please run mol.setup_grid() first before calling get_grid()")
+        return self._grid
+
+    def requires_grid(self) -> bool:
+        return self._vext is not None
+
+    def getparamnames(self, methodname: str, prefix: str = "") -> List[str]:
+        if methodname == "get_nuclei_energy":
+            return [prefix + "_atompos"]
+        raise KeyError("Unknown methodname: %s" % methodname)
+
+    @property
+    def atompos(self) -> torch.Tensor:
+        return self._atompos
+
+    @property
+    def atomzs(self) -> torch.Tensor:
+        return self._atomzs
+
+    @property
+    def spin(self) -> ZType:
+        return self._spin
+
+    @property
+    def charge(self) -> ZType:
+        return self._charge
+
+    @property
+    def numel(self) -> ZType:
+        return self._numel
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self._dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+
+def _parse_basis(atomzs: torch.Tensor, basis: BasisInpType) -> List[List[CGTOBasis]]:
+    natoms = len(atomzs)
+    if isinstance(basis, str):
+        return [loadbasis("%d:%s" % (int(z), basis)) for z in atomzs]
+    if isinstance(basis, dict):
+        basis_int: Dict[int, List[CGTOBasis]] = {}
+        for k, v in basis.items():
+            atz = int(get_atomz(k))
+            basis_int[atz] = v if isinstance(v, list) else loadbasis("%d:%s" % (atz, v))
+        return [basis_int[int(z)] for z in atomzs]
+    assert len(atomzs) == len(basis) and len(basis) > 0
+    if isinstance(basis[0], CGTOBasis):
+        return [basis for _ in range(natoms)]
+    if isinstance(basis[0], str):
+        return [loadbasis("%d:%s" % (int(z), b)) for (z, b) in zip(atomzs, basis)]
+    return basis
+
+
+def _get_nelecs_spin(nelecs_tot: torch.Tensor, spin: Optional[ZType], charge: ZType):
+    frac_mode = nelecs_tot.is_floating_point() or is_z_float(charge) or (spin is not None and is_z_float(spin))
+    assert nelecs_tot >= charge, "Only %f electrons, but needs %f charge" % (float(nelecs_tot), charge)
+    nelecs = nelecs_tot - charge
+    if spin is None:
+        assert not frac_mode, "Fraction case requires the spin argument to be specified"
+        spin = nelecs % 2
+    else:
+        assert spin >= 0
+        if not frac_mode:
+            assert (nelecs - spin) % 2 == 0, "Spin %d is not suited for %d electrons" % (spin, nelecs)
+    return nelecs, spin, frac_mode
+
+
+def _get_orb_weights(nelecs, spin, frac_mode: bool, dtype, device):
+    # (total, spin-up, spin-down) occupations, mol.py:421-443
+    nspin_dn = (nelecs - spin) * 0.5 if frac_mode else torch.div(nelecs - spin, 2, rounding_mode="floor")
+    nspin_up = nspin_dn + spin
+    owu = occnumber(nspin_up, dtype=dtype, device=device)
+    owd = occnumber(nspin_dn, n=len(owu), dtype=dtype, device=device)
+    ow = owu + owd
+    if nspin_dn > 0:
+        owd = occnumber(nspin_dn, dtype=dtype, device=device)
+    else:
+        owd = occnumber(0, n=1, dtype=dtype, device=device)
+    return ow, owu, owd
