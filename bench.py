@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Fock-build benchmark (BASELINE.json metric): wall-ms per SCF-iteration Fock build.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+
+A "step" is ONE Fock build at a fixed density: F_2e = J[D] (+ a K'[D]) + Vxc[D] through
+``HamiltonCGTO.get_fock_2e`` -- every kernel, the basis changes and (N > 1) the single packed
+all-reduce.  Default workload = the configuration the metric is quoted on: C60 / def2-SVP / PBE with
+density fitting on the sg3 grid (1 060 440 points, nao 840).  Inputs (AO values 28.5 GB, packed
+(ij|P) 9.7 GB) are far larger than the 126 MB L2, so no flush is needed between iterations.
+
+Prints ONE JSON line (rank 0).  ``value`` = device-timed ms per step, max over ranks; ``e2e`` = the
+same build called with HOST buffers (pinned density in, Fock matrix out, copies inside the timed
+region); ``roofline`` = the dominant kernel timed live with CUDA events inside the timed region;
+``cpu_baseline`` = the reference-equivalent PyTorch-CPU ops of oracle/fock_ref.py on a bounded sample.
+``--impl reference`` times only that CPU path (rank 0), on the same workload and metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (system, basis, xc, df aux basis or None, exx fraction, grid)
+    "c60-pbe-df": ("c60", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
+    "benzene-lda-4c": ("benzene", "cc-pvdz", "lda_x + lda_c_pw", None, 0.0, "sg3"),
+    "h2o-pbe-df": ("h2o", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
+    "h2o-hf": ("h2o", "sto-3g", None, None, 1.0, "sg3"),
+    "taxol-like-pbe0-4c": ("taxol_like", "def2-svp", "0.75*gga_x_pbe + gga_c_pbe", None, 0.25, "sg3"),
+    "taxol-like-pbe-df": ("taxol_like", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
+}
+METRIC = "fock_build_wall_ms_per_scf_iter"
+
+
+def geometry(name):
+    from dqc_b200.utils import systems
+    return getattr(systems, name)()
+
+
+def seeded_dm(nao, nocc, device):
+    """D = 2 C C^T, C = first nocc columns of qr(randn(nao, nao)) under manual_seed(0)."""
+    g = torch.Generator().manual_seed(0)
+    q, _ = torch.linalg.qr(torch.randn(nao, nao, dtype=torch.float64, generator=g))
+    c = q[:, :nocc]
+    return (2 * c @ c.T).to(device)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's per-iteration torch-CPU ops (oracle/fock_ref.py) on a bounded sample
+def cpu_reference_step_factory(workload, grid_sample=65536, aux_sample=96):
+    """Builds the sampled CPU problem with the ORACLE only (no CUDA kernel on this path) and returns
+    (step_fn, scale_info).  step_fn() runs one sampled Fock build; full-size time is extrapolated
+    linearly in ngrid (XC part) and naux (DF-J part) -- both are exactly linear in those sizes in the
+    reference (hcgto.py:399-418,461-481 chunk loops; dfmol.py:70-75 einsums)."""
+    from oracle import fock_ref, cint, xc_ref
+    from dqc_b200.hamilton.intor.lcintwrap import LibcintWrapper
+    from dqc_b200.grid.factory import get_predefined_grid
+    from tests import util
+    sysname, basis, xc, aux, exx, gridname = WORKLOADS[workload]
+    zs, pos = geometry(sysname)
+    torch.set_num_threads(os.cpu_count() or 1)
+    w, _ = util.make_wrapper(zs, pos.tolist(), basis)
+    nao = w.nao()
+    info = {"nao": nao, "cores": torch.get_num_threads()}
+    # grid sample: every k-th point of the real sg3 grid positions (weights irrelevant for timing: 1e-3)
+    per_atom = {}
+    ngrid_full = 0
+    pts = []
+    for z, p in zip(zs, pos):
+        if z not in per_atom:
+            g1 = get_predefined_grid(gridname, [z], torch.zeros(1, 3, dtype=torch.float64), device=torch.device("cpu"))
+            per_atom[z] = g1.get_rgrid().numpy()
+        ngrid_full += per_atom[z].shape[0]
+        pts.append(per_atom[z] + p)
+    pts = np.concatenate(pts)
+    stride = max(1, ngrid_full // grid_sample)
+    sample = np.ascontiguousarray(pts[::stride])
+    info.update(ngrid_full=ngrid_full, ngrid_sample=int(sample.shape[0]))
+    h = fock_ref.RefHamilton(w, orthozer=True)
+    if xc is not None:
+        h.setup_grid(sample, np.full(sample.shape[0], 1e-3), xc)
+    naux_full = 0
+    if aux is not None:
+        auxw, _ = util.make_wrapper(zs, pos.tolist(), aux)
+        naux_full = auxw.nao()
+        bw, aw = LibcintWrapper.concatenate(w, auxw)
+        atm, bas, env = aw.atm_bas_env
+        a0, a1 = aw.shell_idxs
+        b0, b1 = bw.shell_idxs
+        # first aux shells up to ~aux_sample functions
+        loc = aw.full_shell_to_aoloc
+        a_hi = a0 + 1
+        while a_hi < a1 and loc[a_hi] - loc[a0] < aux_sample:
+            a_hi += 1
+        j3c = torch.as_tensor(cint.int3c2e(atm, bas, env, (b0, b1, b0, b1, a0, a_hi)))
+        j2c = torch.as_tensor(cint.int2c2e(atm, bas, env, (a0, a_hi, a0, a_hi)))
+        h.j3c, h.j2c, h.inv_j2c = j3c, j2c, torch.inverse(j2c)
+        info.update(naux_full=naux_full, naux_sample=int(j3c.shape[-1]))
+    elif exx != 0.0 or xc is None or aux is None:
+        info["note"] = "dense-ERI J/K of this workload is not part of the CPU sample (nao^4 tensor)"
+    nocc = max(1, int(sum(zs)) // 2)
+    dm = seeded_dm(h.nao, min(nocc, h.nao), torch.device("cpu"))
+
+    def step():
+        t = {}
+        t0 = time.perf_counter()
+        if h.j3c is not None:
+            h.get_elrep(dm)
+        t["dfj_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if xc is not None:
+            h.get_vxc(dm)
+        t["xc_s"] = time.perf_counter() - t0
+        return t
+    return step, info
+
+
+def run_cpu_reference(workload, steps, warmup):
+    step, info = cpu_reference_step_factory(workload)
+    for _ in range(warmup):
+        step()
+    acc = {"dfj_s": 0.0, "xc_s": 0.0}
+    for _ in range(steps):
+        t = step()
+        for k in acc:
+            acc[k] += t[k]
+    dfj = acc["dfj_s"] / steps
+    xcs = acc["xc_s"] / steps
+    full = xcs * info["ngrid_full"] / max(1, info["ngrid_sample"])
+    if info.get("naux_full"):
+        full += dfj * info["naux_full"] / info["naux_sample"]
+    sample = "XC ops on %d of %d grid points" % (info["ngrid_sample"], info["ngrid_full"])
+    if info.get("naux_full"):
+        sample += ", DF-J ops on %d of %d aux functions" % (info["naux_sample"], info["naux_full"])
+    sample += "; per-step time extrapolated linearly to the full sizes"
+    return full * 1e3, info, sample
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c60-pbe-df", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sysname, basis, xc, aux, exx, gridname = WORKLOADS[args.workload]
+    config = {"workload": "%s: %s / %s / xc=%s / %s / grid %s" % (
+        args.workload, sysname, basis, xc, ("DF-J aux=" + aux) if aux else "direct 4c J/K", gridname),
+        "exx_fraction": exx, "l2_policy": "inputs (AO values, packed (ij|P)) larger than L2; no flush",
+        "parallelism": "grid rows + aux shells (or J/K work items) sharded over %d GPU(s), one packed all-reduce" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ms, info, sample = run_cpu_reference(args.workload, max(1, args.steps), args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": ms, "unit": "ms", "cores": info["cores"], "kind": "port", "sample": sample},
+                "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from dqc_b200 import Mol, get_xc, _lib
+    from dqc_b200.utils.dist import get_context
+    ctx = get_context()
+    assert ctx.world == world
+
+    zs, pos = geometry(sysname)
+    t_setup = time.perf_counter()
+    mol = Mol((torch.tensor(zs), torch.tensor(pos, dtype=torch.float64)), basis=basis, grid=gridname, device=dev)
+    if aux is not None:
+        mol.densityfit(auxbasis=aux)
+    h = mol.get_hamiltonian()
+    if xc is not None:
+        mol.setup_grid()
+        h.setup_grid(mol.get_grid(), get_xc(xc))
+    h.build()
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    nao = h.nao
+    nocc = max(1, int(sum(zs)) // 2)
+    dm = seeded_dm(nao, min(nocc, nao), dev)
+    ngrid = int(mol.get_grid().get_rgrid().shape[0]) if xc is not None else 0
+    config.update(nao=nao, nao_ao=h._nao_ao, ngrid=ngrid, natoms=len(zs),
+                  naux=(h.df._naux if h.df is not None else None), setup_s=round(t_setup, 2))
+
+    def step():
+        return h.get_fock_2e(dm, exx=exx, with_xc=xc is not None).fullmatrix()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    # ---- timed region: device time, CUDA events on the current stream, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.profile_enable(True)
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fock = step()
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0])
+    ms_per_step = total_ms / args.steps
+
+    # ---- e2e: host buffers in and out, copies inside the timed region ----
+    dm_host = dm.cpu().pin_memory()
+    fock_host = torch.empty_like(dm_host).pin_memory()
+    dm_dev = torch.empty_like(dm)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        dm_dev.copy_(dm_host, non_blocking=True)
+        f = h.get_fock_2e(dm_dev, exx=exx, with_xc=xc is not None).fullmatrix()
+        fock_host.copy_(f, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    e2e_ms /= args.steps
+    assert torch.allclose(fock_host.to(dev), fock, rtol=0, atol=1e-9), "e2e and device-resident Fock differ"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (timed live above) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fpk:
+            peaks = json.load(fpk)
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    dmma_peak = _lib.peak_fp64_dmma(20000)
+    ngl_local, ld = (h._ngl, h._ld) if xc is not None else (0, 0)
+    ncomp = 4 if (xc is not None and h.xcfamily == 2) else 1
+    kern = {k: {"launches": c, "ms_per_launch": ms / c} for k, (c, ms) in prof.items()}
+    dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+    roofline = None
+    if dominant in ("vxc_gemm_kernel", "rho_kernel"):
+        flops = 2.0 * ngl_local * ld * ld          # per launch (2 ngrid nao^2, padded sizes)
+        ach = flops / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e12
+        roofline = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                    "frac": ach / dmma_peak, "traffic": None,
+                    "peak_source": "fp64 DMMA (mma.sync m8n8k4) issue-rate microbenchmark run in this process "
+                                   "(b200qc_peak_fp64_dmma); MEASURED_PEAKS.json has no fp64 entry -- tcgen05 has no "
+                                   "f64 kind, so the bf16 figure is not the bound of this kernel",
+                    "algorithmic_flops_per_launch": flops}
+    elif dominant in ("dfj_pass1_kernel", "dfj_pass2_kernel"):
+        nb = h.df._j3c_packed.numel() * 8.0
+        ach = nb / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_launch": nb}
+    elif dominant == "jk_kernel":
+        roofline = {"kernel": dominant, "bound": "fp64-alu", "achieved": h._jkplan.nquartets / (
+            sum(ms for k, (c, ms) in prof.items() if k == "jk_kernel") / args.steps * 1e-3), "peak": None,
+            "unit": "contracted shell quartets/s", "frac": None, "traffic": None}
+    # secondary rooflines (HBM-bound kernels) for context
+    extra = {}
+    if "dfj_pass1_kernel" in kern and h.df is not None and h.df._j3c_packed is not None:
+        nb = h.df._j3c_packed.numel() * 8.0
+        for k in ("dfj_pass1_kernel", "dfj_pass2_kernel"):
+            extra[k] = {"GB/s": nb / (kern[k]["ms_per_launch"] * 1e-3) / 1e9, "frac_of_hbm": nb / (
+                kern[k]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
+    if "vxc_vb_kernel" in kern:
+        nb = (ncomp + 1) * ngl_local * ld * 8.0
+        extra["vxc_vb_kernel"] = {"GB/s": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9,
+                                  "frac_of_hbm": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
+    for k in ("rho_kernel", "vxc_gemm_kernel"):
+        if k in kern:
+            fl = 2.0 * ngl_local * ld * ld
+            extra[k] = {"TFLOP/s": fl / (kern[k]["ms_per_launch"] * 1e-3) / 1e12,
+                        "frac_of_fp64_dmma": fl / (kern[k]["ms_per_launch"] * 1e-3) / 1e12 / dmma_peak}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        ms, info, sample = run_cpu_reference(args.workload, 2, 1)
+        cpu_baseline = {"value": ms, "unit": "ms", "cores": info["cores"], "kind": "port", "sample": sample}
+
+    xc_ms = sum(ms for k, (c, ms) in prof.items() if k in ("rho_kernel", "xc_kernel", "vxc_vb_kernel",
+                                                           "vxc_gemm_kernel", "slab_reduce_kernel")) / args.steps
+    line = {"metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(dm_host.numel() * 8),
+                    "d2h_bytes_per_step": int(fock_host.numel() * 8)},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "xc_grid_points_per_s": (ngrid / (xc_ms * 1e-3)) if xc_ms > 0 else None,
+            "fp64_dmma_peak_tflops": dmma_peak, "kernels": kern, "kernel_rooflines": extra}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

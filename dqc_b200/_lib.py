@@ -27,6 +27,11 @@ _SIGS = {
     "b200qc_last_error": (ctypes.c_char_p, []),
     "b200qc_version": (ctypes.c_int, []),
     "b200qc_launch_count": (ctypes.c_int64, []),
+    "b200qc_profile": (ctypes.c_int, [ctypes.c_int]),
+    "b200qc_profile_nkernels": (ctypes.c_int, []),
+    "b200qc_profile_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "b200qc_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_peak_fp64_dmma": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_free": (ctypes.c_int, [ctypes.c_void_p]),
@@ -130,6 +135,30 @@ def _np(a: np.ndarray) -> ctypes.c_void_p:
 
 def launch_count() -> int:
     return int(load(False).b200qc_launch_count())
+
+
+def profile_enable(on: bool = True):
+    """Start (or stop) per-kernel CUDA-event timing inside the library."""
+    _check(load().b200qc_profile(1 if on else 0), "profile")
+
+
+def profile_read():
+    """{kernel name: (launch count, total device ms)} since the last read; synchronises."""
+    lib = load()
+    n = lib.b200qc_profile_nkernels()
+    ms = np.zeros(n, dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.int64)
+    _check(lib.b200qc_profile_read(_np(ms), _np(cnt)), "profile_read")
+    return {lib.b200qc_profile_name(i).decode(): (int(cnt[i]), float(ms[i])) for i in range(n) if cnt[i] > 0}
+
+
+def peak_fp64_dmma(iters: int = 20000) -> float:
+    """Measured fp64 tensor-pipe peak (TFLOP/s) of the current device."""
+    lib = load()
+    scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
+    out = ctypes.c_double(0.0)
+    _check(lib.b200qc_peak_fp64_dmma(iters, _ptr(scratch), ctypes.byref(out), _stream()), "peak_fp64_dmma")
+    return float(out.value)
 
 
 def round_up(n: int, m: int) -> int:

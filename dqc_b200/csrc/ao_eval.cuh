@@ -138,6 +138,7 @@ extern "C" int b200qc_eval_gto(const b200qc_basis *basis, int sh0, int sh1, int 
     if (ngrid == 0) return 0;
     const int nblk = (int)((ngrid + AO_PTS - 1) / AO_PTS);
     const size_t smem = sizeof(double) * (deriv ? 4 : 1) * AO_WIN * 33;
+    prof_begin(PROF_AO_EVAL, as_stream(stream));
     if (deriv) {
         QC_CHECK(cudaFuncSetAttribute(ao_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ao_eval_kernel<true><<<nblk, AO_THREADS, smem, as_stream(stream)>>>(
@@ -146,6 +147,7 @@ extern "C" int b200qc_eval_gto(const b200qc_basis *basis, int sh0, int sh1, int 
         ao_eval_kernel<false><<<nblk, AO_THREADS, smem, as_stream(stream)>>>(
             basis->d_shells, basis->d_env, basis->d_ao_loc, sh0, sh1, coords, ngrid, ao, ngrid_ld, ao_ld);
     }
+    prof_end(as_stream(stream));
     QC_LAUNCHED(1);
     return 0;
 }

@@ -73,7 +73,9 @@ extern "C" int b200qc_becke_weights(const double *xyz, const int *owner, int64_t
     QC_REQUIRE(smem <= 200 * 1024, "too many atoms for the shared-memory distance column");
     QC_CHECK(cudaFuncSetAttribute(becke_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nblk = (int)((ngrid + BECKE_THREADS - 1) / BECKE_THREADS);
+    prof_begin(PROF_BECKE, st);
     becke_weights_kernel<<<nblk, BECKE_THREADS, smem, st>>>(xyz, owner, ngrid, atompos, natom, rinv, aij, w);
+    prof_end(st);
     QC_LAUNCHED(1);
     QC_CHECK(cudaFreeAsync(rinv, st));
     return 0;

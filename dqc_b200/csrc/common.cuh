@@ -98,3 +98,34 @@ static __constant__ RysTable c_rys;
 static bool g_rys_ready = false;
 
 static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
+
+// ---- optional per-kernel timing (bench.py's roofline numbers) ------------------------------
+// When enabled every major launch is bracketed by CUDA events on its own stream; reading the
+// profile synchronises once and returns, per kernel id, launch count and summed device time.
+enum {
+    PROF_AO_EVAL = 0, PROF_BECKE, PROF_RHO, PROF_XC, PROF_VXC_VB, PROF_VXC_GEMM, PROF_VXC_REDUCE,
+    PROF_DFJ_PASS1, PROF_DFJ_PASS2, PROF_DFJ_SMALL, PROF_JK, PROF_INTS, PROF_PEAK, PROF_N
+};
+static const char *const g_prof_names[PROF_N] = {
+    "ao_eval_kernel", "becke_weights_kernel", "rho_kernel", "xc_kernel", "vxc_vb_kernel", "vxc_gemm_kernel",
+    "slab_reduce_kernel", "dfj_pass1_kernel", "dfj_pass2_kernel", "dfj_small_kernels", "jk_kernel",
+    "int_dense_kernel", "dmma_peak_kernel"};
+struct ProfRec {
+    int id;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static inline void prof_begin(int id, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r;
+    r.id = id;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+static inline void prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof.empty()) return;
+    cudaEventRecord(g_prof.back().b, st);
+}

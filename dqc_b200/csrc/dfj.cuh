@@ -155,14 +155,20 @@ extern "C" int b200qc_dfj_pass1(const double *j3c, int64_t nao, int64_t naux, in
     cudaStream_t st = as_stream(stream);
     const int64_t npair = nao * (nao + 1) / 2;
     double *dvec = work, *partial = work + dfj_dvec_len(npair) + 2 * ld;
+    prof_begin(PROF_DFJ_SMALL, st);
     dfj_gather_dm_kernel<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(dm, (int)nao, npair, dvec);
+    prof_end(st);
     QC_LAUNCHED(1);
     const int nslab = dfj_nslab(npair, ld);
     const int64_t rows = (npair + nslab - 1) / nslab;
     dim3 grid((unsigned)nslab, (unsigned)((ld + DFJ_COLS - 1) / DFJ_COLS));
+    prof_begin(PROF_DFJ_PASS1, st);
     dfj_pass1_kernel<<<grid, DFJ_TPB, 0, st>>>(j3c, npair, ld, dvec, rows, partial);
+    prof_end(st);
     QC_LAUNCHED(1);
+    prof_begin(PROF_DFJ_SMALL, st);
     dfj_reduce_kernel<<<(unsigned)((naux + 255) / 256), 256, 0, st>>>(partial, nslab, ld, naux, temp);
+    prof_end(st);
     QC_LAUNCHED(1);
     return 0;
 }
@@ -173,7 +179,9 @@ extern "C" int b200qc_dfj_pass2(const double *j3c, int64_t nao, int64_t naux, in
     QC_REQUIRE(ld % 2 == 0 && ld >= naux, "ld must be even and >= naux");
     QC_REQUIRE(((uintptr_t)j3c | (uintptr_t)coef) % 16 == 0, "j3c and coef must be 16-byte aligned");
     const int64_t npair = nao * (nao + 1) / 2;
+    prof_begin(PROF_DFJ_PASS2, as_stream(stream));
     dfj_pass2_kernel<<<NUM_SMS * 8, 256, 0, as_stream(stream)>>>(j3c, npair, naux, ld, coef, (int)nao, vj);
+    prof_end(as_stream(stream));
     QC_LAUNCHED(1);
     return 0;
 }

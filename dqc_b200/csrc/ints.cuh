@@ -447,7 +447,9 @@ static int int_launch_t(const IntClass &K, const IntArgs &A, cudaStream_t st) {
     const int64_t ntask = A.nbra * A.nket;
     const int64_t nblk = (ntask + GPC - 1) / GPC;
     QC_REQUIRE(nblk < 2147483647LL, "too many integral tasks in one launch");
+    prof_begin(PROF_INTS, st);
     int_dense_kernel<G, NACC><<<(unsigned)nblk, INT_THREADS, smem, st>>>(K, A);
+    prof_end(st);
     QC_LAUNCHED(1);
     return 0;
 }

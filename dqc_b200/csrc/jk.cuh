@@ -207,8 +207,10 @@ static int jk_launch_t(const JKClassPair &cp, const IntArgs &A, int rank, int wo
     if (mine <= 0) return 0;
     const int64_t nblk = (mine + GPC - 1) / GPC;
     QC_REQUIRE(nblk < 2147483647LL, "too many J/K work items in one launch");
+    prof_begin(PROF_JK, st);
     jk_kernel<G, NACC><<<(unsigned)nblk, INT_THREADS, smem, st>>>(cp.K, A, cp.d_work_off, cp.d_nket_of_bra, cp.nitems,
                                                                   rank, world);
+    prof_end(st);
     QC_LAUNCHED(1);
     return 0;
 }

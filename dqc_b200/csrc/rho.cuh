@@ -74,6 +74,7 @@ extern "C" int b200qc_rho(const double *ao, int64_t ngrid_ld, int64_t ao_ld, con
     QC_REQUIRE(ngrid_ld % GM_BM == 0 && ao_ld % GM_BN == 0, "ngrid_ld must be a multiple of 128 and ao_ld of 64");
     if (ngrid_ld == 0) return 0;
     const unsigned nblk = (unsigned)(ngrid_ld / GM_BM);
+    prof_begin(PROF_RHO, as_stream(stream));
     if (grad) {
         QC_CHECK(cudaFuncSetAttribute(rho_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
         rho_kernel<4><<<nblk, GM_THREADS, GM_SMEM_BYTES, as_stream(stream)>>>(ao, ngrid_ld, ao_ld, dm, rho, grad);
@@ -81,6 +82,7 @@ extern "C" int b200qc_rho(const double *ao, int64_t ngrid_ld, int64_t ao_ld, con
         QC_CHECK(cudaFuncSetAttribute(rho_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
         rho_kernel<1><<<nblk, GM_THREADS, GM_SMEM_BYTES, as_stream(stream)>>>(ao, ngrid_ld, ao_ld, dm, rho, grad);
     }
+    prof_end(as_stream(stream));
     QC_LAUNCHED(1);
     return 0;
 }

@@ -11,6 +11,37 @@ extern "C" const char *b200qc_last_error(void) { return g_last_error.c_str(); }
 extern "C" int b200qc_version(void) { return 100; }
 extern "C" int64_t b200qc_launch_count(void) { return g_launch_count; }
 
+extern "C" int b200qc_profile(int on) {
+    for (ProfRec &r : g_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return 0;
+}
+extern "C" int b200qc_profile_nkernels(void) { return PROF_N; }
+extern "C" const char *b200qc_profile_name(int id) { return (id >= 0 && id < PROF_N) ? g_prof_names[id] : ""; }
+// ms_total / counts: PROF_N entries each; synchronises the device, then clears the records
+extern "C" int b200qc_profile_read(double *ms_total, int64_t *counts) {
+    QC_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < PROF_N; i++) {
+        ms_total[i] = 0.0;
+        counts[i] = 0;
+    }
+    for (ProfRec &r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ms_total[r.id] += ms;
+            counts[r.id]++;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return 0;
+}
+
 namespace {
 double h_binom(int n, int k) {
     if (k < 0 || k > n) return 0.0;

@@ -103,20 +103,26 @@ extern "C" int b200qc_vxc_mat(const double *ao, int64_t ngrid_ld, int64_t ao_ld,
     double *vb = work, *partial = work + ngrid_ld * ao_ld;
     const int wpb = 8;
     const unsigned nb1 = (unsigned)((ngrid_ld + wpb - 1) / wpb);
+    prof_begin(PROF_VXC_VB, st);
     if (vgrad)
         vxc_vb_kernel<4><<<nb1, wpb * 32, 0, st>>>(ao, ngrid_ld, ao_ld, weights, vrho, vgrad, vb);
     else
         vxc_vb_kernel<1><<<nb1, wpb * 32, 0, st>>>(ao, ngrid_ld, ao_ld, weights, vrho, vgrad, vb);
+    prof_end(st);
     QC_LAUNCHED(1);
     const int nsplit = vxc_nsplit(ngrid_ld, ao_ld);
     int64_t rows = (ngrid_ld + nsplit - 1) / nsplit;
     rows = (rows + GM_BK - 1) / GM_BK * GM_BK;
     dim3 grid((unsigned)(ao_ld / GM_BN), (unsigned)((ao_ld + GM_BM - 1) / GM_BM), (unsigned)nsplit);
     QC_CHECK(cudaFuncSetAttribute(vxc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
+    prof_begin(PROF_VXC_GEMM, st);
     vxc_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, st>>>(ao, vb, ao_ld, rows, ngrid_ld, partial);
+    prof_end(st);
     QC_LAUNCHED(1);
     const int64_t n = ao_ld * ao_ld;
+    prof_begin(PROF_VXC_REDUCE, st);
     slab_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, nsplit, n, mat);
+    prof_end(st);
     QC_LAUNCHED(1);
     return 0;
 }

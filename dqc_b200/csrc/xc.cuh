@@ -293,8 +293,10 @@ extern "C" int b200qc_xc_unpol(int nterm, const int *h_func_ids, const double *h
     if (int rc = xc_pack_terms(nterm, h_func_ids, h_coefs, t, gga)) return rc;
     QC_REQUIRE(!gga || grad != nullptr, "GGA functional needs the density gradient");
     if (n == 0) return 0;
+    prof_begin(PROF_XC, as_stream(stream));
     xc_unpol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(t, n, ld, rho, grad, edens, vrho,
                                                                                gga ? vgrad : nullptr);
+    prof_end(as_stream(stream));
     QC_LAUNCHED(1);
     if (!gga && vgrad) QC_CHECK(cudaMemsetAsync(vgrad, 0, sizeof(double) * 3 * ld, as_stream(stream)));
     return 0;
@@ -308,8 +310,10 @@ extern "C" int b200qc_xc_pol(int nterm, const int *h_func_ids, const double *h_c
     if (int rc = xc_pack_terms(nterm, h_func_ids, h_coefs, t, gga)) return rc;
     QC_REQUIRE(!gga || grad != nullptr, "GGA functional needs the density gradient");
     if (n == 0) return 0;
+    prof_begin(PROF_XC, as_stream(stream));
     xc_pol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(t, n, ld, rho, gga ? grad : nullptr,
                                                                              edens, vrho, gga ? vgrad : nullptr);
+    prof_end(as_stream(stream));
     QC_LAUNCHED(1);
     if (!gga && vgrad) QC_CHECK(cudaMemsetAsync(vgrad, 0, sizeof(double) * 6 * ld, as_stream(stream)));
     return 0;

@@ -28,6 +28,16 @@ int b200qc_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t b200qc_launch_count(void);
 
+/* per-kernel device timing for the benchmark: enable, run, read (ms_total / counts hold
+ * b200qc_profile_nkernels() entries, names from b200qc_profile_name); read synchronises */
+int b200qc_profile(int on);
+int b200qc_profile_nkernels(void);
+const char *b200qc_profile_name(int id);
+int b200qc_profile_read(double *h_ms_total, int64_t *h_counts);
+/* measured fp64 tensor-pipe (DMMA m8n8k4) peak of this device in TFLOP/s: the roofline
+ * denominator of K2 / K4 (MEASURED_PEAKS.json has no fp64 entry).  scratch: >= 1 double (device) */
+int b200qc_peak_fp64_dmma(int iters, double *scratch, double *h_tflops, void *stream);
+
 /* ---- basis / tables ------------------------------------------------------------------ */
 /* Replaces the (atm, bas, env) argument pack every dqclibs call receives
  * (molintor.py:629-638, gtoeval.py:219-233) and CINTcgto_spheric (lcintwrap.py:376-383):
