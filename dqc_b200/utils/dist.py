@@ -38,12 +38,15 @@ class ParallelContext(object):
         return out
 
     def allgather_cat(self, t: torch.Tensor, sizes: List[int]) -> torch.Tensor:
-        """Concatenate the per-rank 1-D slices (sizes known to everyone)."""
+        """Concatenate the per-rank 1-D slices (sizes known to everyone, possibly uneven).  Done as
+        a sum of zero-padded full-length vectors: one collective, and exact (x + 0 == x)."""
         if self.world == 1:
             return t
-        bufs = [torch.empty(n, dtype=t.dtype, device=t.device) for n in sizes]
-        dist.all_gather(bufs, t.contiguous(), group=self.group)
-        return torch.cat(bufs)
+        off = sum(sizes[:self.rank])
+        full = torch.zeros(sum(sizes), dtype=t.dtype, device=t.device)
+        full[off:off + sizes[self.rank]] = t
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+        return full
 
 
 _default = None
