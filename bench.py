@@ -333,13 +333,18 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     dmma_peak = _lib.peak_fp64_dmma(20000)
-    ngl_local, ld = (h._ngl, h._ld) if xc is not None else (0, 0)
+    gb = h._gb if xc is not None else None
     ncomp = 4 if (xc is not None and h.xcfamily == 2) else 1
+    xc_flops = gb.flops_per_pass if gb is not None else 0.0      # 2 * sum_sb SBP * nsp^2 (K2 and K4 GEMM each)
+    if gb is not None:
+        config.update(sb_points=gb.sbp, ao_screen=gb.eps, kept_ao_fraction=round(gb.kept_fraction, 4),
+                      ao_resident_gb=round(gb.ao_bytes / 1e9, 2),
+                      dense_equiv_flops_per_pass=2.0 * ngrid * h._nao_ao ** 2 / world)
     kern = {k: {"launches": c, "ms_per_launch": ms / c} for k, (c, ms) in prof.items()}
     dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
     roofline = None
     if dominant in ("vxc_gemm_kernel", "rho_kernel"):
-        flops = 2.0 * ngl_local * ld * ld          # per launch (2 ngrid nao^2, padded sizes)
+        flops = xc_flops                           # per launch: 2 * SBP * nsp^2 summed over this rank's superblocks
         ach = flops / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e12
         roofline = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
                     "frac": ach / dmma_peak, "traffic": None,
@@ -365,12 +370,12 @@ def main():
             extra[k] = {"GB/s": nb / (kern[k]["ms_per_launch"] * 1e-3) / 1e9, "frac_of_hbm": nb / (
                 kern[k]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     if "vxc_vb_kernel" in kern:
-        nb = (ncomp + 1) * ngl_local * ld * 8.0
+        nb = (ncomp + 1) * gb.ao_bytes / ncomp
         extra["vxc_vb_kernel"] = {"GB/s": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9,
                                   "frac_of_hbm": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     for k in ("rho_kernel", "vxc_gemm_kernel"):
         if k in kern:
-            fl = 2.0 * ngl_local * ld * ld
+            fl = xc_flops
             extra[k] = {"TFLOP/s": fl / (kern[k]["ms_per_launch"] * 1e-3) / 1e12,
                         "frac_of_fp64_dmma": fl / (kern[k]["ms_per_launch"] * 1e-3) / 1e12 / dmma_peak}
 

@@ -54,6 +54,17 @@ _SIGS = {
     "b200qc_vxc_mat": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p]),
+    "b200qc_ao_screen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_eval_gto_sb": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_rho_sb": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_vxc_sb": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int1e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int2c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -447,3 +458,118 @@ def dfj_pass2(j3c_packed, nao, naux, coef):
     vj = torch.empty((nao, nao), dtype=torch.float64, device=coef.device)
     _check(lib.b200qc_dfj_pass2(_ptr(j3c_packed), nao, naux, ld, _ptr(cpad), _ptr(vj), _stream()), "dfj_pass2")
     return vj
+
+
+# ------------------------------------------------------------------------------------------
+# block-sparse grid path (csrc/xc_sb.cuh)
+
+SB_DTYPE = np.dtype([("ao_off", np.int64), ("d_off", np.int64), ("nsp", np.int32), ("idx_off", np.int32),
+                     ("shell_off", np.int32), ("nshell", np.int32)])
+
+
+def ao_screen(basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, sbp: int, eps: float, deriv: int):
+    """(nsb, nshell) uint8: 1 where the shell's envelope can exceed eps somewhere on the superblock."""
+    lib = load()
+    ngrid = coords.shape[0]
+    nsb = (ngrid + sbp - 1) // sbp
+    flags = torch.zeros((nsb, sh1 - sh0), dtype=torch.uint8, device=coords.device)
+    _check(lib.b200qc_ao_screen(basis.handle, sh0, sh1, _ptr(coords.contiguous()), ngrid, sbp, float(eps), deriv,
+                                _ptr(flags), _stream()), "ao_screen")
+    return flags
+
+
+class GridBlocks(object):
+    """Superblock decomposition of a grid slice: screening flags -> compact AO storage + descriptors.
+
+    Built once per geometry (HamiltonCGTO.setup_grid); ``rho`` and ``vxc_mat`` are the per-iteration
+    kernels (K2 / K4) on it."""
+
+    def __init__(self, basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, weights: torch.Tensor,
+                 deriv: int, sbp: int = 1024, eps: float = 1e-12, flags: Optional[np.ndarray] = None):
+        lib = load()
+        dev = coords.device
+        self.basis, self.sh0, self.sh1 = basis, sh0, sh1
+        self.ngrid = int(coords.shape[0])
+        self.sbp, self.deriv, self.eps = int(sbp), int(deriv), float(eps)
+        self.ncomp = 4 if deriv else 1
+        self.nsb = (self.ngrid + self.sbp - 1) // self.sbp
+        self.ngl = self.nsb * self.sbp
+        self.nao = basis.nao(sh0, sh1)
+        coords = coords.contiguous()
+        if flags is None:
+            flags = ao_screen(basis, sh0, sh1, coords, self.sbp, eps, deriv).cpu().numpy()
+        kept = flags.astype(bool)
+        nshell = sh1 - sh0
+        loc = basis.ao_loc[sh0:sh1 + 1].astype(np.int64) - int(basis.ao_loc[sh0])
+        sizes = (loc[1:] - loc[:-1]).astype(np.int64)
+        ksz = kept * sizes[None, :]
+        nsig = ksz.sum(1)
+        nsp = np.maximum(64, (nsig + 63) // 64 * 64).astype(np.int64)
+        nsh = kept.sum(1).astype(np.int64)
+        excl = lambda a: np.concatenate([[0], np.cumsum(a)[:-1]]).astype(np.int64)
+        sb_i, sh_i = np.nonzero(kept)
+        col = (np.cumsum(ksz, axis=1) - ksz)[kept]                       # compact first column of each kept shell
+        idx_off, shell_off = excl(nsp), excl(nsh)
+        ao_off, d_off, vb_off = excl(self.ncomp * self.sbp * nsp), excl(nsp * nsp), excl(self.sbp * nsp)
+        idx = np.full(int(nsp.sum()), self.nao, dtype=np.int32)
+        rep = sizes[sh_i]
+        if rep.sum() > 0:
+            start = np.repeat(idx_off[sb_i] + col, rep)
+            within = np.arange(int(rep.sum()), dtype=np.int64) - np.repeat(excl(rep), rep)
+            idx[start + within] = (np.repeat(loc[sh_i], rep) + within).astype(np.int32)
+        desc = np.zeros(self.nsb, dtype=SB_DTYPE)
+        desc["ao_off"], desc["d_off"], desc["nsp"] = ao_off, d_off, nsp
+        desc["idx_off"], desc["shell_off"], desc["nshell"] = idx_off, shell_off, nsh
+        self.nsp = nsp
+        self.max_nsp = int(nsp.max()) if self.nsb else 64
+        self.kept_fraction = float(nsig.sum()) / max(1, self.nao * self.nsb)
+        self.flops_per_pass = float(2.0 * self.sbp * (nsp.astype(np.float64) ** 2).sum())   # K2 == K4 GEMM flops
+        self.ao_bytes = float(self.ncomp * self.sbp * nsp.sum() * 8)
+        tt = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(dev)
+        self.d_desc = torch.as_tensor(desc.view(np.uint8)).to(dev)
+        self.d_idx = tt(idx, torch.int32)
+        self.d_shell_ids = tt(sh_i + sh0, torch.int32)
+        self.d_shell_col = tt(col, torch.int32)
+        self.d_vb_off = tt(vb_off, torch.int64)
+        self.ao = torch.zeros(int(self.ncomp * self.sbp * nsp.sum()), dtype=torch.float64, device=dev)
+        self.dsb = torch.empty(int((nsp * nsp).sum()), dtype=torch.float64, device=dev)
+        self.vb = torch.empty(int(self.sbp * nsp.sum()), dtype=torch.float64, device=dev)
+        self.w = torch.zeros(self.ngl, dtype=torch.float64, device=dev)
+        self.w[:self.ngrid] = weights
+        if self.nsb:
+            _check(lib.b200qc_eval_gto_sb(basis.handle, deriv, _ptr(coords), self.ngrid, self.sbp, self.nsb,
+                                          _ptr(self.d_desc), _ptr(self.d_shell_ids), _ptr(self.d_shell_col),
+                                          _ptr(self.ao), _stream()), "eval_gto_sb")
+
+    def rho(self, dm: torch.Tensor, with_grad: bool):
+        """dm (nao, nao) symmetric AO-basis density -> rho (ngl,), grad (3, ngl) | None (zero in the padding)."""
+        lib = load()
+        assert dm.shape == (self.nao, self.nao) and (not with_grad or self.deriv)
+        r = torch.empty(self.ngl, dtype=torch.float64, device=dm.device)
+        g = torch.empty((3, self.ngl), dtype=torch.float64, device=dm.device) if with_grad else None
+        _check(lib.b200qc_rho_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
+                                 _ptr(dm.contiguous()), self.nao, _ptr(self.dsb), _ptr(r), _ptr(g), _stream()), "rho_sb")
+        return r, g
+
+    def vxc_mat(self, vrho: torch.Tensor, vgrad: Optional[torch.Tensor]) -> torch.Tensor:
+        """vrho (ngl,), vgrad (3, ngl) | None -> (nao, nao) = sum_g w phi^T (vrho phi + 2 vgrad . grad phi)."""
+        lib = load()
+        assert vrho.shape[0] == self.ngl and (vgrad is None or self.deriv)
+        mat = torch.empty((self.nao, self.nao), dtype=torch.float64, device=vrho.device)
+        _check(lib.b200qc_vxc_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
+                                 _ptr(self.w), _ptr(vrho.contiguous()), _ptr(vgrad), self.nao, _ptr(self.d_vb_off),
+                                 _ptr(self.vb), _ptr(mat), _stream()), "vxc_sb")
+        return mat
+
+    def dense_ao(self) -> torch.Tensor:
+        """(ncomp, ngrid, nao) dense AO values rebuilt from the compact storage (API parity / tests only)."""
+        out = torch.zeros((self.ncomp, self.ngrid, self.nao + 1), dtype=torch.float64, device=self.ao.device)
+        idx = self.d_idx.long()
+        desc = self.d_desc.cpu().numpy().view(SB_DTYPE)
+        for sb in range(self.nsb):
+            n, a0, i0 = int(desc["nsp"][sb]), int(desc["ao_off"][sb]), int(desc["idx_off"][sb])
+            blk = self.ao[a0:a0 + self.ncomp * self.sbp * n].reshape(self.ncomp, self.sbp, n)
+            r0 = sb * self.sbp
+            r1 = min(r0 + self.sbp, self.ngrid)
+            out[:, r0:r1, idx[i0:i0 + n]] = blk[:, :r1 - r0, :]
+        return out[:, :, :self.nao]

@@ -11,10 +11,10 @@ where the numbers come from:
   dense (ij|kl) nao^4 + convert4, :129-132            never stored: Schwarz-screened direct J/K plan
   J, K einsums over nao^4, :204-241                   b200qc_jkplan_run (quartets digested on the fly)
   DF: dfmol.py                                        dqc_b200/df/dfmol.py (packed (ij|P), two GEMV passes)
-  AO / grad AO on the grid, :168-186                  b200qc_eval_gto into one padded resident buffer
-  _dm2densinfo chunk loop, :371-443                   b200qc_rho (fp64 tensor-pipe tiles, fused row dots)
+  AO / grad AO on the grid, :168-186                  b200qc_eval_gto_sb: compact per-superblock storage
+  _dm2densinfo chunk loop, :371-443                   b200qc_rho_sb (fp64 tensor-pipe tiles, fused row dots)
   libxc, dqc/xc/libxc.py                              b200qc_xc_unpol / _pol
-  _get_vxc_from_potinfo chunk loop, :445-495          b200qc_vxc_mat (split-K tensor-pipe GEMM)
+  _get_vxc_from_potinfo chunk loop, :445-495          b200qc_vxc_sb (per-superblock tensor-pipe GEMM)
 
 Multi-GPU (one process per GPU): each rank keeps the AO values of a contiguous slice of the grid,
 every n-th J/K work item and a slice of the aux shells; the partial AO-basis matrices are summed by
@@ -22,6 +22,7 @@ one packed all-reduce in ``get_fock_2e`` (or one per call of the individual ``ge
 There is no CPU fallback: constructing this class without a CUDA device raises.
 """
 from typing import List, Optional, Tuple, Union
+import numpy as np
 import torch
 from dqc_b200 import _lib
 from dqc_b200.df.dfmol import DFMol
@@ -31,6 +32,7 @@ from dqc_b200.hamilton.intor import molintor as intor
 from dqc_b200.hamilton.intor import gtoeval
 from dqc_b200.hamilton.intor.lcintwrap import LibcintWrapper
 from dqc_b200.hamilton.orbconverter import OrbitalOrthogonalizer, IdentityOrbConverter
+from dqc_b200.utils.config import config
 from dqc_b200.utils.datastruct import AtomCGTOBasis, ValGrad, SpinParam, DensityFitInfo
 from dqc_b200.utils.dist import ParallelContext, get_context, split_rows
 from dqc_b200.utils.linop import LinearOperator
@@ -139,34 +141,42 @@ class HamiltonCGTO(BaseHamilton):
             raise NotImplementedError("meta-GGA functionals are not on the B200 Fock-build path yet")
         self.grid = grid
         assert grid.coord_type == "cart"
-        rgrid_all = grid.get_rgrid().to(self.device)
+        rgrid_all = grid.get_rgrid().to(self.device).to(torch.float64).contiguous()
         dvol_all = grid.get_dvolume().to(self.device)
         self._ngrid_total = rgrid_all.shape[0]
-        # this rank's contiguous slice of the grid (boundaries on the 128-point CTA tile)
-        g0, g1 = split_rows(self._ngrid_total, self._ctx.world, self._ctx.rank, _lib.GRID_ALIGN)
-        self._grid_slice = (g0, g1)
-        self.rgrid = rgrid_all[g0:g1].contiguous()
-        self.dvolume = dvol_all[g0:g1].contiguous()
-        ng = g1 - g0
+        deriv = 1 if self.xcfamily == 2 else 0
+        sbp, eps = config.SB_POINTS, config.AO_SCREEN
+        s0, s1 = self.libcint_wrapper.shell_idxs
         logger.log("Calculating the basis values in the grid")
         with torch.cuda.device(self.device):
-            # one buffer (ncomp, ngrid_ld, ao_ld): component 0 = values, 1..3 = gradient (GGA)
-            self._ao = gtoeval.eval_gto_padded(self.libcint_wrapper, self.rgrid, 1 if self.xcfamily == 2 else 0)
-        self._ngl, self._ld = self._ao.shape[1], self._ao.shape[2]
-        self._wpad = torch.zeros(self._ngl, dtype=torch.float64, device=self.device)
-        self._wpad[:ng] = self.dvolume
+            # superblock screening on the whole grid (cheap), then a contiguous range of superblocks per
+            # rank balanced by the contraction cost nsp^2; each rank evaluates and keeps only its AOs
+            flags = _lib.ao_screen(self._devbasis, s0, s1, rgrid_all, sbp, eps, deriv).cpu().numpy()
+            sizes = np.diff(self._devbasis.ao_loc[s0:s1 + 1]).astype(np.float64)
+            nsp = np.maximum(64.0, np.ceil((flags.astype(np.float64) * sizes[None, :]).sum(1) / 64.0) * 64.0)
+            csum = np.concatenate([[0.0], np.cumsum(nsp * nsp + 64.0 * nsp)])
+            world, rank = self._ctx.world, self._ctx.rank
+            bounds = [int(np.searchsorted(csum, csum[-1] * r / world)) for r in range(world)] + [len(nsp)]
+            bounds = [min(max(b, 0), len(nsp)) for b in bounds]
+            sb_lo, sb_hi = bounds[rank], max(bounds[rank], bounds[rank + 1])
+            g0, g1 = min(sb_lo * sbp, self._ngrid_total), min(sb_hi * sbp, self._ngrid_total)
+            self._grid_slice = (g0, g1)
+            self.rgrid = rgrid_all[g0:g1].contiguous()
+            self.dvolume = dvol_all[g0:g1].contiguous()
+            self._gb = _lib.GridBlocks(self._devbasis, s0, s1, self.rgrid, self.dvolume, deriv, sbp, eps,
+                                       flags=flags[sb_lo:sb_hi])
         self.is_grid_set = True
         self.is_ao_set = True
         self.is_grad_ao_set = self.xcfamily == 2
 
-    # the reference's attribute names, materialised on demand (views of the padded buffer)
+    # the reference's attribute names, rebuilt on demand from the compact storage (API parity only)
     @property
     def basis(self) -> torch.Tensor:
-        return self._ao[0, :self.rgrid.shape[0], :self._nao_ao]
+        return self._gb.dense_ao()[0]
 
     @property
     def grad_basis(self) -> torch.Tensor:
-        return self._ao[1:, :self.rgrid.shape[0], :self._nao_ao]
+        return self._gb.dense_ao()[1:]
 
     @property
     def basis_dvolume(self) -> torch.Tensor:
@@ -222,16 +232,14 @@ class HamiltonCGTO(BaseHamilton):
 
     def _vmat_ao_partial(self, vrho: torch.Tensor, vgrad: Optional[torch.Tensor]) -> torch.Tensor:
         """sum_g w phi^T (vrho phi + 2 vgrad . grad phi) over this rank's grid slice, (nao_ao, nao_ao)."""
-        ng, ngl = self.rgrid.shape[0], self._ngl
+        ng, ngl = self.rgrid.shape[0], self._gb.ngl
         vr = torch.zeros(ngl, dtype=torch.float64, device=self.device)
         vr[:ng] = vrho
         vg = None
         if vgrad is not None:
             vg = torch.zeros(3, ngl, dtype=torch.float64, device=self.device)
             vg[:, :ng] = vgrad
-        ao = self._ao if vg is not None else self._ao[:1]
-        mat = _lib.vxc_mat(ao, self._wpad, vr, vg)
-        return mat[:self._nao_ao, :self._nao_ao]
+        return self._gb.vxc_mat(vr, vg)
 
     def get_vext(self, vext: torch.Tensor) -> LinearOperator:
         # vext: (*BR, ngrid) sampled on the FULL grid
@@ -359,12 +367,10 @@ class HamiltonCGTO(BaseHamilton):
             raise RuntimeError("Please call `setup_grid(grid, xc)` to call this function")
         bshape, dm2 = self._flat(dm)
         dmdmt = self._orthozer.unconvert_dm(_symm(dm2))
-        ng, ld, gga = self.rgrid.shape[0], self._ld, self.xcfamily == 2
+        ng, gga = self.rgrid.shape[0], self.xcfamily == 2
         vals, grads = [], []
         for b in range(dmdmt.shape[0]):
-            dpad = torch.zeros(ld, ld, dtype=torch.float64, device=self.device)
-            dpad[:self._nao_ao, :self._nao_ao] = dmdmt[b]
-            rho, grad = _lib.rho(self._ao, dpad, gga)
+            rho, grad = self._gb.rho(dmdmt[b].contiguous(), gga)
             vals.append(rho[:ng])
             if gga:
                 grads.append(grad[:, :ng])

@@ -12,10 +12,11 @@ class _Config:
     THRESHOLD_MEMORY: int = 10 * 1024 ** 3
     CHUNK_MEMORY: int = 16 * 1024 ** 2
     VERBOSE: int = 0
-    # grid points per block handled by one CTA pass in the XC kernels
-    GRID_BLOCK: int = 128
-    # integral screening threshold on the primitive-pair prefactor (0 => none, like the reference)
-    INT_SCREEN: float = 0.0
+    # grid points per superblock of the block-sparse XC path (multiple of 128)
+    SB_POINTS: int = 1024
+    # a shell is dropped from a superblock when its envelope stays below this on every point of it
+    # (0 keeps every shell everywhere, like the reference's non0tab = 1)
+    AO_SCREEN: float = 1e-12
 
 
 config = _Config()

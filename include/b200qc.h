@@ -94,6 +94,30 @@ int64_t b200qc_vxc_worksize(int64_t ngrid_ld, int64_t ao_ld);
 int b200qc_vxc_mat(const double *ao, int64_t ngrid_ld, int64_t ao_ld, const double *weights,
                    const double *vrho, const double *vgrad, double *mat, double *work, void *stream);
 
+/* ---- block-sparse grid path ("superblocks") -- the production form of K1 / K2 / K4 -------- */
+/* The grid is cut into superblocks (SB) of `sbp` consecutive points (multiple of 128); each SB keeps
+ * only the shells whose envelope can exceed eps on it (the reference keeps everything: non0tab = 1,
+ * gtoeval.py:211; eps = 0 reproduces that).  Per-SB descriptor (32 bytes, device array):
+ *   { int64 ao_off; int64 d_off; int32 nsp; int32 idx_off; int32 shell_off; int32 nshell; }
+ * ao_off: start of the SB's compact AO block [ncomp][sbp][nsp] (doubles); d_off: start of its gathered
+ * density (nsp x nsp) in the scratch; nsp: kept AOs padded to a multiple of 64; idx: AO index of every
+ * compact column (padding = nao); shell_ids / shell_col: kept shells and their first compact column. */
+/* flags: (nsb, sh1 - sh0) bytes, 1 = shell kept on that SB; deriv = 1 also bounds the gradient */
+int b200qc_ao_screen(const b200qc_basis *basis, int sh0, int sh1, const double *coords, int64_t ngrid, int sbp,
+                     double eps, int deriv, unsigned char *flags, void *stream);
+/* compact AO values (pre-zeroed buffer); same arithmetic as b200qc_eval_gto */
+int b200qc_eval_gto_sb(const b200qc_basis *basis, int deriv, const double *coords, int64_t ngrid, int sbp, int nsb,
+                       const void *sbdesc, const int *shell_ids, const int *shell_col, double *ao, void *stream);
+/* rho (nsb * sbp), grad (3, nsb * sbp) or NULL from dm (nao, nao) symmetric AO-basis density
+ * (hcgto.py:371-443); dsb: scratch of sum_sb nsp^2 doubles */
+int b200qc_rho_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                  const double *dm, int nao, double *dsb, double *rho, double *grad, void *stream);
+/* mat (nao, nao) = sum_g w phi^T (vrho phi + 2 vgrad . grad phi) (hcgto.py:445-495), overwritten;
+ * vb: scratch of sum_sb sbp * nsp doubles with per-SB offsets vb_off (device int64) */
+int b200qc_vxc_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                  const double *weights, const double *vrho, const double *vgrad, int nao, const int64_t *vb_off,
+                  double *vb, double *mat, void *stream);
+
 /* ---- one- and two-electron integrals (Rys quadrature) ---------------------------------- */
 /* kind: 0 int1e_ovlp, 1 int1e_kin, 2 int1e_nuc, 3 int1e_rinv (origin rinv_orig[3], host).
  * Replaces GTOint2c (molintor.py:624-644).  out: (nao_i, nao_j) row-major for shells

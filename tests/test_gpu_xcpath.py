@@ -205,3 +205,48 @@ def test_gemm_engine_large_random(cuda):
     mat1 = _lib.vxc_mat(ao[:1].contiguous(), w, vr, None)
     ref1 = (ao[0] * w[:, None]).T @ (vr[:, None] * ao[0])
     assert float((mat1 - ref1).abs().max() / ref1.abs().max()) < 1e-13
+
+
+@pytest.mark.parametrize("eps,sbp", [(0.0, 1024), (1e-12, 1024), (1e-12, 128), (1e-8, 256)])
+@pytest.mark.parametrize("gga", [False, True])
+def test_superblock_path_matches_dense_kernels(cuda, eps, sbp, gga):
+    """Block-sparse K1/K2/K4 (GridBlocks) against the dense kernels on a spread-out molecule where the
+    screening really drops shells: identical at eps = 0, within O(eps) otherwise."""
+    from dqc_b200 import _lib
+    from dqc_b200.grid.factory import get_predefined_grid
+    zs = [6, 1, 8, 7, 1, 6]
+    pos = [[0.0, 0.0, 0.0], [1.9, 0.3, -0.4], [9.0, 1.0, 0.5], [-8.0, -6.0, 2.0], [14.0, -3.0, -1.0], [0.5, 11.0, 7.0]]
+    w, _ = util.make_wrapper(zs, pos, "def2-svp")
+    nao, nb = w.nao(), len(w)
+    grid = get_predefined_grid("sg2", zs, torch.tensor(pos, dtype=torch.float64, device=cuda), device=cuda)
+    xyz, wts = grid.get_rgrid()[::7].contiguous(), grid.get_dvolume()[::7].contiguous()   # ~6 k points, atom-ordered
+    ng = xyz.shape[0]
+    db = w.device_basis(cuda)
+    gb = _lib.GridBlocks(db, 0, nb, xyz, wts, 1 if gga else 0, sbp=sbp, eps=eps)
+    if eps == 0.0:
+        assert gb.kept_fraction == 1.0
+    else:
+        assert gb.kept_fraction < 0.95           # the screening is exercised
+    ao = _lib.eval_gto(db, 0, nb, xyz, 1 if gga else 0)
+    tol = 1e-13 if eps == 0.0 else 200 * eps
+    dense = gb.dense_ao()
+    assert float((dense - ao[:, :ng, :nao]).abs().max()) <= (0.0 if eps == 0.0 else 2 * eps * 10)
+    dm = util.seeded_dm(nao, nao // 3, seed=4).to(cuda)
+    rho_d, grad_d = _lib.rho(ao, _pad_dm(dm, ao.shape[2], cuda), gga)
+    rho_s, grad_s = gb.rho(dm, gga)
+    assert float((rho_s[:ng] - rho_d[:ng]).abs().max()) < tol * 10
+    assert float(rho_s[ng:].abs().max()) == 0.0 if gb.ngl > ng else True
+    if gga:
+        assert float((grad_s[:, :ng] - grad_d[:, :ng]).abs().max()) < tol * 100
+    g = torch.Generator().manual_seed(1)
+    vr = torch.randn(ng, dtype=torch.float64, generator=g).to(cuda)
+    vg = torch.randn(3, ng, dtype=torch.float64, generator=g).to(cuda) if gga else None
+
+    def pad(t, n):
+        out = torch.zeros(*t.shape[:-1], n, dtype=torch.float64, device=cuda)
+        out[..., :ng] = t
+        return out
+    m_d = _lib.vxc_mat(ao, pad(wts, ao.shape[1]), pad(vr, ao.shape[1]), pad(vg, ao.shape[1]) if gga else None)[:nao, :nao]
+    m_s = gb.vxc_mat(pad(vr, gb.ngl), pad(vg, gb.ngl) if gga else None)
+    scale = float(m_d.abs().max())
+    assert float((m_s - m_d).abs().max()) < max(tol * 100, 1e-12 * scale)
