@@ -216,7 +216,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     sysname, basis, xc, aux, exx, gridname = WORKLOADS[args.workload]
     config = {"workload": "%s: %s / %s / xc=%s / %s / grid %s" % (
-        args.workload, sysname, basis, xc, ("DF-J aux=" + aux) if aux else "direct 4c J/K", gridname),
+        args.workload, sysname, basis, xc, ("DF-J aux=" + aux) if aux else "4-centre J/K", gridname),
         "exx_fraction": exx, "l2_policy": "inputs (AO values, packed (ij|P)) larger than L2; no flush",
         "parallelism": "grid rows + aux shells (or J/K work items) sharded over %d GPU(s), one packed all-reduce" % world}
 
@@ -260,6 +260,10 @@ def main():
     nocc = max(1, int(sum(zs)) // 2)
     dm = seeded_dm(nao, min(nocc, nao), dev)
     ngrid = int(mol.get_grid().get_rgrid().shape[0]) if xc is not None else 0
+    if aux is None:
+        config["jk_engine"] = type(h._jkplan).__name__ + (
+            " (both dense (ij|kl) layouts resident in HBM, J/K = GEMVs)" if type(h._jkplan).__name__ == "StoredERI"
+            else " (Schwarz-screened direct build, %d unique shell quartets)" % h._jkplan.nquartets)
     config.update(nao=nao, nao_ao=h._nao_ao, ngrid=ngrid, natoms=len(zs),
                   naux=(h.df._naux if h.df is not None else None), setup_s=round(t_setup, 2))
 
@@ -354,6 +358,12 @@ def main():
                     "algorithmic_flops_per_launch": flops}
     elif dominant in ("dfj_pass1_kernel", "dfj_pass2_kernel"):
         nb = h.df._j3c_packed.numel() * 8.0
+        ach = nb / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_launch": nb}
+    elif dominant == "gemv_rows_kernel":
+        nb = 8.0 * h._nao_ao ** 4
         ach = nb / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,

@@ -72,6 +72,10 @@ _SIGS = {
     "b200qc_int2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int3c2e_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                              ctypes.c_void_p]),
+    "b200qc_eri_store": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
+    "b200qc_gemv": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_jkplan_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                             ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_jkplan_nquartets": (ctypes.c_int64, [ctypes.c_void_p]),
@@ -371,6 +375,43 @@ def int3c2e_packed(basis: DeviceBasis, shls, ld: Optional[int] = None):
     out = torch.zeros((nao * (nao + 1) // 2, ld), dtype=torch.float64, device=basis.device)
     _check(lib.b200qc_int3c2e_packed(basis.handle, _np(sl), _ptr(out), ld, _stream()), "int3c2e_packed")
     return out
+
+
+class StoredERI(object):
+    """Both dense layouts of (ij|kl) resident in HBM (small molecules); J / K are HBM-bound GEMVs."""
+
+    def __init__(self, basis: DeviceBasis, sh0: int, sh1: int):
+        lib = load()
+        ensure_rys_table()
+        n = basis.nao(sh0, sh1)
+        self.nao = n
+        self.eri_j = torch.empty(n ** 4, dtype=torch.float64, device=basis.device)
+        self.eri_k = torch.empty(n ** 4, dtype=torch.float64, device=basis.device)
+        with torch.cuda.device(basis.device):
+            _check(lib.b200qc_eri_store(basis.handle, sh0, sh1, _ptr(self.eri_j), _ptr(self.eri_k), _stream()),
+                   "eri_store")
+
+    @staticmethod
+    def nbytes(nao: int) -> int:
+        return 2 * 8 * nao ** 4
+
+    def _gemv(self, A, dm):
+        lib = load()
+        n2 = self.nao * self.nao
+        ld = n2 + (n2 & 1)
+        if ld != n2:
+            raise B200QCError("stored-ERI GEMV needs an even nao^2")  # never hit: handled in run()
+        x = dm.reshape(-1).contiguous()
+        y = torch.empty(n2, dtype=torch.float64, device=dm.device)
+        _check(lib.b200qc_gemv(_ptr(A), n2, n2, n2, _ptr(x), _ptr(y), _stream()), "gemv")
+        return y.reshape(self.nao, self.nao)
+
+    def run(self, dm: torch.Tensor, with_j=True, with_k=True, rank=0, world=1):
+        """dm (nset, nao, nao) -> vj, vk (nset, nao, nao) (same contract as JKPlan.run; world must be 1)."""
+        assert world == 1
+        vj = torch.stack([self._gemv(self.eri_j, d) for d in dm]) if with_j else None
+        vk = torch.stack([self._gemv(self.eri_k, d) for d in dm]) if with_k else None
+        return vj, vk
 
 
 class JKPlan(object):

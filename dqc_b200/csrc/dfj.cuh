@@ -207,3 +207,48 @@ extern "C" int b200qc_pack_tril(const double *full, int64_t nao, int64_t naux, i
     QC_LAUNCHED(1);
     return 0;
 }
+
+// y[r] = sum_c A[r * ld + c] x[c]  -- the HBM-bound contraction of the stored-ERI regime
+// (J = eri_j . vec(D), K = eri_k . vec(D), hcgto.py:209,234); warp per row, two loads in flight.
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(const double *__restrict__ A, int64_t nrow, int64_t ncol, int64_t ld, const double *__restrict__ x,
+                 double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t nhalf = ncol / 2;
+    for (int64_t r = warp; r < nrow; r += nwarp) {
+        const double2 *row = reinterpret_cast<const double2 *>(A + r * ld);
+        const double2 *xv = reinterpret_cast<const double2 *>(x);
+        double s0 = 0.0, s1 = 0.0;
+        int64_t k = lane;
+        for (; k + 32 < nhalf; k += 64) {
+            const double2 v0 = __ldcs(row + k), v1 = __ldcs(row + k + 32);
+            const double2 c0 = __ldg(xv + k), c1 = __ldg(xv + k + 32);
+            s0 += v0.x * c0.x + v0.y * c0.y;
+            s1 += v1.x * c1.x + v1.y * c1.y;
+        }
+        for (; k < nhalf; k += 32) {
+            const double2 v0 = __ldcs(row + k);
+            const double2 c0 = __ldg(xv + k);
+            s0 += v0.x * c0.x + v0.y * c0.y;
+        }
+        double s = s0 + s1;
+        if ((ncol & 1) && lane == 0) s += A[r * ld + ncol - 1] * x[ncol - 1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[r] = s;
+    }
+}
+
+extern "C" int b200qc_gemv(const double *A, int64_t nrow, int64_t ncol, int64_t ld, const double *x, double *y,
+                           void *stream) {
+    QC_REQUIRE(ld % 2 == 0 && ld >= ncol, "ld must be even and >= ncol");
+    QC_REQUIRE(((uintptr_t)A | (uintptr_t)x) % 16 == 0, "A and x must be 16-byte aligned");
+    if (nrow == 0) return 0;
+    prof_begin(PROF_GEMV, as_stream(stream));
+    gemv_rows_kernel<<<NUM_SMS * 8, 256, 0, as_stream(stream)>>>(A, nrow, ncol, ld, x, y);
+    prof_end(as_stream(stream));
+    QC_LAUNCHED(1);
+    return 0;
+}

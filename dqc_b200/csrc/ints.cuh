@@ -31,6 +31,7 @@
 #define SINK_PACK3C 1     // out[pair(i >= j) * s2 + k], s2 = naux
 #define SINK_SCHWARZ 2    // out[ish * s0 + jsh] = sqrt(max |(ab|ab)|)  (bra == ket)
 #define SINK_JK 3         // digestion into J / K (jk.cuh)
+#define SINK_STORE_JK 4   // bra i >= j, ket k >= l: the 4 images into out[i][j][k][l] and out2[i][k][j][l]
 
 #define INT_THREADS 128
 #define INT_MAX_COMP 1312  // 32 lanes x 41 components
@@ -54,7 +55,7 @@ struct IntArgs {
     const int2 *bra, *ket;   // pair lists (second = -1: absent centre)
     int64_t nbra, nket;
     const double *charges;   // NUC: (ncharge, 4) = x, y, z, q   (value = sum_C q_C <a| 1/|r-C| |b>)
-    double *out;
+    double *out, *out2;
     int64_t s0, s1, s2, s3;  // dense strides / sink parameters
     int off[4];              // AO offset of each slot's slice start (subtracted before striding)
     // J/K sink
@@ -383,6 +384,26 @@ int_dense_kernel(const IntClass K, const IntArgs A) {
             const int a = r / n1;
             A.out[(ai + a) * A.s0 + (aj + b) * A.s1 + (ak + c) * A.s2 + (al + d) * A.s3] = blk[e];
         }
+    } else if (K.sink == SINK_STORE_JK) {
+        // stored-ERI regime: out = (ij|kl) as [i][j][k][l] (J layout), out2 = (ij|kl) as [i][k][j][l] (K layout)
+        const int64_t q1 = A.s2, q2 = q1 * q1, q3 = q2 * q1;   // strides of a dense nao^4 tensor
+        for (int e = lg; e < ntot; e += G) {
+            int r = e;
+            const int d = r % n3; r /= n3;
+            const int c = r % n2; r /= n2;
+            const int b = r % n1;
+            const int a = r / n1;
+            const int64_t I = ai + a, J = aj + b, Kk = ak + c, L = al + d;
+            const double v = blk[e];
+            A.out[I * q3 + J * q2 + Kk * q1 + L] = v;
+            A.out[J * q3 + I * q2 + Kk * q1 + L] = v;
+            A.out[I * q3 + J * q2 + L * q1 + Kk] = v;
+            A.out[J * q3 + I * q2 + L * q1 + Kk] = v;
+            A.out2[I * q3 + Kk * q2 + J * q1 + L] = v;
+            A.out2[J * q3 + Kk * q2 + I * q1 + L] = v;
+            A.out2[I * q3 + L * q2 + J * q1 + Kk] = v;
+            A.out2[J * q3 + L * q2 + I * q1 + Kk] = v;
+        }
     } else {  // SINK_PACK3C: i >= j only, k contiguous
         for (int e = lg; e < ntot; e += G) {
             int r = e;
@@ -676,6 +697,26 @@ extern "C" int b200qc_int2e(const b200qc_basis *basis, const int *sl, double *ou
     A.off[2] = basis->h_ao_loc[sl[4]];
     A.off[3] = basis->h_ao_loc[sl[6]];
     int rc = int_run_eri(basis, bra, ket, true, true, SINK_DENSE, A, st);
+    QC_CHECK(cudaStreamSynchronize(st));
+    return rc;
+}
+
+// Stored-ERI regime (small molecules): both dense layouts of (ij|kl) over shells [sh0, sh1) filled from
+// the quartets with i >= j, k >= l (4-fold symmetry).  eri_j[i][j][k][l] = eri_k[i][k][j][l] = (ij|kl).
+extern "C" int b200qc_eri_store(const b200qc_basis *basis, int sh0, int sh1, double *eri_j, double *eri_k,
+                                void *stream) {
+    if (int_require_ready(basis)) return 2;
+    QC_REQUIRE(0 <= sh0 && sh0 < sh1 && sh1 <= basis->nbas && eri_j && eri_k, "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    PairLists bra, ket;
+    make_pair_lists(basis, sh0, sh1, sh0, sh1, true, bra);
+    make_pair_lists(basis, sh0, sh1, sh0, sh1, true, ket);
+    IntArgs A = {};
+    A.out = eri_j;
+    A.out2 = eri_k;
+    A.s2 = basis->h_ao_loc[sh1] - basis->h_ao_loc[sh0];
+    for (int q = 0; q < 4; q++) A.off[q] = basis->h_ao_loc[sh0];
+    int rc = int_run_eri(basis, bra, ket, true, true, SINK_STORE_JK, A, st);
     QC_CHECK(cudaStreamSynchronize(st));
     return rc;
 }

@@ -119,9 +119,16 @@ class HamiltonCGTO(BaseHamilton):
             self.nucl_mat = nucl_mat
             self.kinnucl_mat = kin_mat + nucl_mat
             if self._df is None:
-                logger.log("Planning the direct electron-repulsion build")
                 s0, s1 = self.libcint_wrapper.shell_idxs
-                self._jkplan = _lib.JKPlan(self._devbasis, s0, s1, self._jk_thresh)
+                n = self._nao_ao
+                if self._ctx.world == 1 and n % 2 == 0 and _lib.StoredERI.nbytes(n) <= config.ERI_STORE_MAX_BYTES:
+                    # small molecule: (ij|kl) resident in HBM like the reference's el_mat (:129), J and K
+                    # per iteration are two HBM-bound GEMVs
+                    logger.log("Calculating the electron repulsion matrix")
+                    self._jkplan = _lib.StoredERI(self._devbasis, s0, s1)
+                else:
+                    logger.log("Planning the direct electron-repulsion build")
+                    self._jkplan = _lib.JKPlan(self._devbasis, s0, s1, self._jk_thresh)
             else:
                 logger.log("Building the density fitting matrices")
                 self._df.build()

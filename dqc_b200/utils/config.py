@@ -1,5 +1,6 @@
 """Run-time knobs.  Mirrors the reference's module-level ``config`` singleton
 (dqc/utils/config.py:6-14: THRESHOLD_MEMORY, CHUNK_MEMORY, VERBOSE) and adds the GPU knobs."""
+import os
 from dataclasses import dataclass
 
 __all__ = ["config"]
@@ -13,10 +14,13 @@ class _Config:
     CHUNK_MEMORY: int = 16 * 1024 ** 2
     VERBOSE: int = 0
     # grid points per superblock of the block-sparse XC path (multiple of 128)
-    SB_POINTS: int = 1024
+    SB_POINTS: int = int(os.environ.get("B200QC_SB_POINTS", "512"))
+    # without density fitting, keep both dense layouts of (ij|kl) in HBM when 2 * 8 * nao^4 bytes fit under
+    # this (single GPU); beyond it J/K are built directly from Schwarz-screened quartets every iteration
+    ERI_STORE_MAX_BYTES: int = int(float(os.environ.get("B200QC_ERI_STORE_MAX_BYTES", str(32 * 1024 ** 3))))
     # a shell is dropped from a superblock when its envelope stays below this on every point of it
     # (0 keeps every shell everywhere, like the reference's non0tab = 1)
-    AO_SCREEN: float = 1e-12
+    AO_SCREEN: float = float(os.environ.get("B200QC_AO_SCREEN", "1e-12"))
 
 
 config = _Config()

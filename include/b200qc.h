@@ -138,6 +138,14 @@ int b200qc_int2e(const b200qc_basis *basis, const int *h_shls_slice /*8*/, doubl
 int b200qc_int3c2e_packed(const b200qc_basis *basis, const int *h_shls_slice /*6*/, double *out, int64_t ld,
                           void *stream);
 
+/* Stored-ERI regime for small molecules (2 nao^4 doubles fit HBM): eri_j[i][j][k][l] =
+ * eri_k[i][k][j][l] = (ij|kl), filled from the quartets with i >= j, k >= l.  The reference stores
+ * el_mat the same way (hcgto.py:129); J and K per iteration are then two HBM-bound GEMVs
+ * (b200qc_gemv) instead of its einsums (hcgto.py:209,234). */
+int b200qc_eri_store(const b200qc_basis *basis, int sh0, int sh1, double *eri_j, double *eri_k, void *stream);
+/* y[r] = sum_c A[r * ld + c] x[c]; ld even, A and x 16-byte aligned */
+int b200qc_gemv(const double *A, int64_t nrow, int64_t ncol, int64_t ld, const double *x, double *y, void *stream);
+
 /* ---- K8: direct J/K -- replaces the dense-ERI einsums of hcgto.py:204-241 ---------------- */
 /* without ever storing (ij|kl) (the reference holds nao^4 doubles, hcgto.py:129).
  * dm: (nset, nao, nao) SYMMETRIC, AO basis of shells [sh0, sh1); vj / vk: (nset, nao, nao) or NULL;

@@ -23,12 +23,19 @@ def _diatomic(atomzs, dist):
 
 # ---------------------------------------------------------------------------------------------
 # fixed-density parity against the oracle
-@pytest.mark.parametrize("orthozer", [True, False])
-def test_jk_hcore_match_oracle_fixed_dm(cuda, orthozer):
+@pytest.mark.parametrize("orthozer,stored", [(True, True), (False, True), (True, False)])
+def test_jk_hcore_match_oracle_fixed_dm(cuda, orthozer, stored):
     from oracle import fock_ref
+    from dqc_b200 import config, _lib
     zs, pos = util.H2O
     mol = _mol(zs, pos, "def2-svp", cuda, orthogonalize_basis=orthozer)
-    h = mol.get_hamiltonian().build()
+    old = config.ERI_STORE_MAX_BYTES
+    try:
+        config.ERI_STORE_MAX_BYTES = old if stored else 0      # stored-ERI GEMVs vs direct J/K plan
+        h = mol.get_hamiltonian().build()
+    finally:
+        config.ERI_STORE_MAX_BYTES = old
+    assert isinstance(h._jkplan, _lib.StoredERI if stored else _lib.JKPlan)
     w, _ = util.make_wrapper(zs, pos, "def2-svp")
     ref = fock_ref.RefHamilton(w, orthozer=orthozer).build_eri()
     assert h.nao == ref.nao
