@@ -320,7 +320,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
     e2e_ms /= args.steps
-    assert torch.allclose(fock_host.to(dev), fock, rtol=0, atol=1e-9), "e2e and device-resident Fock differ"
+    # same build twice: equal up to the summation-order noise of the fp64 atomics (J/K digestion, Vxc
+    # scatter) amplified by the orthogonaliser X = U s^-1/2
+    dev_diff = float((fock_host.to(dev) - fock).abs().max())
+    assert dev_diff <= 1e-8 * max(1.0, float(fock.abs().max())), "e2e and device-resident Fock differ: %g" % dev_diff
 
     if rank != 0:
         if world > 1:
