@@ -65,6 +65,14 @@ _SIGS = {
     "b200qc_vxc_sb": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_vxc_i8_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
+    "b200qc_vxc_sb_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "b200qc_int1e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int2c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -526,7 +534,8 @@ class GridBlocks(object):
     kernels (K2 / K4) on it."""
 
     def __init__(self, basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, weights: torch.Tensor,
-                 deriv: int, sbp: int = 1024, eps: float = 1e-12, flags: Optional[np.ndarray] = None):
+                 deriv: int, sbp: int = 1024, eps: float = 1e-12, flags: Optional[np.ndarray] = None,
+                 i8_slices: int = 0, i8_variant: int = 0):
         lib = load()
         dev = coords.device
         self.basis, self.sh0, self.sh1 = basis, sh0, sh1
@@ -581,6 +590,17 @@ class GridBlocks(object):
             _check(lib.b200qc_eval_gto_sb(basis.handle, deriv, _ptr(coords), self.ngrid, self.sbp, self.nsb,
                                           _ptr(self.d_desc), _ptr(self.d_shell_ids), _ptr(self.d_shell_col),
                                           _ptr(self.ao), _stream()), "eval_gto_sb")
+        # optional tcgen05 int8 (Ozaki) form of the Vxc GEMM: the AO values are sliced once here
+        self.i8_slices, self.i8_variant = int(i8_slices), int(i8_variant)
+        if self.i8_slices and self.nsb:
+            nel = int(self.sbp * nsp.sum())
+            self.aplanes = torch.empty(self.i8_slices * nel, dtype=torch.int8, device=dev)
+            self.bplanes = torch.empty(self.i8_slices * nel, dtype=torch.int8, device=dev)
+            self.ascale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
+            self.bscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
+            _check(lib.b200qc_vxc_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.i8_slices,
+                                             _ptr(self.ao), _ptr(self.d_vb_off), _ptr(self.aplanes), _ptr(self.ascale),
+                                             _stream()), "vxc_i8_prepare")
 
     def rho(self, dm: torch.Tensor, with_grad: bool):
         """dm (nao, nao) symmetric AO-basis density -> rho (ngl,), grad (3, ngl) | None (zero in the padding)."""
@@ -597,6 +617,13 @@ class GridBlocks(object):
         lib = load()
         assert vrho.shape[0] == self.ngl and (vgrad is None or self.deriv)
         mat = torch.empty((self.nao, self.nao), dtype=torch.float64, device=vrho.device)
+        if self.i8_slices and self.nsb:
+            _check(lib.b200qc_vxc_sb_i8(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.i8_slices,
+                                        _ptr(self.d_idx), _ptr(self.ao), _ptr(self.w), _ptr(vrho.contiguous()),
+                                        _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(self.vb), _ptr(self.aplanes),
+                                        _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.bscale), _ptr(mat),
+                                        self.i8_variant, _stream()), "vxc_sb_i8")
+            return mat
         _check(lib.b200qc_vxc_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
                                  _ptr(self.w), _ptr(vrho.contiguous()), _ptr(vgrad), self.nao, _ptr(self.d_vb_off),
                                  _ptr(self.vb), _ptr(mat), _stream()), "vxc_sb")

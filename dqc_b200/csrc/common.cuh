@@ -104,12 +104,12 @@ static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 // profile synchronises once and returns, per kernel id, launch count and summed device time.
 enum {
     PROF_AO_EVAL = 0, PROF_BECKE, PROF_RHO, PROF_XC, PROF_VXC_VB, PROF_VXC_GEMM, PROF_VXC_REDUCE,
-    PROF_DFJ_PASS1, PROF_DFJ_PASS2, PROF_DFJ_SMALL, PROF_JK, PROF_INTS, PROF_PEAK, PROF_SB_GATHER, PROF_GEMV, PROF_N
+    PROF_DFJ_PASS1, PROF_DFJ_PASS2, PROF_DFJ_SMALL, PROF_JK, PROF_INTS, PROF_PEAK, PROF_SB_GATHER, PROF_GEMV, PROF_I8_SLICE, PROF_N
 };
 static const char *const g_prof_names[PROF_N] = {
     "ao_eval_kernel", "becke_weights_kernel", "rho_kernel", "xc_kernel", "vxc_vb_kernel", "vxc_gemm_kernel",
     "slab_reduce_kernel", "dfj_pass1_kernel", "dfj_pass2_kernel", "dfj_small_kernels", "jk_kernel",
-    "int_dense_kernel", "dmma_peak_kernel", "sb_gather_dm_kernel", "gemv_rows_kernel"};
+    "int_dense_kernel", "dmma_peak_kernel", "sb_gather_dm_kernel", "gemv_rows_kernel", "sb_slice_kernel"};
 struct ProfRec {
     int id;
     cudaEvent_t a, b;

@@ -1,0 +1,305 @@
+// K4 on the 5th-generation tensor cores: M_sb = phi_sb^T vb_sb as an error-free sliced int8 GEMM
+// (Ozaki scheme) on tcgen05.mma.kind::i8 with int32 accumulators in TMEM.
+//
+// tcgen05.mma has no f64 kind; the DMMA (mma.sync m8n8k4) form of this GEMM saturates the fp64 tensor
+// pipe at ~30 TFLOP/s.  Here both fp64 operands are cut, per superblock and per column, into S int8
+// slices of a block-fixed-point representation
+//     x = 2^e * sum_s q_s 2^(-6 - 7 s),   q_s in [-64, 64],   e = exponent of the column maximum,
+// every slice product sum_g q_s^A q_t^B is EXACT in int32 (|.| <= 512 * 4096 per product, <= 2^24 per
+// anti-diagonal), products with s + t = d share the scale 2^(-12 - 7 d) and one TMEM accumulator, and the
+// S accumulators are recombined in fp64 in the epilogue.  Truncation at s + t < S leaves a relative
+// error of ~(S + 1) 2^(-7 S - 5) of (column max x column max x K): S = 6 reproduces the fp64 Vxc matrix
+// to ~1e-12 (tools/ozaki_emul.py), five orders inside the 1e-6 parity bar, with S (S + 1) / 2 = 21 int8
+// MMAs per fp64 one.
+//
+// Kernel layout: CTA tile 128 (mu) x 64 (nu), K tile = 64 grid rows, 2-stage cp.async ring; operands
+// are MN-major (the AO index is the contiguous one in memory) and land in shared memory in the
+// no-swizzle canonical UMMA layout (core matrix = 16 bytes of MN x 8 rows of K); one thread issues the
+// S (S + 1) / 2 x 2 MMAs of a K tile and commits them to an mbarrier that frees the stage; 8 warps drain
+// TMEM (tcgen05.ld 32x32b) and add the tile into M[idx][idx] with fp64 atomics.
+#pragma once
+#include "xc_sb.cuh"
+
+#define I8_BM 128
+#define I8_BN 64
+#define I8_KT 64
+#define I8_THREADS 256
+#define I8_STAGES 2
+
+// ---- slicing: X [rows][ld] fp64 per superblock -> S int8 planes [S][rows][ld] + per-column scale ----
+template <int S>
+__global__ void __launch_bounds__(256)
+sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, const int64_t *__restrict__ x_off,
+                int comp_stride_is_ao, int sbp, signed char *__restrict__ planes, double *__restrict__ scales) {
+    const SBDesc d = sbd[blockIdx.y];
+    const int c0 = blockIdx.x * 64;
+    if (c0 >= d.nsp) return;
+    const int col = c0 + (threadIdx.x & 63), rg = threadIdx.x >> 6;   // 64 columns x 4 row groups
+    const int64_t ld = d.nsp;
+    const double *X = x + (comp_stride_is_ao ? d.ao_off : x_off[blockIdx.y]);
+    __shared__ double smax[4][64];
+    double m = 0.0;
+    for (int r = rg; r < sbp; r += 4) m = fmax(m, fabs(X[(int64_t)r * ld + col]));
+    smax[rg][threadIdx.x & 63] = m;
+    __syncthreads();
+    m = fmax(fmax(smax[0][threadIdx.x & 63], smax[1][threadIdx.x & 63]),
+             fmax(smax[2][threadIdx.x & 63], smax[3][threadIdx.x & 63]));
+    int e = 0;
+    if (m > 0.0) frexp(m, &e);              // m = f 2^e, f in [0.5, 1)  =>  |x| / 2^e < 1
+    const double inv = ldexp(64.0, -e);     // y = x 2^(6 - e), |y| < 64
+    if (rg == 0) scales[d.idx_off + col] = ldexp(1.0, e);
+    // plane s of this SB: planes + S * x_elem_off + (s * sbp + r) * ld + col, with x_elem_off = sum sbp * nsp
+    signed char *P = planes + (int64_t)S * x_off[blockIdx.y];
+    for (int r = rg; r < sbp; r += 4) {
+        double y = X[(int64_t)r * ld + col] * inv;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const double q = rint(y);
+            P[((int64_t)s * sbp + r) * ld + col] = (signed char)(int)q;
+            y = (y - q) * 128.0;
+        }
+    }
+}
+
+// ---- tcgen05 plumbing (PTX spellings as in the CUTLASS sm100 headers) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(phase) : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                 ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+// no-swizzle shared-memory matrix descriptor (version 1); byte offsets are stored without their 4 LSBs
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+
+// instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = 64, M = 128 (dense)
+#define I8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((I8_BN >> 3) << 17) | ((I8_BM >> 4) << 24))
+
+template <int S>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const signed char *__restrict__ aplanes,
+                   const signed char *__restrict__ bplanes, const int64_t *__restrict__ x_off,
+                   const double *__restrict__ ascale, const double *__restrict__ bscale, int sbp, int nao,
+                   double *__restrict__ mat, int variant) {
+    extern __shared__ __align__(1024) unsigned char i8_smem[];
+    constexpr int A_PLANE = I8_KT * I8_BM;            // 8192 bytes: 8 K-groups x 8 MN-chunks x 128-byte core matrices
+    constexpr int B_PLANE = I8_KT * I8_BN;            // 4096 bytes
+    constexpr int STAGE = S * (A_PLANE + B_PLANE);
+    __shared__ uint64_t mbar[I8_STAGES + 1];
+    __shared__ uint32_t tmem_base_smem;
+    const SBDesc d = sbd[blockIdx.y];
+    const int ntn = d.nsp / I8_BN, ntm = (d.nsp + I8_BM - 1) / I8_BM;
+    if ((int)blockIdx.x >= ntn * ntm) return;
+    const int tm = blockIdx.x / ntn, tn = blockIdx.x % ntn;
+    const int m0 = tm * I8_BM, n0 = tn * I8_BN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ld = d.nsp;
+    const signed char *A = aplanes + (int64_t)S * x_off[blockIdx.y];
+    const signed char *B = bplanes + (int64_t)S * x_off[blockIdx.y];
+
+    if (tid == 0) {
+        for (int i = 0; i <= I8_STAGES; i++) mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_smem;
+    const uint32_t sbase = smem_u32(i8_smem);
+
+    auto load_stage = [&](int kt, int slot) {
+        const uint32_t sa = sbase + slot * STAGE, sb = sa + S * A_PLANE;
+        const int64_t g0 = (int64_t)kt * I8_KT;
+        for (int c = tid; c < S * 512; c += I8_THREADS) {          // A: 16-byte chunks (8 rows x 4 chunks per warp)
+            const int plane = c >> 9, rem = c & 511;
+            const int kg = rem >> 6, within = rem & 63, r = within & 7, mc = within >> 3;
+            const bool ok = m0 + mc * 16 < d.nsp;
+            const signed char *src = A + ((int64_t)plane * sbp + g0 + kg * 8 + r) * ld + m0 + mc * 16;
+            cp_async16_ca(sa + plane * A_PLANE + kg * 1024 + mc * 128 + r * 16, ok ? src : A, ok);
+        }
+        for (int c = tid; c < S * 256; c += I8_THREADS) {          // B
+            const int plane = c >> 8, rem = c & 255;
+            const int kg = rem >> 5, within = rem & 31, r = within & 7, nc = within >> 3;
+            const signed char *src = B + ((int64_t)plane * sbp + g0 + kg * 8 + r) * ld + n0 + nc * 16;
+            cp_async16_ca(sb + plane * B_PLANE + kg * 512 + nc * 128 + r * 16, src, true);
+        }
+    };
+
+    const int nk = sbp / I8_KT;
+    load_stage(0, 0);
+    cp_async_commit();
+    uint32_t phase[I8_STAGES] = {0, 0};
+    for (int kt = 0; kt < nk; kt++) {
+        const int slot = kt % I8_STAGES, nslot = (kt + 1) % I8_STAGES;
+        if (kt + 1 < nk) {
+            if (kt + 1 >= I8_STAGES) {                 // the MMAs that read `nslot` (K tile kt + 1 - STAGES) are done
+                mbar_wait(&mbar[nslot], phase[nslot]);
+                phase[nslot] ^= 1;
+            }
+            load_stage(kt + 1, nslot);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = sbase + slot * STAGE, sb = sa + S * A_PLANE;
+            // MN-major, no swizzle: SBO = stride between 16-element MN chunks (128 B), LBO = stride between
+            // 8-row K groups (A: 1024 B, B: 512 B); variant 1 swaps the two fields (kept for bring-up)
+            const uint32_t lbo_a = variant ? 128 : 1024, sbo_a = variant ? 1024 : 128;
+            const uint32_t lbo_b = variant ? 128 : 512, sbo_b = variant ? 512 : 128;
+#pragma unroll
+            for (int ks = 0; ks < I8_KT / 32; ks++)
+#pragma unroll
+                for (int dd = 0; dd < S; dd++)
+#pragma unroll
+                    for (int s = 0; s <= dd; s++) {
+                        const int t = dd - s;
+                        const uint64_t da = umma_desc(sa + s * A_PLANE + ks * 4 * 1024, lbo_a, sbo_a);
+                        const uint64_t db = umma_desc(sb + t * B_PLANE + ks * 4 * 512, lbo_b, sbo_b);
+                        umma_i8(tmem + dd * I8_BN, da, db, I8_IDESC, (kt > 0 || ks > 0 || s > 0) ? 1u : 0u);
+                    }
+            umma_commit(&mbar[slot]);                  // frees this stage when the MMAs above retire
+            if (kt == nk - 1) umma_commit(&mbar[I8_STAGES]);
+        }
+    }
+    cp_async_wait<0>();
+    mbar_wait(&mbar[I8_STAGES], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: warp w drains TMEM lanes 32 (w % 4) .., columns 32 (w / 4) .. of each accumulator ----
+    const int lg = warp & 3, ch = warp >> 2;
+    double acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) acc[j] = 0.0;
+#pragma unroll
+    for (int dd = S - 1; dd >= 0; dd--) {              // smallest terms first
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
+        const double sc = ldexp(1.0, -12 - 7 * dd);
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] += (double)(int)v[j] * sc;
+    }
+    const int row = m0 + lg * 32 + lane;
+    if (row < d.nsp) {
+        const int *ix = idx + d.idx_off;
+        const int a = ix[row];
+        if (a < nao) {
+            const double sa_ = ascale[d.idx_off + row];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int col = n0 + ch * 32 + j;
+                const int b = ix[col];
+                if (b < nao) atomicAdd(mat + (int64_t)a * nao + b, acc[j] * sa_ * bscale[d.idx_off + col]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// slices the (static) AO values of every superblock once: aplanes [S][sbp][nsp] int8 per SB at S * x_off[sb]
+extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const double *ao,
+                                     const int64_t *x_off, signed char *aplanes, double *ascale, void *stream) {
+    QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    if (nsb == 0) return 0;
+    dim3 grid((unsigned)(max_nsp / 64), (unsigned)nsb);
+    const SBDesc *sbd = (const SBDesc *)sbdesc;
+    if (nslice == 5) sb_slice_kernel<5><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, x_off, 1, sbp, aplanes, ascale);
+    else sb_slice_kernel<6><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, x_off, 1, sbp, aplanes, ascale);
+    QC_LAUNCHED(1);
+    return 0;
+}
+
+template <int S>
+static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *vb,
+                      const int64_t *x_off, const signed char *aplanes, const double *ascale, signed char *bplanes,
+                      double *bscale, int nao, double *mat, int variant, cudaStream_t st) {
+    dim3 gs((unsigned)(max_nsp / 64), (unsigned)nsb);
+    prof_begin(PROF_I8_SLICE, st);
+    sb_slice_kernel<S><<<gs, 256, 0, st>>>(sbd, vb, x_off, 0, sbp, bplanes, bscale);
+    prof_end(st);
+    QC_LAUNCHED(1);
+    const size_t smem = (size_t)I8_STAGES * S * (I8_KT * I8_BM + I8_KT * I8_BN);
+    QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int maxtiles = (max_nsp / I8_BN) * ((max_nsp + I8_BM - 1) / I8_BM);
+    dim3 grid((unsigned)maxtiles, (unsigned)nsb);
+    prof_begin(PROF_VXC_GEMM, st);
+    vxc_i8_gemm_kernel<S><<<grid, I8_THREADS, smem, st>>>(sbd, idx, aplanes, bplanes, x_off, ascale, bscale, sbp, nao,
+                                                          mat, variant);
+    prof_end(st);
+    QC_LAUNCHED(1);
+    return 0;
+}
+
+// Same contract as b200qc_vxc_sb, with the GEMM on tcgen05 int8 slices.  aplanes / ascale come from
+// b200qc_vxc_i8_prepare; bplanes (S * sum_sb sbp * nsp bytes) and bscale (sum_sb nsp doubles) are scratch.
+extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
+                                const double *ao, const double *weights, const double *vrho, const double *vgrad,
+                                int nao, const int64_t *vb_off, double *vb, const signed char *aplanes,
+                                const double *ascale, signed char *bplanes, double *bscale, double *mat, int variant,
+                                void *stream) {
+    QC_REQUIRE(sbp % I8_KT == 0 && sbp % GM_BM == 0, "superblock size must be a multiple of 128");
+    QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
+    cudaStream_t st = as_stream(stream);
+    QC_CHECK(cudaMemsetAsync(mat, 0, sizeof(double) * nao * nao, st));
+    if (nsb == 0) return 0;
+    const SBDesc *sbd = (const SBDesc *)sbdesc;
+    const int64_t ngl = (int64_t)nsb * sbp;
+    const int wpb = 8;
+    const unsigned nb1 = (unsigned)((ngl + wpb - 1) / wpb);
+    prof_begin(PROF_VXC_VB, st);
+    if (vgrad)
+        vxc_vb_sb_kernel<4><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
+    else
+        vxc_vb_sb_kernel<1><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
+    prof_end(st);
+    QC_LAUNCHED(1);
+    if (nslice == 5)
+        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, ascale, bplanes, bscale, nao, mat, variant, st);
+    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, ascale, bplanes, bscale, nao, mat, variant, st);
+}

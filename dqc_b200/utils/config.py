@@ -15,6 +15,9 @@ class _Config:
     VERBOSE: int = 0
     # grid points per superblock of the block-sparse XC path (multiple of 128)
     SB_POINTS: int = int(os.environ.get("B200QC_SB_POINTS", "512"))
+    # Vxc GEMM on tcgen05 as an error-free sliced int8 product: 0 = off (fp64 DMMA), 5 or 6 = number of slices
+    VXC_I8_SLICES: int = int(os.environ.get("B200QC_VXC_I8", "0"))
+    I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
     # without density fitting, keep both dense layouts of (ij|kl) in HBM when 2 * 8 * nao^4 bytes fit under
     # this (single GPU); beyond it J/K are built directly from Schwarz-screened quartets every iteration
     ERI_STORE_MAX_BYTES: int = int(float(os.environ.get("B200QC_ERI_STORE_MAX_BYTES", str(32 * 1024 ** 3))))
