@@ -72,7 +72,7 @@ _SIGS = {
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int1e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int2c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -593,14 +593,18 @@ class GridBlocks(object):
         # optional tcgen05 int8 (Ozaki) form of the Vxc GEMM: the AO values are sliced once here
         self.i8_slices, self.i8_variant = int(i8_slices), int(i8_variant)
         if self.i8_slices and self.nsb:
-            nel = int(self.sbp * nsp.sum())
-            self.aplanes = torch.empty(self.i8_slices * nel, dtype=torch.int8, device=dev)
-            self.bplanes = torch.empty(self.i8_slices * nel, dtype=torch.int8, device=dev)
+            S = self.i8_slices
+            a_bytes = S * self.sbp * ((nsp + 127) // 128 * 128)      # A operand: whole 128-column M tiles
+            b_bytes = S * self.sbp * nsp
+            self.d_a_off = tt(excl(a_bytes), torch.int64)
+            self.d_b_off = tt(excl(b_bytes), torch.int64)
+            self.aplanes = torch.zeros(int(a_bytes.sum()), dtype=torch.int8, device=dev)
+            self.bplanes = torch.empty(int(b_bytes.sum()), dtype=torch.int8, device=dev)
             self.ascale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
             self.bscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
-            _check(lib.b200qc_vxc_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.i8_slices,
-                                             _ptr(self.ao), _ptr(self.d_vb_off), _ptr(self.aplanes), _ptr(self.ascale),
-                                             _stream()), "vxc_i8_prepare")
+            _check(lib.b200qc_vxc_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, S, _ptr(self.ao),
+                                             _ptr(self.d_a_off), _ptr(self.aplanes), _ptr(self.ascale), _stream()),
+                   "vxc_i8_prepare")
 
     def rho(self, dm: torch.Tensor, with_grad: bool):
         """dm (nao, nao) symmetric AO-basis density -> rho (ngl,), grad (3, ngl) | None (zero in the padding)."""
@@ -621,8 +625,8 @@ class GridBlocks(object):
             _check(lib.b200qc_vxc_sb_i8(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.i8_slices,
                                         _ptr(self.d_idx), _ptr(self.ao), _ptr(self.w), _ptr(vrho.contiguous()),
                                         _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(self.vb), _ptr(self.aplanes),
-                                        _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.bscale), _ptr(mat),
-                                        self.i8_variant, _stream()), "vxc_sb_i8")
+                                        _ptr(self.d_a_off), _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.d_b_off),
+                                        _ptr(self.bscale), _ptr(mat), _stream()), "vxc_sb_i8")
             return mat
         _check(lib.b200qc_vxc_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
                                  _ptr(self.w), _ptr(vrho.contiguous()), _ptr(vgrad), self.nao, _ptr(self.d_vb_off),

@@ -12,31 +12,40 @@
 // to ~1e-12 (tools/ozaki_emul.py), five orders inside the 1e-6 parity bar, with S (S + 1) / 2 = 21 int8
 // MMAs per fp64 one.
 //
-// Kernel layout: CTA tile 128 (mu) x 64 (nu), K tile = 64 grid rows, 2-stage cp.async ring; operands
-// are MN-major (the AO index is the contiguous one in memory) and land in shared memory in the
-// no-swizzle canonical UMMA layout (core matrix = 16 bytes of MN x 8 rows of K); one thread issues the
-// S (S + 1) / 2 x 2 MMAs of a K tile and commits them to an mbarrier that frees the stage; 8 warps drain
-// TMEM (tcgen05.ld 32x32b) and add the tile into M[idx][idx] with fp64 atomics.
+// Kernel layout: CTA tile 128 (mu) x 64 (nu), K tile = 32 grid rows (one MMA K step), 5-stage ring.
+// Operands are MN-major (the AO index is the contiguous one) in the no-swizzle canonical UMMA layout
+// (core matrix = 16 bytes of MN x 8 rows of K).  The slicing kernels write the planes to global memory
+// ALREADY in that tiled order, so a pipeline stage is two contiguous blocks and the producer is one
+// thread issuing two 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) -- no tensor maps, no
+// per-thread address arithmetic.  Warp-specialised: warp 0 = producer, warp 1 = MMA issuer (one thread,
+// S (S + 1) / 2 MMAs per stage, tcgen05.commit frees the stage), warps 4-7 = epilogue (tcgen05.ld 32x32b,
+// fp64 recombination, tile staged in shared memory, row-wise coalesced fp64 atomics into M[idx][idx]).
 #pragma once
 #include "xc_sb.cuh"
 
 #define I8_BM 128
 #define I8_BN 64
-#define I8_KT 64
+#define I8_KT 32          // one MMA K step (32 int8) per pipeline stage
 #define I8_THREADS 256
-#define I8_STAGES 2
+#define I8_STAGES 5       // S = 6: 5 x 36 KB of operands in flight per SM
+#define I8_EPI_LD 65      // padded row stride (doubles) of the epilogue staging tile
+#define I8_A_PLANE (I8_KT * I8_BM)   // 4096 bytes: [4 K groups][8 MN chunks][8 rows][16 bytes]
+#define I8_B_PLANE (I8_KT * I8_BN)   // 2048 bytes: [4 K groups][4 MN chunks][8 rows][16 bytes]
 
-// ---- slicing: X [rows][ld] fp64 per superblock -> S int8 planes [S][rows][ld] + per-column scale ----
-template <int S>
+// ---- slicing: X [rows][ld] fp64 per superblock -> S int8 planes in the TILED operand order + per-column scale
+// out (per SB, bytes): [tile = col / W][k tile = row / 32][slice][(row % 32) / 8][(col % W) / 16][row % 8][col % 16]
+// with W = 128 (A operand, M tiles, zero-padded to a whole tile by the caller's memset) or 64 (B operand).
+template <int S, int W>
 __global__ void __launch_bounds__(256)
 sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, const int64_t *__restrict__ x_off,
-                int comp_stride_is_ao, int sbp, signed char *__restrict__ planes, double *__restrict__ scales) {
+                int x_is_ao, int sbp, const int64_t *__restrict__ p_off, signed char *__restrict__ planes,
+                double *__restrict__ scales) {
     const SBDesc d = sbd[blockIdx.y];
     const int c0 = blockIdx.x * 64;
     if (c0 >= d.nsp) return;
     const int col = c0 + (threadIdx.x & 63), rg = threadIdx.x >> 6;   // 64 columns x 4 row groups
     const int64_t ld = d.nsp;
-    const double *X = x + (comp_stride_is_ao ? d.ao_off : x_off[blockIdx.y]);
+    const double *X = x + (x_is_ao ? d.ao_off : x_off[blockIdx.y]);
     __shared__ double smax[4][64];
     double m = 0.0;
     for (int r = rg; r < sbp; r += 4) m = fmax(m, fabs(X[(int64_t)r * ld + col]));
@@ -48,14 +57,17 @@ sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, co
     if (m > 0.0) frexp(m, &e);              // m = f 2^e, f in [0.5, 1)  =>  |x| / 2^e < 1
     const double inv = ldexp(64.0, -e);     // y = x 2^(6 - e), |y| < 64
     if (rg == 0) scales[d.idx_off + col] = ldexp(1.0, e);
-    // plane s of this SB: planes + S * x_elem_off + (s * sbp + r) * ld + col, with x_elem_off = sum sbp * nsp
-    signed char *P = planes + (int64_t)S * x_off[blockIdx.y];
+    constexpr int PLANE = I8_KT * W;
+    const int nk = sbp / I8_KT;
+    const int tile = col / W, wc = col % W;
+    signed char *P = planes + p_off[blockIdx.y] + (int64_t)tile * nk * S * PLANE + (wc >> 4) * 128 + (wc & 15);
     for (int r = rg; r < sbp; r += 4) {
         double y = X[(int64_t)r * ld + col] * inv;
+        signed char *Q = P + (int64_t)(r >> 5) * S * PLANE + ((r & 31) >> 3) * (W / 16) * 128 + (r & 7) * 16;
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const double q = rint(y);
-            P[((int64_t)s * sbp + r) * ld + col] = (signed char)(int)q;
+            Q[s * PLANE] = (signed char)(int)q;
             y = (y - q) * 128.0;
         }
     }
@@ -104,9 +116,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, bool valid) {
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = 64, M = 128 (dense)
@@ -115,14 +130,13 @@ __device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, boo
 template <int S>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const signed char *__restrict__ aplanes,
-                   const signed char *__restrict__ bplanes, const int64_t *__restrict__ x_off,
-                   const double *__restrict__ ascale, const double *__restrict__ bscale, int sbp, int nao,
-                   double *__restrict__ mat, int variant) {
+                   const int64_t *__restrict__ a_off, const signed char *__restrict__ bplanes,
+                   const int64_t *__restrict__ b_off, const double *__restrict__ ascale,
+                   const double *__restrict__ bscale, int sbp, int nao, double *__restrict__ mat) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
-    constexpr int A_PLANE = I8_KT * I8_BM;            // 8192 bytes: 8 K-groups x 8 MN-chunks x 128-byte core matrices
-    constexpr int B_PLANE = I8_KT * I8_BN;            // 4096 bytes
-    constexpr int STAGE = S * (A_PLANE + B_PLANE);
-    __shared__ uint64_t mbar[I8_STAGES + 1];
+    constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * I8_B_PLANE, STAGE = A_STAGE + B_STAGE;
+    constexpr uint32_t LBO_A = (I8_BM / 16) * 128, LBO_B = (I8_BN / 16) * 128;   // stride between 8-row K groups
+    __shared__ uint64_t full_bar[I8_STAGES], empty_bar[I8_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_smem;
     const SBDesc d = sbd[blockIdx.y];
     const int ntn = d.nsp / I8_BN, ntm = (d.nsp + I8_BM - 1) / I8_BM;
@@ -130,15 +144,17 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, 
     const int tm = blockIdx.x / ntn, tn = blockIdx.x % ntn;
     const int m0 = tm * I8_BM, n0 = tn * I8_BN;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t ld = d.nsp;
-    const signed char *A = aplanes + (int64_t)S * x_off[blockIdx.y];
-    const signed char *B = bplanes + (int64_t)S * x_off[blockIdx.y];
+    const int nk = sbp / I8_KT;
 
     if (tid == 0) {
-        for (int i = 0; i <= I8_STAGES; i++) mbar_init(&mbar[i], 1);
+        for (int i = 0; i < I8_STAGES; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -148,140 +164,133 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, 
     const uint32_t tmem = tmem_base_smem;
     const uint32_t sbase = smem_u32(i8_smem);
 
-    auto load_stage = [&](int kt, int slot) {
-        const uint32_t sa = sbase + slot * STAGE, sb = sa + S * A_PLANE;
-        const int64_t g0 = (int64_t)kt * I8_KT;
-        for (int c = tid; c < S * 512; c += I8_THREADS) {          // A: 16-byte chunks (8 rows x 4 chunks per warp)
-            const int plane = c >> 9, rem = c & 511;
-            const int kg = rem >> 6, within = rem & 63, r = within & 7, mc = within >> 3;
-            const bool ok = m0 + mc * 16 < d.nsp;
-            const signed char *src = A + ((int64_t)plane * sbp + g0 + kg * 8 + r) * ld + m0 + mc * 16;
-            cp_async16_ca(sa + plane * A_PLANE + kg * 1024 + mc * 128 + r * 16, ok ? src : A, ok);
-        }
-        for (int c = tid; c < S * 256; c += I8_THREADS) {          // B
-            const int plane = c >> 8, rem = c & 255;
-            const int kg = rem >> 5, within = rem & 31, r = within & 7, nc = within >> 3;
-            const signed char *src = B + ((int64_t)plane * sbp + g0 + kg * 8 + r) * ld + n0 + nc * 16;
-            cp_async16_ca(sb + plane * B_PLANE + kg * 512 + nc * 128 + r * 16, src, true);
-        }
-    };
-
-    const int nk = sbp / I8_KT;
-    load_stage(0, 0);
-    cp_async_commit();
-    uint32_t phase[I8_STAGES] = {0, 0};
-    for (int kt = 0; kt < nk; kt++) {
-        const int slot = kt % I8_STAGES, nslot = (kt + 1) % I8_STAGES;
-        if (kt + 1 < nk) {
-            if (kt + 1 >= I8_STAGES) {                 // the MMAs that read `nslot` (K tile kt + 1 - STAGES) are done
-                mbar_wait(&mbar[nslot], phase[nslot]);
-                phase[nslot] ^= 1;
+    if (warp == 0) {
+        // ===== producer: two contiguous blocks per stage =====
+        if (lane == 0) {
+            const signed char *A = aplanes + a_off[blockIdx.y] + (int64_t)tm * nk * A_STAGE;
+            const signed char *B = bplanes + b_off[blockIdx.y] + (int64_t)tn * nk * B_STAGE;
+            for (int kt = 0; kt < nk; kt++) {
+                const int slot = kt % I8_STAGES;
+                mbar_wait(&empty_bar[slot], ((kt / I8_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full_bar[slot], STAGE);
+                bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
+                bulk_g2s(sbase + slot * STAGE + A_STAGE, B + (int64_t)kt * B_STAGE, B_STAGE, &full_bar[slot]);
             }
-            load_stage(kt + 1, nslot);
         }
-        cp_async_commit();
-        cp_async_wait<1>();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = sbase + slot * STAGE, sb = sa + S * A_PLANE;
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
             // MN-major, no swizzle: SBO = stride between 16-element MN chunks (128 B), LBO = stride between
-            // 8-row K groups (A: 1024 B, B: 512 B); variant 1 swaps the two fields (kept for bring-up)
-            const uint32_t lbo_a = variant ? 128 : 1024, sbo_a = variant ? 1024 : 128;
-            const uint32_t lbo_b = variant ? 128 : 512, sbo_b = variant ? 512 : 128;
-#pragma unroll
-            for (int ks = 0; ks < I8_KT / 32; ks++)
+            // 8-row K groups (A: 1024 B, B: 512 B)
+            const uint64_t da0 = umma_desc(sbase, LBO_A, 128), db0 = umma_desc(sbase + A_STAGE, LBO_B, 128);
+            for (int kt = 0; kt < nk; kt++) {
+                const int slot = kt % I8_STAGES;
+                mbar_wait(&full_bar[slot], (kt / I8_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
 #pragma unroll
                 for (int dd = 0; dd < S; dd++)
 #pragma unroll
-                    for (int s = 0; s <= dd; s++) {
-                        const int t = dd - s;
-                        const uint64_t da = umma_desc(sa + s * A_PLANE + ks * 4 * 1024, lbo_a, sbo_a);
-                        const uint64_t db = umma_desc(sb + t * B_PLANE + ks * 4 * 512, lbo_b, sbo_b);
-                        umma_i8(tmem + dd * I8_BN, da, db, I8_IDESC, (kt > 0 || ks > 0 || s > 0) ? 1u : 0u);
-                    }
-            umma_commit(&mbar[slot]);                  // frees this stage when the MMAs above retire
-            if (kt == nk - 1) umma_commit(&mbar[I8_STAGES]);
-        }
-    }
-    cp_async_wait<0>();
-    mbar_wait(&mbar[I8_STAGES], 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // ---- epilogue: warp w drains TMEM lanes 32 (w % 4) .., columns 32 (w / 4) .. of each accumulator ----
-    const int lg = warp & 3, ch = warp >> 2;
-    double acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) acc[j] = 0.0;
-#pragma unroll
-    for (int dd = S - 1; dd >= 0; dd--) {              // smallest terms first
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
-        const double sc = ldexp(1.0, -12 - 7 * dd);
-#pragma unroll
-        for (int j = 0; j < 32; j++) acc[j] += (double)(int)v[j] * sc;
-    }
-    const int row = m0 + lg * 32 + lane;
-    if (row < d.nsp) {
-        const int *ix = idx + d.idx_off;
-        const int a = ix[row];
-        if (a < nao) {
-            const double sa_ = ascale[d.idx_off + row];
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int col = n0 + ch * 32 + j;
-                const int b = ix[col];
-                if (b < nao) atomicAdd(mat + (int64_t)a * nao + b, acc[j] * sa_ * bscale[d.idx_off + col]);
+                    for (int s2 = 0; s2 <= dd; s2++)
+                        umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), I8_IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[slot]);         // frees the stage when the MMAs above retire
             }
+            umma_commit(&accum_bar);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .., both 32-column halves =====
+        mbar_wait(&accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3;
+        const int r = lg * 32 + lane;
+        const int row = m0 + r;
+        const double sa_ = row < d.nsp ? ascale[d.idx_off + row] : 0.0;
+        double *tile = reinterpret_cast<double *>(i8_smem);   // every MMA reading the stages has retired
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+            double acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[j] = 0.0;
+#pragma unroll
+            for (int dd = S - 1; dd >= 0; dd--) {      // smallest terms first
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
+                const double sc = ldexp(1.0, -12 - 7 * dd);
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[j] += (double)(int)v[j] * sc;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j++) tile[r * I8_EPI_LD + ch * 32 + j] = acc[j] * sa_;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps only
+        const int *ix = idx + d.idx_off;
+        const int c0 = n0 + lane, c1 = n0 + 32 + lane;
+        const int b0 = ix[c0], b1 = ix[c1];
+        const double s0 = bscale[d.idx_off + c0], s1 = bscale[d.idx_off + c1];
+        for (int rr = lg; rr < I8_BM; rr += 4) {
+            const int grow = m0 + rr;
+            if (grow >= d.nsp) break;
+            const int a = ix[grow];
+            if (a >= nao) continue;
+            double *dst = mat + (int64_t)a * nao;
+            if (b0 < nao) atomicAdd(dst + b0, tile[rr * I8_EPI_LD + lane] * s0);
+            if (b1 < nao) atomicAdd(dst + b1, tile[rr * I8_EPI_LD + 32 + lane] * s1);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// slices the (static) AO values of every superblock once: aplanes [S][sbp][nsp] int8 per SB at S * x_off[sb]
+// Slices the (static) AO values of every superblock once into the tiled A-operand order.
+// aplanes: sum_sb ceil(nsp / 128) * 128 * sbp * nslice bytes, ZERO-FILLED by the caller (partial last M tile);
+// a_off[sb]: byte offset of the SB's block; ascale: sum_sb nsp doubles.
 extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const double *ao,
-                                     const int64_t *x_off, signed char *aplanes, double *ascale, void *stream) {
+                                     const int64_t *a_off, signed char *aplanes, double *ascale, void *stream) {
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE(sbp % I8_KT == 0, "superblock size must be a multiple of 32");
     if (nsb == 0) return 0;
     dim3 grid((unsigned)(max_nsp / 64), (unsigned)nsb);
     const SBDesc *sbd = (const SBDesc *)sbdesc;
-    if (nslice == 5) sb_slice_kernel<5><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, x_off, 1, sbp, aplanes, ascale);
-    else sb_slice_kernel<6><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, x_off, 1, sbp, aplanes, ascale);
+    if (nslice == 5)
+        sb_slice_kernel<5, I8_BM><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, nullptr, 1, sbp, a_off, aplanes, ascale);
+    else
+        sb_slice_kernel<6, I8_BM><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, nullptr, 1, sbp, a_off, aplanes, ascale);
     QC_LAUNCHED(1);
     return 0;
 }
 
 template <int S>
 static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *vb,
-                      const int64_t *x_off, const signed char *aplanes, const double *ascale, signed char *bplanes,
-                      double *bscale, int nao, double *mat, int variant, cudaStream_t st) {
+                      const int64_t *vb_off, const signed char *aplanes, const int64_t *a_off, const double *ascale,
+                      signed char *bplanes, const int64_t *b_off, double *bscale, int nao, double *mat,
+                      cudaStream_t st) {
     dim3 gs((unsigned)(max_nsp / 64), (unsigned)nsb);
     prof_begin(PROF_I8_SLICE, st);
-    sb_slice_kernel<S><<<gs, 256, 0, st>>>(sbd, vb, x_off, 0, sbp, bplanes, bscale);
+    sb_slice_kernel<S, I8_BN><<<gs, 256, 0, st>>>(sbd, vb, vb_off, 0, sbp, b_off, bplanes, bscale);
     prof_end(st);
     QC_LAUNCHED(1);
-    const size_t smem = (size_t)I8_STAGES * S * (I8_KT * I8_BM + I8_KT * I8_BN);
+    size_t smem = (size_t)I8_STAGES * S * (I8_A_PLANE + I8_B_PLANE);
+    if (smem < sizeof(double) * I8_BM * I8_EPI_LD) smem = sizeof(double) * I8_BM * I8_EPI_LD;
     QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int maxtiles = (max_nsp / I8_BN) * ((max_nsp + I8_BM - 1) / I8_BM);
     dim3 grid((unsigned)maxtiles, (unsigned)nsb);
     prof_begin(PROF_VXC_GEMM, st);
-    vxc_i8_gemm_kernel<S><<<grid, I8_THREADS, smem, st>>>(sbd, idx, aplanes, bplanes, x_off, ascale, bscale, sbp, nao,
-                                                          mat, variant);
+    vxc_i8_gemm_kernel<S><<<grid, I8_THREADS, smem, st>>>(sbd, idx, aplanes, a_off, bplanes, b_off, ascale, bscale, sbp,
+                                                          nao, mat);
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;
 }
 
-// Same contract as b200qc_vxc_sb, with the GEMM on tcgen05 int8 slices.  aplanes / ascale come from
-// b200qc_vxc_i8_prepare; bplanes (S * sum_sb sbp * nsp bytes) and bscale (sum_sb nsp doubles) are scratch.
+// Same contract as b200qc_vxc_sb, with the GEMM on tcgen05 int8 slices.  aplanes / a_off / ascale come from
+// b200qc_vxc_i8_prepare; bplanes (nslice * sum_sb sbp * nsp bytes at b_off[sb]) and bscale (sum_sb nsp) are scratch.
 extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
                                 const double *ao, const double *weights, const double *vrho, const double *vgrad,
                                 int nao, const int64_t *vb_off, double *vb, const signed char *aplanes,
-                                const double *ascale, signed char *bplanes, double *bscale, double *mat, int variant,
-                                void *stream) {
+                                const int64_t *a_off, const double *ascale, signed char *bplanes,
+                                const int64_t *b_off, double *bscale, double *mat, void *stream) {
     QC_REQUIRE(sbp % I8_KT == 0 && sbp % GM_BM == 0, "superblock size must be a multiple of 128");
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
     QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
@@ -300,6 +309,6 @@ extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_ns
     prof_end(st);
     QC_LAUNCHED(1);
     if (nslice == 5)
-        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, ascale, bplanes, bscale, nao, mat, variant, st);
-    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, ascale, bplanes, bscale, nao, mat, variant, st);
+        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, nao, mat, st);
+    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, nao, mat, st);
 }
