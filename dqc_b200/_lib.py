@@ -72,7 +72,8 @@ _SIGS = {
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int1e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int2c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -596,6 +597,9 @@ class GridBlocks(object):
             S = self.i8_slices
             a_bytes = S * self.sbp * ((nsp + 127) // 128 * 128)      # A operand: whole 128-column M tiles
             b_bytes = S * self.sbp * nsp
+            ntile = ((nsp + 127) // 128) * (nsp // 64)
+            self.d_tile_off = tt(excl(ntile), torch.int32)
+            self.ntiles = int(ntile.sum())
             self.d_a_off = tt(excl(a_bytes), torch.int64)
             self.d_b_off = tt(excl(b_bytes), torch.int64)
             self.aplanes = torch.zeros(int(a_bytes.sum()), dtype=torch.int8, device=dev)
@@ -626,7 +630,8 @@ class GridBlocks(object):
                                         _ptr(self.d_idx), _ptr(self.ao), _ptr(self.w), _ptr(vrho.contiguous()),
                                         _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(self.vb), _ptr(self.aplanes),
                                         _ptr(self.d_a_off), _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.d_b_off),
-                                        _ptr(self.bscale), _ptr(mat), _stream()), "vxc_sb_i8")
+                                        _ptr(self.bscale), _ptr(self.d_tile_off), self.ntiles, _ptr(mat), _stream()),
+                   "vxc_sb_i8")
             return mat
         _check(lib.b200qc_vxc_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
                                  _ptr(self.w), _ptr(vrho.contiguous()), _ptr(vgrad), self.nao, _ptr(self.d_vb_off),

@@ -27,7 +27,7 @@
 #define I8_BN 64
 #define I8_KT 32          // one MMA K step (32 int8) per pipeline stage
 #define I8_THREADS 256
-#define I8_STAGES 5       // S = 6: 5 x 36 KB of operands in flight per SM
+#define I8_STAGES 4       // S = 6: 4 x 36 KB of operands in flight per SM (+ 66.5 KB epilogue staging tile)
 #define I8_EPI_LD 65      // padded row stride (doubles) of the epilogue staging tile
 #define I8_A_PLANE (I8_KT * I8_BM)   // 4096 bytes: [4 K groups][8 MN chunks][8 rows][16 bytes]
 #define I8_B_PLANE (I8_KT * I8_BN)   // 2048 bytes: [4 K groups][4 MN chunks][8 rows][16 bytes]
@@ -127,31 +127,32 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = 64, M = 128 (dense)
 #define I8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((I8_BN >> 3) << 17) | ((I8_BM >> 4) << 24))
 
+// Persistent kernel: one CTA per SM walks tiles cta, cta + gridDim.x, ... of the flattened (superblock, M tile,
+// N tile) list; the epilogue of tile i (fp64 recombination already staged in shared memory, atomics still to
+// do) overlaps the main loop of tile i + 1.
 template <int S>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const signed char *__restrict__ aplanes,
+vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_off, int nsb, int ntiles,
+                   const int *__restrict__ idx, const signed char *__restrict__ aplanes,
                    const int64_t *__restrict__ a_off, const signed char *__restrict__ bplanes,
                    const int64_t *__restrict__ b_off, const double *__restrict__ ascale,
                    const double *__restrict__ bscale, int sbp, int nao, double *__restrict__ mat) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * I8_B_PLANE, STAGE = A_STAGE + B_STAGE;
     constexpr uint32_t LBO_A = (I8_BM / 16) * 128, LBO_B = (I8_BN / 16) * 128;   // stride between 8-row K groups
-    __shared__ uint64_t full_bar[I8_STAGES], empty_bar[I8_STAGES], accum_bar;
+    __shared__ uint64_t full_bar[I8_STAGES], empty_bar[I8_STAGES], accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
-    const SBDesc d = sbd[blockIdx.y];
-    const int ntn = d.nsp / I8_BN, ntm = (d.nsp + I8_BM - 1) / I8_BM;
-    if ((int)blockIdx.x >= ntn * ntm) return;
-    const int tm = blockIdx.x / ntn, tn = blockIdx.x % ntn;
-    const int m0 = tm * I8_BM, n0 = tn * I8_BN;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = sbp / I8_KT;
+    double *tile = reinterpret_cast<double *>(i8_smem + I8_STAGES * STAGE);   // epilogue staging, after the ring
 
     if (tid == 0) {
         for (int i = 0; i < I8_STAGES; i++) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(&accum_bar, 1);
+        mbar_init(&accum_full, 1);
+        mbar_init(&accum_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -164,17 +165,36 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, 
     const uint32_t tmem = tmem_base_smem;
     const uint32_t sbase = smem_u32(i8_smem);
 
+    // tile t -> (superblock, M tile, N tile); tile_off is the exclusive prefix of tiles per superblock
+    auto locate = [&](int t, int &sb, int &tm, int &tn) {
+        int lo = 0, hi = nsb;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (tile_off[mid] <= t) lo = mid; else hi = mid;
+        }
+        sb = lo;
+        const int ntn = sbd[sb].nsp / I8_BN;
+        const int r = t - tile_off[sb];
+        tm = r / ntn;
+        tn = r - tm * ntn;
+    };
+
     if (warp == 0) {
         // ===== producer: two contiguous blocks per stage =====
         if (lane == 0) {
-            const signed char *A = aplanes + a_off[blockIdx.y] + (int64_t)tm * nk * A_STAGE;
-            const signed char *B = bplanes + b_off[blockIdx.y] + (int64_t)tn * nk * B_STAGE;
-            for (int kt = 0; kt < nk; kt++) {
-                const int slot = kt % I8_STAGES;
-                mbar_wait(&empty_bar[slot], ((kt / I8_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full_bar[slot], STAGE);
-                bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
-                bulk_g2s(sbase + slot * STAGE + A_STAGE, B + (int64_t)kt * B_STAGE, B_STAGE, &full_bar[slot]);
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                int sb, tm, tn;
+                locate(t, sb, tm, tn);
+                const signed char *A = aplanes + a_off[sb] + (int64_t)tm * nk * A_STAGE;
+                const signed char *B = bplanes + b_off[sb] + (int64_t)tn * nk * B_STAGE;
+                for (int kt = 0; kt < nk; kt++, it++) {
+                    const int slot = it % I8_STAGES;
+                    mbar_wait(&empty_bar[slot], ((it / I8_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[slot], STAGE);
+                    bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
+                    bulk_g2s(sbase + slot * STAGE + A_STAGE, B + (int64_t)kt * B_STAGE, B_STAGE, &full_bar[slot]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -183,59 +203,74 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, 
             // MN-major, no swizzle: SBO = stride between 16-element MN chunks (128 B), LBO = stride between
             // 8-row K groups (A: 1024 B, B: 512 B)
             const uint64_t da0 = umma_desc(sbase, LBO_A, 128), db0 = umma_desc(sbase + A_STAGE, LBO_B, 128);
-            for (int kt = 0; kt < nk; kt++) {
-                const int slot = kt % I8_STAGES;
-                mbar_wait(&full_bar[slot], (kt / I8_STAGES) & 1);
+            int it = 0, nt = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, nt++) {
+                mbar_wait(&accum_empty, (nt & 1) ^ 1);          // the epilogue has drained the previous tile
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
+                for (int kt = 0; kt < nk; kt++, it++) {
+                    const int slot = it % I8_STAGES;
+                    mbar_wait(&full_bar[slot], (it / I8_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
 #pragma unroll
-                for (int dd = 0; dd < S; dd++)
+                    for (int dd = 0; dd < S; dd++)
 #pragma unroll
-                    for (int s2 = 0; s2 <= dd; s2++)
-                        umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
-                                db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), I8_IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
-                umma_commit(&empty_bar[slot]);         // frees the stage when the MMAs above retire
+                        for (int s2 = 0; s2 <= dd; s2++)
+                            umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                    db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), I8_IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[slot]);     // frees the stage when the MMAs above retire
+                }
+                umma_commit(&accum_full);
             }
-            umma_commit(&accum_bar);
         }
     } else if (warp >= 4) {
         // ===== epilogue warps: TMEM lanes 32 (warp % 4) .., both 32-column halves =====
-        mbar_wait(&accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;
         const int r = lg * 32 + lane;
-        const int row = m0 + r;
-        const double sa_ = row < d.nsp ? ascale[d.idx_off + row] : 0.0;
-        double *tile = reinterpret_cast<double *>(i8_smem);   // every MMA reading the stages has retired
+        int nt = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, nt++) {
+            int sb, tm, tn;
+            locate(t, sb, tm, tn);
+            const SBDesc d = sbd[sb];
+            const int m0 = tm * I8_BM, n0 = tn * I8_BN;
+            const int row = m0 + r;
+            const double sa_ = row < d.nsp ? ascale[d.idx_off + row] : 0.0;
+            mbar_wait(&accum_full, nt & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-            double acc[32];
+            for (int ch = 0; ch < 2; ch++) {
+                double acc[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) acc[j] = 0.0;
+                for (int j = 0; j < 32; j++) acc[j] = 0.0;
 #pragma unroll
-            for (int dd = S - 1; dd >= 0; dd--) {      // smallest terms first
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
-                const double sc = ldexp(1.0, -12 - 7 * dd);
+                for (int dd = S - 1; dd >= 0; dd--) {  // smallest terms first
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
+                    const double sc = ldexp(1.0, -12 - 7 * dd);
 #pragma unroll
-                for (int j = 0; j < 32; j++) acc[j] += (double)(int)v[j] * sc;
+                    for (int j = 0; j < 32; j++) acc[j] += (double)(int)v[j] * sc;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j++) tile[r * I8_EPI_LD + ch * 32 + j] = acc[j] * sa_;
             }
-#pragma unroll
-            for (int j = 0; j < 32; j++) tile[r * I8_EPI_LD + ch * 32 + j] = acc[j] * sa_;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps only
-        const int *ix = idx + d.idx_off;
-        const int c0 = n0 + lane, c1 = n0 + 32 + lane;
-        const int b0 = ix[c0], b1 = ix[c1];
-        const double s0 = bscale[d.idx_off + c0], s1 = bscale[d.idx_off + c1];
-        for (int rr = lg; rr < I8_BM; rr += 4) {
-            const int grow = m0 + rr;
-            if (grow >= d.nsp) break;
-            const int a = ix[grow];
-            if (a >= nao) continue;
-            double *dst = mat + (int64_t)a * nao;
-            if (b0 < nao) atomicAdd(dst + b0, tile[rr * I8_EPI_LD + lane] * s0);
-            if (b1 < nao) atomicAdd(dst + b1, tile[rr * I8_EPI_LD + 32 + lane] * s1);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps: TMEM drained, tile staged
+            if (warp == 4 && lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+            const int *ix = idx + d.idx_off;
+            const int c0 = n0 + lane, c1 = n0 + 32 + lane;
+            const int b0 = ix[c0], b1 = ix[c1];
+            const double s0 = bscale[d.idx_off + c0], s1 = bscale[d.idx_off + c1];
+            for (int rr = lg; rr < I8_BM; rr += 4) {
+                const int grow = m0 + rr;
+                if (grow >= d.nsp) break;
+                const int a = ix[grow];
+                if (a >= nao) continue;
+                double *dst = mat + (int64_t)a * nao;
+                if (b0 < nao) atomicAdd(dst + b0, tile[rr * I8_EPI_LD + lane] * s0);
+                if (b1 < nao) atomicAdd(dst + b1, tile[rr * I8_EPI_LD + 32 + lane] * s1);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");    // the staging tile is free again
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -264,33 +299,32 @@ extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int m
 template <int S>
 static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *vb,
                       const int64_t *vb_off, const signed char *aplanes, const int64_t *a_off, const double *ascale,
-                      signed char *bplanes, const int64_t *b_off, double *bscale, int nao, double *mat,
-                      cudaStream_t st) {
+                      signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
+                      int nao, double *mat, cudaStream_t st) {
     dim3 gs((unsigned)(max_nsp / 64), (unsigned)nsb);
     prof_begin(PROF_I8_SLICE, st);
     sb_slice_kernel<S, I8_BN><<<gs, 256, 0, st>>>(sbd, vb, vb_off, 0, sbp, b_off, bplanes, bscale);
     prof_end(st);
     QC_LAUNCHED(1);
-    size_t smem = (size_t)I8_STAGES * S * (I8_A_PLANE + I8_B_PLANE);
-    if (smem < sizeof(double) * I8_BM * I8_EPI_LD) smem = sizeof(double) * I8_BM * I8_EPI_LD;
+    const size_t smem = (size_t)I8_STAGES * S * (I8_A_PLANE + I8_B_PLANE) + sizeof(double) * I8_BM * I8_EPI_LD;
     QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int maxtiles = (max_nsp / I8_BN) * ((max_nsp + I8_BM - 1) / I8_BM);
-    dim3 grid((unsigned)maxtiles, (unsigned)nsb);
     prof_begin(PROF_VXC_GEMM, st);
-    vxc_i8_gemm_kernel<S><<<grid, I8_THREADS, smem, st>>>(sbd, idx, aplanes, a_off, bplanes, b_off, ascale, bscale, sbp,
-                                                          nao, mat);
+    vxc_i8_gemm_kernel<S><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, tile_off, nsb, ntiles, idx, aplanes, a_off, bplanes,
+                                                           b_off, ascale, bscale, sbp, nao, mat);
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;
 }
 
 // Same contract as b200qc_vxc_sb, with the GEMM on tcgen05 int8 slices.  aplanes / a_off / ascale come from
-// b200qc_vxc_i8_prepare; bplanes (nslice * sum_sb sbp * nsp bytes at b_off[sb]) and bscale (sum_sb nsp) are scratch.
+// b200qc_vxc_i8_prepare; bplanes (nslice * sum_sb sbp * nsp bytes at b_off[sb]) and bscale (sum_sb nsp) are scratch;
+// tile_off[sb] = exclusive prefix of ceil(nsp / 128) * (nsp / 64) (device int32), ntiles = its total.
 extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
                                 const double *ao, const double *weights, const double *vrho, const double *vgrad,
                                 int nao, const int64_t *vb_off, double *vb, const signed char *aplanes,
                                 const int64_t *a_off, const double *ascale, signed char *bplanes,
-                                const int64_t *b_off, double *bscale, double *mat, void *stream) {
+                                const int64_t *b_off, double *bscale, const int *tile_off, int ntiles, double *mat,
+                                void *stream) {
     QC_REQUIRE(sbp % I8_KT == 0 && sbp % GM_BM == 0, "superblock size must be a multiple of 128");
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
     QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
@@ -309,6 +343,6 @@ extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_ns
     prof_end(st);
     QC_LAUNCHED(1);
     if (nslice == 5)
-        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, nao, mat, st);
-    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, nao, mat, st);
+        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
+    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
 }

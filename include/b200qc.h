@@ -123,13 +123,16 @@ int b200qc_vxc_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *
  * TMEM, fp64 recombination; |error| ~ 1e-10 / 1e-12 of the fp64 result).  prepare slices the static AO
  * values once into the tiled operand order: aplanes = sum_sb nslice * sbp * ceil(nsp / 128) * 128 bytes
  * (zero-filled by the caller) at a_off[sb], ascale = sum_sb nsp doubles.  bplanes (sum_sb nslice * sbp * nsp
- * bytes at b_off[sb]) and bscale are per-call scratch. */
+ * bytes at b_off[sb]) and bscale are per-call scratch; tile_off[sb] = exclusive prefix (device int32) of the
+ * ceil(nsp / 128) * (nsp / 64) output tiles per superblock, ntiles their total (the GEMM is one persistent
+ * CTA per SM walking that list). */
 int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const double *ao,
                           const int64_t *a_off, signed char *aplanes, double *ascale, void *stream);
 int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx, const double *ao,
                      const double *weights, const double *vrho, const double *vgrad, int nao, const int64_t *vb_off,
                      double *vb, const signed char *aplanes, const int64_t *a_off, const double *ascale,
-                     signed char *bplanes, const int64_t *b_off, double *bscale, double *mat, void *stream);
+                     signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
+                     double *mat, void *stream);
 
 /* ---- one- and two-electron integrals (Rys quadrature) ---------------------------------- */
 /* kind: 0 int1e_ovlp, 1 int1e_kin, 2 int1e_nuc, 3 int1e_rinv (origin rinv_orig[3], host).
