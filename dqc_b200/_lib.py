@@ -74,6 +74,13 @@ _SIGS = {
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_rho_i8_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_rho_sb_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
     "b200qc_int1e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_int2c2e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -536,7 +543,7 @@ class GridBlocks(object):
 
     def __init__(self, basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, weights: torch.Tensor,
                  deriv: int, sbp: int = 1024, eps: float = 1e-12, flags: Optional[np.ndarray] = None,
-                 i8_slices: int = 0, i8_variant: int = 0):
+                 i8_slices: int = 0, i8_variant: int = 0, rho_i8_slices: int = 0):
         lib = load()
         dev = coords.device
         self.basis, self.sh0, self.sh1 = basis, sh0, sh1
@@ -610,12 +617,33 @@ class GridBlocks(object):
                                              _ptr(self.d_a_off), _ptr(self.aplanes), _ptr(self.ascale), _stream()),
                    "vxc_i8_prepare")
 
+        # optional tcgen05 int8 form of the density GEMM: AO rows sliced once here
+        self.rho_i8_slices = int(rho_i8_slices)
+        if self.rho_i8_slices and self.nsb:
+            S = self.rho_i8_slices
+            self.d_ra_off = tt(excl(S * self.sbp * nsp), torch.int64)
+            self.d_rb_off = tt(excl(S * nsp * nsp), torch.int64)
+            self.r_aplanes = torch.empty(int((S * self.sbp * nsp).sum()), dtype=torch.int8, device=dev)
+            self.r_bplanes = torch.empty(int((S * nsp * nsp).sum()), dtype=torch.int8, device=dev)
+            self.r_rscale = torch.empty(self.nsb * self.sbp, dtype=torch.float64, device=dev)
+            self.r_cscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
+            _check(lib.b200qc_rho_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, S, _ptr(self.ao),
+                                             _ptr(self.d_ra_off), _ptr(self.r_aplanes), _ptr(self.r_rscale), _stream()),
+                   "rho_i8_prepare")
+
     def rho(self, dm: torch.Tensor, with_grad: bool):
         """dm (nao, nao) symmetric AO-basis density -> rho (ngl,), grad (3, ngl) | None (zero in the padding)."""
         lib = load()
         assert dm.shape == (self.nao, self.nao) and (not with_grad or self.deriv)
         r = torch.empty(self.ngl, dtype=torch.float64, device=dm.device)
         g = torch.empty((3, self.ngl), dtype=torch.float64, device=dm.device) if with_grad else None
+        if self.rho_i8_slices and self.nsb:
+            _check(lib.b200qc_rho_sb_i8(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.rho_i8_slices,
+                                        _ptr(self.d_idx), _ptr(self.ao), _ptr(dm.contiguous()), self.nao,
+                                        _ptr(self.r_aplanes), _ptr(self.d_ra_off), _ptr(self.r_rscale),
+                                        _ptr(self.r_bplanes), _ptr(self.d_rb_off), _ptr(self.r_cscale), _ptr(r), _ptr(g),
+                                        _stream()), "rho_sb_i8")
+            return r, g
         _check(lib.b200qc_rho_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
                                  _ptr(dm.contiguous()), self.nao, _ptr(self.dsb), _ptr(r), _ptr(g), _stream()), "rho_sb")
         return r, g

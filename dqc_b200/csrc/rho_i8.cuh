@@ -1,0 +1,308 @@
+// K2 on the 5th-generation tensor cores: X = phi_sb D_sb as an error-free sliced int8 GEMM (same Ozaki
+// scheme and pipeline as vxc_i8.cuh), with the density contraction fused into the epilogue:
+//     rho_g = sum_nu X_g,nu phi_g,nu,     grad_d rho_g = 2 sum_nu X_g,nu d_d phi_g,nu.
+// GEMM roles: M = 128 grid points (TMEM lanes), N = 64 AOs per tile, K = the kept AOs of the superblock.
+// Both operands are K-major: A = phi rows (sliced once at set-up, scale per grid point), B = rows of the
+// gathered symmetric density D_sb (gathered + sliced every call, scale per row).  A work unit is one
+// (superblock, 128-row block); its CTA walks the N tiles, the epilogue warps drain the six int32
+// accumulators to fp64 registers (freeing TMEM for the next N tile at once), then multiply with the fp64
+// AO values of the same rows and keep the four row sums in registers across N tiles -- X never leaves the
+// SM, exactly like the DMMA kernel (rho.cuh), and no atomics are needed.
+#pragma once
+#include "vxc_i8.cuh"
+
+#define RI8_STAGES 5      // no staging tile here: 5 x 36 KB ring
+
+// ---- A operand: phi rows -> S int8 planes, K-major tiles; scale per grid row ----
+// out (per SB, bytes): [row tile = g / 128][k tile = mu / 32][slice][(mu % 32) / 16][(g % 128) / 8][g % 8][mu % 16]
+template <int S>
+__global__ void __launch_bounds__(256)
+sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp,
+                     const int64_t *__restrict__ p_off, signed char *__restrict__ planes, double *__restrict__ rscale) {
+    const int sb = blockIdx.y;
+    const SBDesc d = sbd[sb];
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);     // one warp per grid row
+    if (g >= sbp) return;
+    const int64_t ld = d.nsp;
+    const double *X = ao + d.ao_off + (int64_t)g * ld;
+    double m = 0.0;
+    for (int c = lane; c < d.nsp; c += 32) m = fmax(m, fabs(X[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    int e = 0;
+    if (m > 0.0) frexp(m, &e);
+    const double inv = ldexp(64.0, -e);
+    if (lane == 0) rscale[(int64_t)sb * sbp + g] = ldexp(1.0, e);
+    const int nkt = d.nsp / I8_KT;
+    signed char *P = planes + p_off[sb] + (int64_t)(g >> 7) * nkt * S * I8_A_PLANE + ((g & 127) >> 3) * 128 + (g & 7) * 16;
+    for (int c = lane; c < d.nsp; c += 32) {
+        double y = X[c] * inv;
+        signed char *Q = P + (int64_t)(c >> 5) * S * I8_A_PLANE + ((c & 31) >> 4) * 2048 + (c & 15);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const double q = rint(y);
+            Q[s * I8_A_PLANE] = (signed char)(int)q;
+            y = (y - q) * 128.0;
+        }
+    }
+}
+
+// ---- B operand: D_sb[nu][mu] = D[idx_nu][idx_mu] gathered and sliced, K-major tiles; scale per row nu ----
+// out (per SB, bytes): [n tile = nu / 64][k tile = mu / 32][slice][(mu % 32) / 16][(nu % 64) / 8][nu % 8][mu % 16]
+template <int S>
+__global__ void __launch_bounds__(256)
+sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const double *__restrict__ dm,
+                          int nao, const int64_t *__restrict__ p_off, signed char *__restrict__ planes,
+                          double *__restrict__ cscale) {
+    const int sb = blockIdx.y;
+    const SBDesc d = sbd[sb];
+    const int lane = threadIdx.x & 31;
+    const int nu = blockIdx.x * 8 + (threadIdx.x >> 5);    // one warp per row of D_sb
+    if (nu >= d.nsp) return;
+    const int *ix = idx + d.idx_off;
+    const int a = ix[nu];
+    const double *row = dm + (int64_t)(a < nao ? a : 0) * nao;
+    double m = 0.0;
+    for (int c = lane; c < d.nsp; c += 32) {
+        const int b = ix[c];
+        if (a < nao && b < nao) m = fmax(m, fabs(row[b]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    int e = 0;
+    if (m > 0.0) frexp(m, &e);
+    const double inv = ldexp(64.0, -e);
+    if (lane == 0) cscale[d.idx_off + nu] = ldexp(1.0, e);
+    const int nkt = d.nsp / I8_KT;
+    signed char *P = planes + p_off[sb] + (int64_t)(nu >> 6) * nkt * S * I8_B_PLANE + ((nu & 63) >> 3) * 128 + (nu & 7) * 16;
+    for (int c = lane; c < d.nsp; c += 32) {
+        const int b = ix[c];
+        double y = (a < nao && b < nao) ? row[b] * inv : 0.0;
+        signed char *Q = P + (int64_t)(c >> 5) * S * I8_B_PLANE + ((c & 31) >> 4) * 1024 + (c & 15);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const double q = rint(y);
+            Q[s * I8_B_PLANE] = (signed char)(int)q;
+            y = (y - q) * 128.0;
+        }
+    }
+}
+
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
+#define RI8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((I8_BN >> 3) << 17) | ((I8_BM >> 4) << 24))
+
+template <int S, int NCOMP>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__restrict__ ao,
+              const signed char *__restrict__ aplanes, const int64_t *__restrict__ a_off,
+              const signed char *__restrict__ bplanes, const int64_t *__restrict__ b_off,
+              const double *__restrict__ rscale, const double *__restrict__ cscale, int64_t ngrid_ld,
+              double *__restrict__ rho, double *__restrict__ grad) {
+    extern __shared__ __align__(1024) unsigned char i8_smem[];
+    constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * I8_B_PLANE, STAGE = A_STAGE + B_STAGE;
+    __shared__ uint64_t full_bar[RI8_STAGES], empty_bar[RI8_STAGES], accum_full, accum_empty;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mtiles = sbp / I8_BM;
+    const int nunits = nsb * mtiles;
+
+    if (tid == 0) {
+        for (int i = 0; i < RI8_STAGES; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&accum_full, 1);
+        mbar_init(&accum_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_smem;
+    const uint32_t sbase = smem_u32(i8_smem);
+
+    if (warp == 0) {
+        // ===== producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const int sb = u / mtiles, mt = u - sb * mtiles;
+                const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = nsp / I8_BN;
+                const signed char *A = aplanes + a_off[sb] + (int64_t)mt * nkt * A_STAGE;
+                const signed char *B = bplanes + b_off[sb];
+                for (int tn = 0; tn < ntn; tn++)
+                    for (int kt = 0; kt < nkt; kt++, it++) {
+                        const int slot = it % RI8_STAGES;
+                        mbar_wait(&empty_bar[slot], ((it / RI8_STAGES) & 1) ^ 1);
+                        mbar_expect_tx(&full_bar[slot], STAGE);
+                        bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
+                        bulk_g2s(sbase + slot * STAGE + A_STAGE, B + ((int64_t)tn * nkt + kt) * B_STAGE, B_STAGE,
+                                 &full_bar[slot]);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // K-major, no swizzle: LBO = stride between the two 16-byte K chunks of a K = 32 step
+            // (A: 2048 B, B: 1024 B), SBO = stride between 8-row groups (128 B)
+            const uint64_t da0 = umma_desc(sbase, 2048, 128), db0 = umma_desc(sbase + A_STAGE, 1024, 128);
+            int it = 0, nt = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const int sb = u / mtiles;
+                const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = nsp / I8_BN;
+                for (int tn = 0; tn < ntn; tn++, nt++) {
+                    mbar_wait(&accum_empty, (nt & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kt = 0; kt < nkt; kt++, it++) {
+                        const int slot = it % RI8_STAGES;
+                        mbar_wait(&full_bar[slot], (it / RI8_STAGES) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
+#pragma unroll
+                        for (int dd = 0; dd < S; dd++)
+#pragma unroll
+                            for (int s2 = 0; s2 <= dd; s2++)
+                                umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                        db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), RI8_IDESC,
+                                        (kt > 0 || s2 > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[slot]);
+                    }
+                    umma_commit(&accum_full);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps: thread = grid row (TMEM lane) =====
+        const int lg = warp & 3;
+        const int r = lg * 32 + lane;
+        int nt = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const int sb = u / mtiles, mt = u - sb * mtiles;
+            const SBDesc d = sbd[sb];
+            const int ntn = d.nsp / I8_BN;
+            const int64_t ld = d.nsp;
+            const int grow = mt * I8_BM + r;                             // row inside the superblock
+            const double *phi = ao + d.ao_off + (int64_t)grow * ld;      // component 0, this row
+            double part[NCOMP];
+#pragma unroll
+            for (int c = 0; c < NCOMP; c++) part[c] = 0.0;
+            for (int tn = 0; tn < ntn; tn++, nt++) {
+                mbar_wait(&accum_full, nt & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                double x[64];
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) x[ch * 32 + j] = 0.0;
+#pragma unroll
+                    for (int dd = S - 1; dd >= 0; dd--) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
+                        const double sc = ldexp(1.0, -12 - 7 * dd);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) x[ch * 32 + j] += (double)(int)v[j] * sc;
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // all four warps have drained TMEM
+                if (warp == 4 && lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+                // column scales, then the row dots with the fp64 AO values of this row
+                const int n0 = tn * I8_BN;
+                const double *cs = cscale + d.idx_off + n0;
+#pragma unroll
+                for (int j = 0; j < 64; j += 2) {
+                    const double2 s2 = *reinterpret_cast<const double2 *>(cs + j);
+                    x[j] *= s2.x;
+                    x[j + 1] *= s2.y;
+                }
+#pragma unroll
+                for (int c = 0; c < NCOMP; c++) {
+                    const double *row = phi + (int64_t)c * sbp * ld + n0;
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 2) {
+                        const double2 v2 = *reinterpret_cast<const double2 *>(row + j);
+                        s += x[j] * v2.x + x[j + 1] * v2.y;
+                    }
+                    part[c] += s;
+                }
+            }
+            const double sa_ = rscale[(int64_t)sb * sbp + grow];
+            const int64_t g = (int64_t)sb * sbp + grow;
+            rho[g] = sa_ * part[0];
+            if (NCOMP == 4) {
+#pragma unroll
+                for (int dd = 0; dd < 3; dd++) grad[(int64_t)dd * ngrid_ld + g] = 2.0 * sa_ * part[dd + 1];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// Slices the static AO values (component 0) of every superblock once, row-wise, into the K-major tiled
+// A-operand order: aplanes = sum_sb nslice * sbp * nsp bytes at a_off[sb]; rscale = nsb * sbp doubles.
+extern "C" int b200qc_rho_i8_prepare(const void *sbdesc, int nsb, int sbp, int nslice, const double *ao,
+                                     const int64_t *a_off, signed char *aplanes, double *rscale, void *stream) {
+    QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE(sbp % I8_BM == 0, "superblock size must be a multiple of 128");
+    if (nsb == 0) return 0;
+    dim3 grid((unsigned)(sbp / 8), (unsigned)nsb);
+    const SBDesc *sbd = (const SBDesc *)sbdesc;
+    if (nslice == 5) sb_slice_rows_kernel<5><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, a_off, aplanes, rscale);
+    else sb_slice_rows_kernel<6><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, a_off, aplanes, rscale);
+    QC_LAUNCHED(1);
+    return 0;
+}
+
+template <int S>
+static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                      const double *dm, int nao, const signed char *aplanes, const int64_t *a_off,
+                      const double *rscale, signed char *bplanes, const int64_t *b_off, double *cscale, double *rho,
+                      double *grad, cudaStream_t st) {
+    dim3 gg((unsigned)(max_nsp / 8), (unsigned)nsb);
+    prof_begin(PROF_SB_GATHER, st);
+    sb_gather_slice_dm_kernel<S><<<gg, 256, 0, st>>>(sbd, idx, dm, nao, b_off, bplanes, cscale);
+    prof_end(st);
+    QC_LAUNCHED(1);
+    const size_t smem = (size_t)RI8_STAGES * S * (I8_A_PLANE + I8_B_PLANE);
+    const int64_t ngl = (int64_t)nsb * sbp;
+    prof_begin(PROF_RHO, st);
+    if (grad) {
+        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rho_i8_kernel<S, 4><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off, bplanes, b_off, rscale,
+                                                              cscale, ngl, rho, grad);
+    } else {
+        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rho_i8_kernel<S, 1><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off, bplanes, b_off, rscale,
+                                                              cscale, ngl, rho, grad);
+    }
+    prof_end(st);
+    QC_LAUNCHED(1);
+    return 0;
+}
+
+// Same contract as b200qc_rho_sb with the GEMM on tcgen05 int8 slices.  bplanes (sum_sb nslice * nsp^2 bytes at
+// b_off[sb]) and cscale (sum_sb nsp doubles) are per-call scratch.
+extern "C" int b200qc_rho_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
+                                const double *ao, const double *dm, int nao, const signed char *aplanes,
+                                const int64_t *a_off, const double *rscale, signed char *bplanes,
+                                const int64_t *b_off, double *cscale, double *rho, double *grad, void *stream) {
+    QC_REQUIRE(sbp % I8_BM == 0, "superblock size must be a multiple of 128");
+    QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE((int64_t)max_nsp * 6 * 4096 < (1LL << 31), "too many AOs per superblock for exact int32 accumulation");
+    if (nsb == 0) return 0;
+    const SBDesc *sbd = (const SBDesc *)sbdesc;
+    cudaStream_t st = as_stream(stream);
+    if (nslice == 5)
+        return rho_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
+    return rho_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
+}

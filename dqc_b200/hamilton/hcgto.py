@@ -172,7 +172,7 @@ class HamiltonCGTO(BaseHamilton):
             self.dvolume = dvol_all[g0:g1].contiguous()
             self._gb = _lib.GridBlocks(self._devbasis, s0, s1, self.rgrid, self.dvolume, deriv, sbp, eps,
                                        flags=flags[sb_lo:sb_hi], i8_slices=config.VXC_I8_SLICES,
-                                       i8_variant=config.I8_VARIANT)
+                                       i8_variant=config.I8_VARIANT, rho_i8_slices=config.RHO_I8_SLICES)
         self.is_grid_set = True
         self.is_ao_set = True
         self.is_grad_ao_set = self.xcfamily == 2
