@@ -197,17 +197,11 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 double x[64];
 #pragma unroll
-                for (int ch = 0; ch < 2; ch++) {
+                for (int ch = 0; ch < 4; ch++) {
+                    double acc[16];
+                    i8_recombine16<S>(tmem + ((uint32_t)(lg * 32) << 16), ch * 16, acc);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) x[ch * 32 + j] = 0.0;
-#pragma unroll
-                    for (int dd = S - 1; dd >= 0; dd--) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
-                        const double sc = ldexp(1.0, -12 - 7 * dd);
-#pragma unroll
-                        for (int j = 0; j < 32; j++) x[ch * 32 + j] += (double)(int)v[j] * sc;
-                    }
+                    for (int j = 0; j < 16; j++) x[ch * 16 + j] = acc[j];
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");          // all four warps have drained TMEM

@@ -116,6 +116,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 16 columns x 32 lanes, no wait: issue several, then tmem_wait_ld() once
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Recombination of the S anti-diagonal accumulators of 16 columns: the int32 partial sums are merged exactly
+// in int64 (sum_d acc_d 128^(S-1-d), |.| < 2^60), converted once and scaled -- 1 I2F per element instead of S.
+template <int S>
+__device__ __forceinline__ void i8_recombine16(uint32_t tmem_lane_base, int col0, double (&out)[16]) {
+    uint32_t v[S][16];
+#pragma unroll
+    for (int dd = 0; dd < S; dd++) tmem_ld16_nowait(tmem_lane_base + dd * I8_BN + col0, v[dd]);
+    tmem_wait_ld();
+    const double sc = ldexp(1.0, -12 - 7 * (S - 1));
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        long long t = (long long)(int)v[0][j];
+#pragma unroll
+        for (int dd = 1; dd < S; dd++) t = (t << 7) + (long long)(int)v[dd][j];
+        out[j] = __ll2double_rn(t) * sc;
+    }
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
@@ -127,6 +155,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = 64, M = 128 (dense)
 #define I8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((I8_BN >> 3) << 17) | ((I8_BM >> 4) << 24))
 
+static int g_i8_variant = 0;   // timing experiments only (b200qc_i8_debug_variant)
+extern "C" int b200qc_i8_debug_variant(int v) { g_i8_variant = v; return 0; }
+
 // Persistent kernel: one CTA per SM walks tiles cta, cta + gridDim.x, ... of the flattened (superblock, M tile,
 // N tile) list; the epilogue of tile i (fp64 recombination already staged in shared memory, atomics still to
 // do) overlaps the main loop of tile i + 1.
@@ -136,7 +167,7 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
                    const int *__restrict__ idx, const signed char *__restrict__ aplanes,
                    const int64_t *__restrict__ a_off, const signed char *__restrict__ bplanes,
                    const int64_t *__restrict__ b_off, const double *__restrict__ ascale,
-                   const double *__restrict__ bscale, int sbp, int nao, double *__restrict__ mat) {
+                   const double *__restrict__ bscale, int sbp, int nao, double *__restrict__ mat, int variant) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * I8_B_PLANE, STAGE = A_STAGE + B_STAGE;
     constexpr uint32_t LBO_A = (I8_BM / 16) * 128, LBO_B = (I8_BN / 16) * 128;   // stride between 8-row K groups
@@ -212,12 +243,14 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
                     mbar_wait(&full_bar[slot], (it / I8_STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
+                    if (variant != 2) {                // (variant 2: timing experiment without the MMAs)
 #pragma unroll
                     for (int dd = 0; dd < S; dd++)
 #pragma unroll
                         for (int s2 = 0; s2 <= dd; s2++)
                             umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
                                     db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), I8_IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
+                    }
                     umma_commit(&empty_bar[slot]);     // frees the stage when the MMAs above retire
                 }
                 umma_commit(&accum_full);
@@ -237,21 +270,18 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
             const double sa_ = row < d.nsp ? ascale[d.idx_off + row] : 0.0;
             mbar_wait(&accum_full, nt & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (variant == 1) {                        // timing experiment without the epilogue
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 4 && lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+                continue;
+            }
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                double acc[32];
+            for (int ch = 0; ch < 4; ch++) {
+                double acc[16];
+                i8_recombine16<S>(tmem + ((uint32_t)(lg * 32) << 16), ch * 16, acc);
 #pragma unroll
-                for (int j = 0; j < 32; j++) acc[j] = 0.0;
-#pragma unroll
-                for (int dd = S - 1; dd >= 0; dd--) {  // smallest terms first
-                    uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + dd * I8_BN + ch * 32, v);
-                    const double sc = ldexp(1.0, -12 - 7 * dd);
-#pragma unroll
-                    for (int j = 0; j < 32; j++) acc[j] += (double)(int)v[j] * sc;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j++) tile[r * I8_EPI_LD + ch * 32 + j] = acc[j] * sa_;
+                for (int j = 0; j < 16; j++) tile[r * I8_EPI_LD + ch * 16 + j] = acc[j] * sa_;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps: TMEM drained, tile staged
@@ -297,10 +327,24 @@ extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int m
 }
 
 template <int S>
-static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *vb,
+static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                      const double *weights, const double *vrho, const double *vgrad, double *vb,
                       const int64_t *vb_off, const signed char *aplanes, const int64_t *a_off, const double *ascale,
                       signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
                       int nao, double *mat, cudaStream_t st) {
+    // K4a: vb = w (v phi + 2 g . grad phi) in fp64 (one streaming pass at the HBM roofline), then the slicer.
+    // (A fused single-pass variant that staged a 32-column slab of vb in shared memory was slower: one
+    // 128 KB CTA per SM cannot keep enough loads in flight.)
+    const int64_t ngl = (int64_t)nsb * sbp;
+    const int wpb = 8;
+    const unsigned nb1 = (unsigned)((ngl + wpb - 1) / wpb);
+    prof_begin(PROF_VXC_VB, st);
+    if (vgrad)
+        vxc_vb_sb_kernel<4><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
+    else
+        vxc_vb_sb_kernel<1><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
+    prof_end(st);
+    QC_LAUNCHED(1);
     dim3 gs((unsigned)(max_nsp / 64), (unsigned)nsb);
     prof_begin(PROF_I8_SLICE, st);
     sb_slice_kernel<S, I8_BN><<<gs, 256, 0, st>>>(sbd, vb, vb_off, 0, sbp, b_off, bplanes, bscale);
@@ -310,7 +354,7 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(PROF_VXC_GEMM, st);
     vxc_i8_gemm_kernel<S><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, tile_off, nsb, ntiles, idx, aplanes, a_off, bplanes,
-                                                           b_off, ascale, bscale, sbp, nao, mat);
+                                                           b_off, ascale, bscale, sbp, nao, mat, g_i8_variant);
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;
@@ -332,17 +376,9 @@ extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_ns
     QC_CHECK(cudaMemsetAsync(mat, 0, sizeof(double) * nao * nao, st));
     if (nsb == 0) return 0;
     const SBDesc *sbd = (const SBDesc *)sbdesc;
-    const int64_t ngl = (int64_t)nsb * sbp;
-    const int wpb = 8;
-    const unsigned nb1 = (unsigned)((ngl + wpb - 1) / wpb);
-    prof_begin(PROF_VXC_VB, st);
-    if (vgrad)
-        vxc_vb_sb_kernel<4><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
-    else
-        vxc_vb_sb_kernel<1><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
-    prof_end(st);
-    QC_LAUNCHED(1);
     if (nslice == 5)
-        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
-    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, vb, vb_off, aplanes, a_off, ascale, bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
+        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+                             bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
+    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+                         bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
 }

@@ -18,7 +18,7 @@ class _Config:
     # Vxc GEMM on tcgen05 as an error-free sliced int8 product: 0 = off (fp64 DMMA), 5 or 6 = number of slices
     VXC_I8_SLICES: int = int(os.environ.get("B200QC_VXC_I8", "6"))
     # density GEMM (K2) on tcgen05 the same way: 0 = off (fp64 DMMA), 5 or 6 slices
-    RHO_I8_SLICES: int = int(os.environ.get("B200QC_RHO_I8", "0"))
+    RHO_I8_SLICES: int = int(os.environ.get("B200QC_RHO_I8", "6"))
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
     # without density fitting, keep both dense layouts of (ij|kl) in HBM when 2 * 8 * nao^4 bytes fit under
     # this (single GPU); beyond it J/K are built directly from Schwarz-screened quartets every iteration

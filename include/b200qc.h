@@ -134,6 +134,9 @@ int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nsli
                      signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
                      double *mat, void *stream);
 
+/* timing experiments on the kernel above: 0 = normal, 1 = skip the epilogue, 2 = skip the MMAs */
+int b200qc_i8_debug_variant(int v);
+
 /* K2 on tcgen05: the same contraction as b200qc_rho_sb with X = phi D as an error-free sliced int8 GEMM
  * (both operands K-major, int32 accumulators in TMEM) and the row dots with phi / grad phi fused into the
  * epilogue.  prepare slices the static AO values row-wise once: aplanes = sum_sb nslice * sbp * nsp bytes at
