@@ -345,25 +345,48 @@ def main():
     xc_flops = gb.flops_per_pass if gb is not None else 0.0      # 2 * sum_sb SBP * nsp^2 (K2 and K4 GEMM each)
     if gb is not None:
         config.update(sb_points=gb.sbp, ao_screen=gb.eps, kept_ao_fraction=round(gb.kept_fraction, 4),
+                      vxc_gemm=("tcgen05 int8 x%d slices" % gb.i8_slices) if gb.i8_slices else "fp64 DMMA",
+                      rho_gemm=("tcgen05 int8 x%d slices" % gb.rho_i8_slices) if gb.rho_i8_slices else "fp64 DMMA",
                       ao_resident_gb=round(gb.ao_bytes / 1e9, 2),
                       dense_equiv_flops_per_pass=2.0 * ngrid * h._nao_ao ** 2 / world)
     kern = {k: {"launches": c, "ms_per_launch": ms / c} for k, (c, ms) in prof.items()}
     dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
     roofline = None
+    def gemm_roofline(kname):
+        """K2 / K4 GEMM: fp64 DMMA form -> fraction of the measured DMMA peak; tcgen05 int8 (Ozaki) form ->
+        int8 ops (S (S + 1) / 2 slice products) against 2 x the measured bf16 tensor peak."""
+        t = kern[kname]["ms_per_launch"] * 1e-3
+        nsl = (gb.rho_i8_slices if kname == "rho_kernel" else gb.i8_slices) if gb is not None else 0
+        if nsl:
+            nprod = nsl * (nsl + 1) // 2
+            ops = xc_flops * nprod
+            peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+            return {"kernel": kname, "bound": "tensor", "achieved": ops / t / 1e12, "peak": peak, "unit": "TOP/s (int8)",
+                    "frac": ops / t / 1e12 / peak, "traffic": traffic.get(kname),
+                    "peak_source": "tcgen05.mma.kind::i8: 2 x bf16_tflops of MEASURED_PEAKS.json%s (int8 runs at twice the "
+                                   "bf16 rate on sm_100; no int8 entry in the file)" % ("" if "bf16_tflops" in peaks else " FALLBACK 1590"),
+                    "algorithmic_ops_per_launch": ops, "int8_slice_products": nprod,
+                    "fp64_equivalent_tflops": xc_flops / t / 1e12,
+                    "fp64_equivalent_vs_dmma_peak": xc_flops / t / 1e12 / dmma_peak}
+        ach = xc_flops / t / 1e12
+        return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": ach / dmma_peak, "traffic": traffic.get(kname),
+                "peak_source": "fp64 DMMA (mma.sync m8n8k4) issue-rate microbenchmark run in this process "
+                               "(b200qc_peak_fp64_dmma); MEASURED_PEAKS.json has no fp64 entry",
+                "algorithmic_flops_per_launch": xc_flops}
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as ft:
+            traffic = json.load(ft).get(args.workload, {})
+    except Exception:
+        pass
     if dominant in ("vxc_gemm_kernel", "rho_kernel"):
-        flops = xc_flops                           # per launch: 2 * SBP * nsp^2 summed over this rank's superblocks
-        ach = flops / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e12
-        roofline = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
-                    "frac": ach / dmma_peak, "traffic": None,
-                    "peak_source": "fp64 DMMA (mma.sync m8n8k4) issue-rate microbenchmark run in this process "
-                                   "(b200qc_peak_fp64_dmma); MEASURED_PEAKS.json has no fp64 entry -- tcgen05 has no "
-                                   "f64 kind, so the bf16 figure is not the bound of this kernel",
-                    "algorithmic_flops_per_launch": flops}
+        roofline = gemm_roofline(dominant)
     elif dominant in ("dfj_pass1_kernel", "dfj_pass2_kernel"):
         nb = h.df._j3c_packed.numel() * 8.0
         ach = nb / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "frac": ach / hbm_peak, "traffic": traffic.get(dominant), "peak_source": hbm_src,
                     "algorithmic_bytes_per_launch": nb}
     elif dominant == "gemv_rows_kernel":
         nb = 8.0 * h._nao_ao ** 4
@@ -387,18 +410,20 @@ def main():
         extra["vxc_vb_kernel"] = {"GB/s": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9,
                                   "frac_of_hbm": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     for k in ("rho_kernel", "vxc_gemm_kernel"):
-        if k in kern:
-            fl = xc_flops
-            extra[k] = {"TFLOP/s": fl / (kern[k]["ms_per_launch"] * 1e-3) / 1e12,
-                        "frac_of_fp64_dmma": fl / (kern[k]["ms_per_launch"] * 1e-3) / 1e12 / dmma_peak}
+        if k in kern and gb is not None:
+            r = gemm_roofline(k)
+            extra[k] = {kk: r[kk] for kk in ("achieved", "peak", "unit", "frac") if kk in r}
+            if "fp64_equivalent_tflops" in r:
+                extra[k]["fp64_equivalent_tflops"] = r["fp64_equivalent_tflops"]
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         ms, info, sample = run_cpu_reference(args.workload, 2, 1)
         cpu_baseline = {"value": ms, "unit": "ms", "cores": info["cores"], "kind": "port", "sample": sample}
 
-    xc_ms = sum(ms for k, (c, ms) in prof.items() if k in ("rho_kernel", "xc_kernel", "vxc_vb_kernel",
-                                                           "vxc_gemm_kernel", "slab_reduce_kernel")) / args.steps
+    xc_ms = sum(ms for k, (c, ms) in prof.items() if k in ("rho_kernel", "xc_kernel", "vxc_vb_kernel", "vxc_gemm_kernel",
+                                                           "slab_reduce_kernel", "sb_gather_dm_kernel",
+                                                           "sb_slice_kernel")) / args.steps
     line = {"metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

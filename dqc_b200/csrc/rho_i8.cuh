@@ -222,7 +222,8 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                     double s = 0.0;
 #pragma unroll
                     for (int j = 0; j < 64; j += 2) {
-                        const double2 v2 = *reinterpret_cast<const double2 *>(row + j);
+                        // streaming, zero-reuse read: keep it from evicting the re-used int8 operand planes from L2
+                        const double2 v2 = __ldcs(reinterpret_cast<const double2 *>(row + j));
                         s += x[j] * v2.x + x[j + 1] * v2.y;
                     }
                     part[c] += s;
