@@ -110,6 +110,15 @@ _SIGS = {
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_pack_tril": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_i8_slice": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_gemm_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
 }
 
 
@@ -523,6 +532,69 @@ def dfj_pass2(j3c_packed, nao, naux, coef):
 
 SB_DTYPE = np.dtype([("ao_off", np.int64), ("d_off", np.int64), ("nsp", np.int32), ("idx_off", np.int32),
                      ("shell_off", np.int32), ("nshell", np.int32)])
+
+
+# ------------------------------------------------------------------------------------------
+# fp64-accurate GEMM on tcgen05 (sliced int8, csrc/gemm_i8.cuh)
+
+class I8Operand(object):
+    """One fp64 operand of ``gemm_i8`` cut into int8 planes in the tiled UMMA order (b200qc_i8_slice).
+
+    Logical shape (nbatch, R, K): element (b, r, k) is read from ``src`` (a CUDA fp64 tensor, any layout) at
+    element offset ``b * sb + r * sr + k * sk`` -- or, with ``pair_ld``, from the packed (ij|P) tensor
+    (b = i, k = j, r = P).  ``role`` is "A" (128-row tiles) or "B" (64-row tiles)."""
+
+    def __init__(self, role: str, nbatch: int, R: int, K: int, nslice: int = 6, K_last: Optional[int] = None,
+                 device=None):
+        assert role in ("A", "B")
+        self.role, self.nbatch, self.R, self.K, self.S = role, int(nbatch), int(R), int(K), int(nslice)
+        self.K_last = self.K if K_last is None else int(K_last)
+        self.W = 128 if role == "A" else 64
+        self.Rpad, self.Kpad = round_up(self.R, self.W), round_up(self.K, 32)
+        self.rtiles, self.nk, self.nk_last = self.Rpad // self.W, self.Kpad // 32, round_up(self.K_last, 32) // 32
+        self.bstride = self.Rpad * self.Kpad * self.S           # bytes per batch
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.planes = torch.empty(self.nbatch * self.bstride, dtype=torch.int8, device=dev)
+        self.scales = torch.empty(self.nbatch * self.Rpad, dtype=torch.float64, device=dev)
+
+    def fill(self, src: torch.Tensor, sb: int, sr: int, sk: int, pair_ld: int = 0, offset: int = 0):
+        assert src.is_cuda and src.dtype == torch.float64
+        ptr = ctypes.c_void_p(src.data_ptr() + 8 * int(offset))
+        _check(load().b200qc_i8_slice(ptr, self.nbatch, int(sb), int(sr), int(sk), 1 if pair_ld else 0, int(pair_ld),
+                                      self.R, self.K, self.K_last, self.Rpad, self.Kpad, self.W, self.S,
+                                      _ptr(self.planes), _ptr(self.scales), _stream()), "i8_slice")
+        return self
+
+
+def gemm_i8(a: I8Operand, b: I8Operand, out: torch.Tensor, c_bstride: int, ldc: int, M: int, N: int, mode: int = 0,
+            alpha: float = 1.0, nbatch: Optional[int] = None, a_shared: bool = False, b_shared: bool = False):
+    """out[b][m][n] (=, +=) alpha * sum_k A[b][m][k] B[b][n][k] on the tcgen05 int8 engine (b200qc_gemm_i8)."""
+    assert a.role == "A" and b.role == "B" and a.S == b.S and a.nk == b.nk and a.nk_last == b.nk_last
+    nb = int(nbatch if nbatch is not None else max(a.nbatch, b.nbatch))
+    assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous()
+    _check(load().b200qc_gemm_i8(_ptr(a.planes), _ptr(a.scales), 0 if a_shared else a.bstride, 0 if a_shared else a.Rpad,
+                                 _ptr(b.planes), _ptr(b.scales), 0 if b_shared else b.bstride, 0 if b_shared else b.Rpad,
+                                 nb, a.rtiles, b.rtiles, a.nk, a.nk_last, a.S, int(M), int(N), float(alpha),
+                                 _ptr(out), int(c_bstride), int(ldc), int(mode), _stream()), "gemm_i8")
+    return out
+
+
+I8_KCHUNK = {5: 65536, 6: 32768}   # longest K per batch with exact integer accumulation
+
+
+def gemm_f64emu(x: torch.Tensor, y: torch.Tensor, nslice: int = 6, kchunk: Optional[int] = None) -> torch.Tensor:
+    """x (M, K) @ y (N, K)^T in fp64 accuracy on the int8 tensor cores (split over K chunks when K is long)."""
+    assert x.ndim == 2 and y.ndim == 2 and x.shape[1] == y.shape[1]
+    x, y = x.contiguous(), y.contiguous()
+    M, K = x.shape
+    N = y.shape[0]
+    kc = min(I8_KCHUNK[nslice] if kchunk is None else int(kchunk), round_up(K, 32))
+    nchunk = (K + kc - 1) // kc
+    k_last = K - (nchunk - 1) * kc
+    a = I8Operand("A", nchunk, M, kc, nslice, K_last=k_last, device=x.device).fill(x, kc, K, 1)
+    b = I8Operand("B", nchunk, N, kc, nslice, K_last=k_last, device=x.device).fill(y, kc, K, 1)
+    out = torch.zeros(M, N, dtype=torch.float64, device=x.device)
+    return gemm_i8(a, b, out, 0, N, M, N, mode=0 if nchunk == 1 else 1)
 
 
 def ao_screen(basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, sbp: int, eps: float, deriv: int):

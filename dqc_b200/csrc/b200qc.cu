@@ -1,4 +1,5 @@
-// b200qc -- single translation unit of the B200-native Fock-build library (see include/b200qc.h).
+// b200qc -- primary translation unit of the B200-native Fock-build library (see include/b200qc.h): integrals,
+// fp64 kernels, constant tables, shared host state.  The tcgen05 kernels are in b200qc_tc.cu.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 #include "common.cuh"
 #include "tables.cuh"
@@ -9,8 +10,6 @@
 #include "rho.cuh"
 #include "vxc.cuh"
 #include "xc_sb.cuh"
-#include "vxc_i8.cuh"
-#include "rho_i8.cuh"
 #include "rys.cuh"
 #include "ints.cuh"
 #include "jk.cuh"

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/b200qc.h"
@@ -15,8 +16,16 @@
 #define NUM_SMS 148
 
 // ---- error plumbing ----------------------------------------------------------------------
-static void b200qc_set_error(const std::string &msg);
-static int64_t g_launch_count = 0;
+// The library is two translation units (b200qc.cu: integrals, fp64 kernels, tables, plumbing; b200qc_tc.cu: the
+// tcgen05 kernels, -DB200QC_TU_SECONDARY).  Host state shared by both is defined once, in the primary one.
+#define QC_HIDDEN __attribute__((visibility("hidden")))
+#ifdef B200QC_TU_SECONDARY
+#define QC_SHARED(decl, init) extern QC_HIDDEN decl
+#else
+#define QC_SHARED(decl, init) QC_HIDDEN decl init
+#endif
+QC_HIDDEN void b200qc_set_error(const std::string &msg);
+QC_SHARED(int64_t g_launch_count, = 0);
 
 #define QC_CHECK(call)                                                                          \
     do {                                                                                        \
@@ -104,18 +113,19 @@ static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 // profile synchronises once and returns, per kernel id, launch count and summed device time.
 enum {
     PROF_AO_EVAL = 0, PROF_BECKE, PROF_RHO, PROF_XC, PROF_VXC_VB, PROF_VXC_GEMM, PROF_VXC_REDUCE,
-    PROF_DFJ_PASS1, PROF_DFJ_PASS2, PROF_DFJ_SMALL, PROF_JK, PROF_INTS, PROF_PEAK, PROF_SB_GATHER, PROF_GEMV, PROF_I8_SLICE, PROF_N
+    PROF_DFJ_PASS1, PROF_DFJ_PASS2, PROF_DFJ_SMALL, PROF_JK, PROF_INTS, PROF_PEAK, PROF_SB_GATHER, PROF_GEMV, PROF_I8_SLICE, PROF_GEMM_I8, PROF_N
 };
 static const char *const g_prof_names[PROF_N] = {
     "ao_eval_kernel", "becke_weights_kernel", "rho_kernel", "xc_kernel", "vxc_vb_kernel", "vxc_gemm_kernel",
     "slab_reduce_kernel", "dfj_pass1_kernel", "dfj_pass2_kernel", "dfj_small_kernels", "jk_kernel",
-    "int_dense_kernel", "dmma_peak_kernel", "sb_gather_dm_kernel", "gemv_rows_kernel", "sb_slice_kernel"};
+    "int_dense_kernel", "dmma_peak_kernel", "sb_gather_dm_kernel", "gemv_rows_kernel", "sb_slice_kernel",
+    "gemm_i8_kernel"};
 struct ProfRec {
     int id;
     cudaEvent_t a, b;
 };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
+QC_SHARED(bool g_prof_on, = false);
+QC_SHARED(std::vector<ProfRec> g_prof, );
 static inline void prof_begin(int id, cudaStream_t st) {
     if (!g_prof_on) return;
     ProfRec r;

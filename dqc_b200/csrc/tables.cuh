@@ -5,7 +5,7 @@
 #include <mutex>
 
 static thread_local std::string g_last_error;
-static void b200qc_set_error(const std::string &msg) { g_last_error = msg; }
+void b200qc_set_error(const std::string &msg) { g_last_error = msg; }
 
 extern "C" const char *b200qc_last_error(void) { return g_last_error.c_str(); }
 extern "C" int b200qc_version(void) { return 100; }

@@ -21,7 +21,7 @@
 // S (S + 1) / 2 MMAs per stage, tcgen05.commit frees the stage), warps 4-7 = epilogue (tcgen05.ld 32x32b,
 // fp64 recombination, tile staged in shared memory, row-wise coalesced fp64 atomics into M[idx][idx]).
 #pragma once
-#include "xc_sb.cuh"
+#include "sb_common.cuh"
 
 #define I8_BM 128
 #define I8_BN 64
@@ -369,7 +369,7 @@ extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_ns
                                 const int64_t *a_off, const double *ascale, signed char *bplanes,
                                 const int64_t *b_off, double *bscale, const int *tile_off, int ntiles, double *mat,
                                 void *stream) {
-    QC_REQUIRE(sbp % I8_KT == 0 && sbp % GM_BM == 0, "superblock size must be a multiple of 128");
+    QC_REQUIRE(sbp % I8_KT == 0 && sbp % I8_BM == 0, "superblock size must be a multiple of 128");
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
     QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
     cudaStream_t st = as_stream(stream);

@@ -31,6 +31,7 @@ class DFMol(BaseDF):
         self._is_built = False
         self._orthozer = orthozer
         self._ctx = ctx if ctx is not None else get_context()
+        self._k_planes = None       # whitened (ij|P) as int8 operand planes (build_exchange)
 
     def build(self) -> BaseDF:
         self._is_built = True
@@ -86,6 +87,72 @@ class DFMol(BaseDF):
         if nl == 0:
             return torch.zeros(nao, nao, dtype=dmao.dtype, device=dmao.device)
         return _lib.dfj_pass2(self._j3c_packed, nao, nl, coef[self._aux_off:self._aux_off + nl])
+
+    # ---- density-fitted exact exchange (extension: the reference raises, hcgto.py:229-230) ----
+    def build_exchange(self, nslice: Optional[int] = None) -> "DFMol":
+        """One-off set-up of DF-K: B_ij,P = sum_Q (ij|Q) L^-T_QP with (P|Q) = L L^T, kept as the
+        int8 operand planes of stage 1 (batch = AO i, rows = this rank's aux functions P, K = AO j)."""
+        if self._k_planes is not None:
+            return self
+        from dqc_b200.utils.config import config
+        S = int(nslice if nslice is not None else config.DFK_I8_SLICES)
+        nao, naux, nl, p0 = self._nao, self._naux, self._naux_local, self._aux_off
+        dev = self._j2c.device
+        logger.log("Whitening the 2e3c integrals for the exchange build")
+        chol = torch.linalg.cholesky(self._j2c)
+        linv = torch.linalg.solve_triangular(chol, torch.eye(naux, dtype=chol.dtype, device=dev), upper=False)
+        wmat = linv[p0:p0 + nl, :].t().contiguous()                       # (naux, nl): L^-T columns of this rank
+        npair = nao * (nao + 1) // 2
+        b3 = torch.zeros(npair, max(nl, 1), dtype=torch.float64, device=dev)
+        q0 = 0
+        for r in range(self._ctx.world):
+            nq = self._aux_sizes[r]
+            if nq > 0 and nl > 0:
+                if r == self._ctx.rank:
+                    j3c_r = self._j3c_packed
+                else:   # the other ranks' aux slices are recomputed here (one-off), not communicated
+                    j3c_r = intor.coul3c_packed(self._basisw, self._auxbw,
+                                                aux_slice=(self._aux_bounds[r], self._aux_bounds[r + 1]))
+                for r0 in range(0, npair, 32768):
+                    r1 = min(npair, r0 + 32768)
+                    b3[r0:r1] += torch.matmul(j3c_r[r0:r1, :nq], wmat[q0:q0 + nq])
+                del j3c_r
+            q0 += nq
+        self._k_S = S
+        self._k_planes = _lib.I8Operand("A", nao, max(nl, 1), nao, S, device=dev).fill(b3, 0, 0, 0, pair_ld=b3.shape[1])
+        del b3
+        return self
+
+    def exchange_ao_partial(self, cw: torch.Tensor) -> torch.Tensor:
+        """cw (nao, nocc): AO-basis orbitals times sqrt(occupation), D = cw cw^T  ->  this rank's partial
+        K_ij = sum_P sum_o Y_iPo Y_jPo,  Y_iPo = sum_j B_ij,P cw_jo  (two tcgen05 int8 GEMMs, csrc/gemm_i8.cuh)."""
+        self.build_exchange()
+        nao, nl, S = self._nao, self._naux_local, self._k_S
+        dev = cw.device
+        kmat = torch.zeros(nao, nao, dtype=torch.float64, device=dev)
+        nocc = int(cw.shape[1])
+        if nl == 0 or nocc == 0:
+            return kmat
+        cw = cw.contiguous()
+        npad = _lib.round_up(nocc, 64)
+        # stage 1: Y[i][P][o] = sum_j B[i][P][j] cw[j][o]      (batch i; M = P, N = o, K = j)
+        cop = _lib.I8Operand("B", 1, nocc, nao, S, device=dev).fill(cw, 0, 1, nocc)
+        y = torch.empty(nao, nl, npad, dtype=torch.float64, device=dev)
+        _lib.gemm_i8(self._k_planes, cop, y, nl * npad, npad, nl, npad, mode=0, nbatch=nao, b_shared=True)
+        # stage 2: K[i][k] = sum_(P,o) Y[i][(P,o)] Y[k][(P,o)]   (split-K chunks as batches, lower-triangle tiles)
+        ktot = nl * npad
+        mt = (nao + 127) // 128
+        ntl = sum(min((nao + 63) // 64, 2 * t + 2) for t in range(mt))
+        want = max(1, (4 * 148 + ntl - 1) // ntl)                       # >= ~4 waves of tiles over the SMs
+        kc = min(_lib.I8_KCHUNK[S], max(2048, _lib.round_up((ktot + want - 1) // want, 32)))
+        kc = min(kc, _lib.round_up(ktot, 32))
+        nchunk = (ktot + kc - 1) // kc
+        k_last = ktot - (nchunk - 1) * kc
+        ya = _lib.I8Operand("A", nchunk, nao, kc, S, K_last=k_last, device=dev).fill(y, kc, ktot, 1)
+        yb = _lib.I8Operand("B", nchunk, nao, kc, S, K_last=k_last, device=dev).fill(y, kc, ktot, 1)
+        _lib.gemm_i8(ya, yb, kmat, 0, nao, nao, nao, mode=2)
+        low = torch.tril(kmat)
+        return low + torch.tril(kmat, -1).t()
 
     def get_elrep(self, dm: torch.Tensor) -> LinearOperator:
         # dm: (*BD, nao2, nao2) in the orthogonalised basis

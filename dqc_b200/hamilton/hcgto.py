@@ -222,9 +222,48 @@ class HamiltonCGTO(BaseHamilton):
         mat = self._orthozer.convert2(mat).reshape(*bshape, self.nao, self.nao)
         return LinearOperator.m(_symm(mat), is_hermitian=True)
 
+    # ---- density-fitted exact exchange (extension; the reference raises here, hcgto.py:229-230) ----
+    def _dm_factors(self, dm: torch.Tensor, scale: float = 1.0):
+        """Orthogonal-basis density (nao, nao) -> [(sign, cw)] with X (scale dm) X^T = sum sign cw cw^T, cw in the
+        AO basis.  Densities made by ``ao_orb2dm`` carry their orbitals; anything else is eigen-decomposed."""
+        fac = getattr(dm, "_b200_orb", None)
+        if fac is not None and bool((fac[1] >= 0).all()):
+            orb, w = fac
+            cw = self._orthozer.convert_ortho_orb(orb * torch.sqrt(scale * w).unsqueeze(-2))
+            return [(1.0, cw[:, w > 0].contiguous())]
+        dmao = self._orthozer.unconvert_dm(_symm(dm)) * scale
+        lam, vec = torch.linalg.eigh(dmao)
+        tol = 1e-13 * float(lam.abs().max())
+        out = []
+        for sign in (1.0, -1.0):
+            sel = (sign * lam) > tol
+            if bool(sel.any()):
+                out.append((sign, (vec[:, sel] * torch.sqrt(sign * lam[sel])).contiguous()))
+        return out
+
+    def _dfk_ao_partial(self, dm: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """This rank's partial K[scale dm] in the AO basis from the density-fitted integrals."""
+        mat = torch.zeros(self._nao_ao, self._nao_ao, dtype=torch.float64, device=self.device)
+        for sign, cw in self._dm_factors(dm, scale):
+            mat = mat + sign * self._df.exchange_ao_partial(cw)
+        return mat
+
     def get_exchange(self, dm):
         if self._df is not None:
-            raise RuntimeError("Exact exchange cannot be computed with density fitting")
+            if not config.DF_EXCHANGE:
+                raise RuntimeError("Exact exchange cannot be computed with density fitting")
+            def one(dm_, scale):
+                bshape, dm2 = self._flat(dm_)
+                if dm_.ndim == 2:     # keeps the orbital tag of ao_orb2dm
+                    mats = self._dfk_ao_partial(dm_, scale).unsqueeze(0)
+                else:
+                    mats = torch.stack([self._dfk_ao_partial(dm2[b], scale) for b in range(dm2.shape[0])])
+                mats = self._ctx.allreduce_(mats)
+                mat = -0.5 * self._orthozer.convert2(mats).reshape(*bshape, self.nao, self.nao)
+                return LinearOperator.m(_symm(mat), is_hermitian=True)
+            if isinstance(dm, torch.Tensor):
+                return one(dm, 1.0)
+            return SpinParam(u=one(dm.u, 2.0), d=one(dm.d, 2.0))
         if isinstance(dm, torch.Tensor):
             bshape, dm2 = self._flat(dm)
             # symmetrised K[dm] == K[sym(dm)] (hcgto.py:234-236): the kernel needs a symmetric density
@@ -294,9 +333,14 @@ class HamiltonCGTO(BaseHamilton):
         assert dmtot.ndim == 2, "get_fock_2e handles one density at a time"
         parts: List[torch.Tensor] = []
         if self._df is not None:
-            if exx != 0.0:
+            if exx != 0.0 and not config.DF_EXCHANGE:
                 raise RuntimeError("Exact exchange cannot be computed with density fitting")
             parts.append(self._df.elrep_ao_partial(self._orthozer.unconvert_dm(dmtot).contiguous()))
+            if exx != 0.0:
+                if polarized:
+                    parts.extend([self._dfk_ao_partial(dm.u, 2.0), self._dfk_ao_partial(dm.d, 2.0)])
+                else:
+                    parts.append(self._dfk_ao_partial(dmtot))
         else:
             dmao = self._orthozer.unconvert_dm(_symm(dmtot)).unsqueeze(0)
             vj, _ = self._jk_ao_partial(dmao.contiguous(), True, False)
@@ -328,7 +372,10 @@ class HamiltonCGTO(BaseHamilton):
     # ---- density-matrix interface ----
     def ao_orb2dm(self, orb: torch.Tensor, orb_weight: torch.Tensor) -> torch.Tensor:
         orb_w = orb * orb_weight.unsqueeze(-2)
-        return torch.matmul(orb, orb_w.transpose(-2, -1))
+        dm = torch.matmul(orb, orb_w.transpose(-2, -1))
+        if orb.ndim == 2 and orb_weight.ndim == 1:
+            dm._b200_orb = (orb, orb_weight)     # lets the DF-K build skip the eigen-decomposition of dm
+        return dm
 
     def aodm2dens(self, dm: torch.Tensor, xyz: torch.Tensor) -> torch.Tensor:
         # xyz: (*BR, ndim), dm: (*BD, nao, nao) -> (*BRD)

@@ -20,6 +20,10 @@ class _Config:
     # density GEMM (K2) on tcgen05 the same way: 0 = off (fp64 DMMA), 5 or 6 slices
     RHO_I8_SLICES: int = int(os.environ.get("B200QC_RHO_I8", "6"))
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
+    # density-fitted exact exchange (two batched GEMMs on tcgen05): 5 or 6 int8 slices
+    DFK_I8_SLICES: int = int(os.environ.get("B200QC_DFK_I8", "6"))
+    # the reference raises for exact exchange with density fitting (hcgto.py:229-230); set to 0 for that behaviour
+    DF_EXCHANGE: bool = os.environ.get("B200QC_DF_EXCHANGE", "1") != "0"
     # without density fitting, keep both dense layouts of (ij|kl) in HBM when 2 * 8 * nao^4 bytes fit under
     # this (single GPU); beyond it J/K are built directly from Schwarz-screened quartets every iteration
     ERI_STORE_MAX_BYTES: int = int(float(os.environ.get("B200QC_ERI_STORE_MAX_BYTES", str(32 * 1024 ** 3))))

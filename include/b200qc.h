@@ -214,6 +214,34 @@ int b200qc_dfj_pass2(const double *j3c_packed, int64_t nao, int64_t naux, int64_
 /* pack (nao, nao, naux) -> (npair, ld) */
 int b200qc_pack_tril(const double *full, int64_t nao, int64_t naux, int64_t ld, double *packed, void *stream);
 
+/* ---- K10 / K11: fp64-accurate GEMM on tcgen05 (density-fitted exact exchange) -------------------- */
+/* The reference has no DF-K (hcgto.py:229-230 raises); SURVEY 8a defines the extension
+ * K^DF_ij = sum_PQ (ik|P) (P|Q)^-1 (Q|jl) D_kl, built here from two batched GEMMs
+ *     C[b][m][n] (=, +=) alpha * sum_k A[b][m][k] B[b][n][k]
+ * done as error-free sliced int8 products (Ozaki scheme; nslice = 5 or 6 slices of 7 bits,
+ * tcgen05.mma.kind::i8, int32 accumulators in TMEM, exact int64 recombination, power-of-two row scales).
+ *
+ * b200qc_i8_slice: fp64 operand -> int8 planes in the tiled UMMA order (bytes)
+ *   [batch][row tile = r / tile_rows][k tile = k / 32][slice][(k % 32) / 16][(r % tile_rows) / 8][r % 8][k % 16]
+ * tile_rows = 128 for an A operand, 64 for a B operand; planes = nbatch * Rpad * Kpad * nslice bytes,
+ * scales = nbatch * Rpad doubles (one power of two per row and batch).  Element (b, r, k) is read from
+ * src[b * sb + r * sr + k * sk]; rows >= R and columns >= K (K_last in the last batch) are zero.  pair_mode != 0
+ * reads the packed (ij|P) layout instead: b = i, k = j, r = P at src[tri(i, j) * pair_ld + r].
+ *
+ * b200qc_gemm_i8: one persistent CTA per SM walks the (batch, M tile, N tile) list.  a_bstride / b_bstride are
+ * the BYTES between the planes of consecutive batches (0 = operand shared by every batch), as_bstride /
+ * bs_bstride the scale entries between batches; nk = K steps of 32 per batch (nk_last in the last batch; the
+ * planes of every batch still span nk steps).  mode 0 stores C[b * c_bstride + m * ldc + n]; mode 1 adds
+ * atomically (split-K: batches = K chunks, c_bstride = 0); mode 2 = mode 1 restricted to the tiles that touch
+ * the lower triangle (symmetric results: the caller mirrors). */
+int b200qc_i8_slice(const double *src, int nbatch, int64_t sb, int64_t sr, int64_t sk, int pair_mode,
+                    int64_t pair_ld, int R, int K, int K_last, int Rpad, int Kpad, int tile_rows, int nslice,
+                    signed char *planes, double *scales, void *stream);
+int b200qc_gemm_i8(const signed char *aplanes, const double *ascale, int64_t a_bstride, int64_t as_bstride,
+                   const signed char *bplanes, const double *bscale, int64_t b_bstride, int64_t bs_bstride,
+                   int nbatch, int mtiles, int ntiles, int nk, int nk_last, int nslice, int M, int N, double alpha,
+                   double *C, int64_t c_bstride, int64_t ldc, int mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,8 +106,22 @@ class RefHamilton:
         return self.conv2(mat)
 
     def get_exchange(self, dm):
+        if self.j3c is not None and self.el_mat is None:
+            return self.get_exchange_df(dm)
         mat = -0.5 * torch.einsum("...il,ijkl->...ijk", dm, self.el_mat).sum(dim=-3)
         return (mat + mat.transpose(-2, -1)) * 0.5
+
+    def get_exchange_df(self, dm):
+        """Density-fitted exact exchange -- NOT in the reference (it raises, hcgto.py:229-230).  The extension is
+        the one SURVEY 8a defines, with the reference's own conventions for the factor and the symmetrisation
+        (hcgto.py:234-241): K'_ij = -1/2 sum_PQ sum_kl (ik|P) (P|Q)^-1 (Q|jl) D_kl, written with the plain
+        inverse the reference uses for J (dfmol.py:48)."""
+        dmao = self.unconv_dm((dm + dm.transpose(-2, -1)) * 0.5)
+        half = torch.einsum("ikp,kl->ilp", self.j3c, dmao)                 # (i, l, P)
+        half = torch.einsum("ilp,pq->ilq", half, self.inv_j2c)
+        mat = -0.5 * torch.einsum("ilq,jlq->ij", half, self.j3c)
+        mat = (mat + mat.transpose(-2, -1)) * 0.5
+        return self.conv2(mat)
 
     def dm2densinfo(self, dm):
         dmdmt = self.unconv_dm((dm + dm.transpose(-2, -1)) * 0.5)

@@ -122,8 +122,18 @@ def test_dfj_operator_matches_oracle(cuda):
     assert float((back(got, Xg) - back(want, Xr)).abs().max()) < 1e-8
     assert float((h.df.j2c.cpu() - ref.j2c).abs().max()) < 1e-10
     assert float((h.df.j3c.cpu() - ref.j3c).abs().max()) < 1e-10
-    with pytest.raises(RuntimeError):
-        h.get_exchange(dm_g.to(cuda))          # hcgto.py:229-230
+    # the reference raises for exact exchange with density fitting (hcgto.py:229-230); here that is the
+    # behaviour with the DF-K extension switched off
+    from dqc_b200 import config
+    old = config.DF_EXCHANGE
+    try:
+        config.DF_EXCHANGE = False
+        with pytest.raises(RuntimeError):
+            h.get_exchange(dm_g.to(cuda))
+        with pytest.raises(RuntimeError):
+            h.get_fock_2e(dm_g.to(cuda), exx=0.25, with_xc=False)
+    finally:
+        config.DF_EXCHANGE = old
 
 
 # ---------------------------------------------------------------------------------------------
