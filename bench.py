@@ -38,6 +38,10 @@ WORKLOADS = {
     "h2o-hf": ("h2o", "sto-3g", None, None, 1.0, "sg3"),
     "taxol-like-pbe0-4c": ("taxol_like", "def2-svp", "0.75*gga_x_pbe + gga_c_pbe", None, 0.25, "sg3"),
     "taxol-like-pbe-df": ("taxol_like", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
+    # hybrids with density-fitted J AND K (the DF-K extension: two batched tcgen05 int8 GEMMs per build)
+    "c60-pbe0-df": ("c60", "def2-svp", "0.75*gga_x_pbe + gga_c_pbe", "etb-jfit", 0.25, "sg3"),
+    "benzene-pbe0-df": ("benzene", "cc-pvdz", "0.75*gga_x_pbe + gga_c_pbe", "etb-jfit", 0.25, "sg3"),
+    "taxol-like-pbe0-df": ("taxol_like", "def2-svp", "0.75*gga_x_pbe + gga_c_pbe", "etb-jfit", 0.25, "sg3"),
 }
 METRIC = "fock_build_wall_ms_per_scf_iter"
 
@@ -47,11 +51,16 @@ def geometry(name):
     return getattr(systems, name)()
 
 
-def seeded_dm(nao, nocc, device):
-    """D = 2 C C^T, C = first nocc columns of qr(randn(nao, nao)) under manual_seed(0)."""
+def seeded_orb(nao, nocc):
+    """C = first nocc columns of qr(randn(nao, nao)) under manual_seed(0), on the host."""
     g = torch.Generator().manual_seed(0)
     q, _ = torch.linalg.qr(torch.randn(nao, nao, dtype=torch.float64, generator=g))
-    c = q[:, :nocc]
+    return q[:, :nocc].contiguous()
+
+
+def seeded_dm(nao, nocc, device):
+    """D = 2 C C^T of the seeded orbitals."""
+    c = seeded_orb(nao, nocc)
     return (2 * c @ c.T).to(device)
 
 
@@ -161,6 +170,8 @@ def cpu_reference_step_factory(workload, grid_sample=65536, aux_sample=96):
         j2c = torch.as_tensor(cint.int2c2e(atm, bas, env, (a0, a_hi, a0, a_hi)))
         h.j3c, h.j2c, h.inv_j2c = j3c, j2c, torch.inverse(j2c)
         info.update(naux_full=naux_full, naux_sample=int(j3c.shape[-1]))
+        if exx != 0.0:
+            info["note"] = "the reference has no density-fitted exchange (hcgto.py:229-230 raises): K is not in the CPU sample"
     elif exx != 0.0 or xc is None or aux is None:
         info["note"] = "dense-ERI J/K of this workload is not part of the CPU sample (nao^4 tensor)"
     nocc = max(1, int(sum(zs)) // 2)
@@ -258,7 +269,10 @@ def main():
     t_setup = time.perf_counter() - t_setup
     nao = h.nao
     nocc = max(1, int(sum(zs)) // 2)
-    dm = seeded_dm(nao, min(nocc, nao), dev)
+    # the density the SCF engine would hand over: D = C w C^T through ao_orb2dm (hcgto.py:272-281), w = 2
+    orb_host = seeded_orb(nao, min(nocc, nao)).pin_memory()
+    occ = torch.full((orb_host.shape[1],), 2.0, dtype=torch.float64, device=dev)
+    dm = h.ao_orb2dm(orb_host.to(dev), occ)
     ngrid = int(mol.get_grid().get_rgrid().shape[0]) if xc is not None else 0
     if aux is None:
         config["jk_engine"] = type(h._jkplan).__name__ + (
@@ -302,14 +316,15 @@ def main():
     ms_per_step = total_ms / args.steps
 
     # ---- e2e: host buffers in and out, copies inside the timed region ----
-    dm_host = dm.cpu().pin_memory()
-    fock_host = torch.empty_like(dm_host).pin_memory()
-    dm_dev = torch.empty_like(dm)
+    # host side of an SCF iteration: occupied orbitals in (pinned), Fock matrix out (pinned); D = C w C^T is
+    # formed on the device by ao_orb2dm like the engine does (scp2dm), then the same get_fock_2e call
+    fock_host = torch.empty(nao, nao, dtype=torch.float64).pin_memory()
+    orb_dev = torch.empty_like(orb_host, device=dev)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        dm_dev.copy_(dm_host, non_blocking=True)
-        f = h.get_fock_2e(dm_dev, exx=exx, with_xc=xc is not None).fullmatrix()
+        orb_dev.copy_(orb_host, non_blocking=True)
+        f = h.get_fock_2e(h.ao_orb2dm(orb_dev, occ), exx=exx, with_xc=xc is not None).fullmatrix()
         fock_host.copy_(f, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
@@ -374,6 +389,22 @@ def main():
                 "peak_source": "fp64 DMMA (mma.sync m8n8k4) issue-rate microbenchmark run in this process "
                                "(b200qc_peak_fp64_dmma); MEASURED_PEAKS.json has no fp64 entry",
                 "algorithmic_flops_per_launch": xc_flops}
+    def dfk_roofline():
+        """DF-K: both tcgen05 GEMM launches of a build together.  Algorithmic fp64 flops: stage 1
+        2 nao^2 naux nocc, stage 2 (symmetric) nao^2 naux nocc; each is S (S + 1) / 2 int8 products."""
+        nsl = h.df._k_S
+        nprod = nsl * (nsl + 1) // 2
+        c, ms = prof["gemm_i8_kernel"]
+        nocc_ = orb_host.shape[1]
+        fl = 3.0 * h._nao_ao ** 2 * h.df._naux_local * nocc_ * (c / (2.0 * args.steps))   # per build
+        t = ms / args.steps * 1e-3
+        peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+        return {"kernel": "gemm_i8_kernel", "bound": "tensor", "achieved": fl * nprod / t / 1e12, "peak": peak,
+                "unit": "TOP/s (int8)", "frac": fl * nprod / t / 1e12 / peak, "traffic": traffic.get("gemm_i8_kernel"),
+                "peak_source": "tcgen05.mma.kind::i8: 2 x bf16_tflops of MEASURED_PEAKS.json (no int8 entry in the file)",
+                "algorithmic_ops_per_launch": fl * nprod / 2.0, "launches_per_build": c / args.steps,
+                "int8_slice_products": nprod, "fp64_equivalent_tflops": fl / t / 1e12,
+                "fp64_equivalent_vs_dmma_peak": fl / t / 1e12 / dmma_peak}
     traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as ft:
@@ -394,6 +425,8 @@ def main():
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
                     "algorithmic_bytes_per_launch": nb}
+    elif dominant == "gemm_i8_kernel":
+        roofline = dfk_roofline()
     elif dominant == "jk_kernel":
         roofline = {"kernel": dominant, "bound": "fp64-alu", "achieved": h._jkplan.nquartets / (
             sum(ms for k, (c, ms) in prof.items() if k == "jk_kernel") / args.steps * 1e-3), "peak": None,
@@ -409,6 +442,9 @@ def main():
         nb = (ncomp + 1) * gb.ao_bytes / ncomp
         extra["vxc_vb_kernel"] = {"GB/s": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9,
                                   "frac_of_hbm": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
+    if "gemm_i8_kernel" in kern and h.df is not None and getattr(h.df, "_k_planes", None) is not None:
+        r = dfk_roofline()
+        extra["gemm_i8_kernel"] = {kk: r[kk] for kk in ("achieved", "peak", "unit", "frac", "fp64_equivalent_tflops")}
     for k in ("rho_kernel", "vxc_gemm_kernel"):
         if k in kern and gb is not None:
             r = gemm_roofline(k)
@@ -428,7 +464,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(dm_host.numel() * 8),
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(orb_host.numel() * 8),
                     "d2h_bytes_per_step": int(fock_host.numel() * 8)},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -118,7 +118,12 @@ _SIGS = {
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
-                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
+                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_int, ctypes.c_void_p]),
+    "b200qc_i8_slice_dual": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 
@@ -566,8 +571,20 @@ class I8Operand(object):
         return self
 
 
+def i8_slice_dual(src: torch.Tensor, nbatch: int, sb: int, sr: int, rowmax: torch.Tensor, rm_ld: int, R: int, K: int,
+                  K_last: int, nslice: int = 6):
+    """One pass over a K-contiguous fp64 operand with known row maxima -> (A-form, B-form) I8Operands."""
+    a = I8Operand("A", nbatch, R, K, nslice, K_last=K_last, device=src.device)
+    b = I8Operand("B", nbatch, R, K, nslice, K_last=K_last, device=src.device)
+    _check(load().b200qc_i8_slice_dual(_ptr(src), int(nbatch), int(sb), int(sr), _ptr(rowmax), int(rm_ld), int(R),
+                                       int(K), int(K_last), a.Kpad, int(nslice), _ptr(a.planes), _ptr(a.scales),
+                                       _ptr(b.planes), _ptr(b.scales), _stream()), "i8_slice_dual")
+    return a, b
+
+
 def gemm_i8(a: I8Operand, b: I8Operand, out: torch.Tensor, c_bstride: int, ldc: int, M: int, N: int, mode: int = 0,
-            alpha: float = 1.0, nbatch: Optional[int] = None, a_shared: bool = False, b_shared: bool = False):
+            alpha: float = 1.0, nbatch: Optional[int] = None, a_shared: bool = False, b_shared: bool = False,
+            rowmax: Optional[torch.Tensor] = None, rm_bstride: int = 0, rm_div: int = 1):
     """out[b][m][n] (=, +=) alpha * sum_k A[b][m][k] B[b][n][k] on the tcgen05 int8 engine (b200qc_gemm_i8)."""
     assert a.role == "A" and b.role == "B" and a.S == b.S and a.nk == b.nk and a.nk_last == b.nk_last
     nb = int(nbatch if nbatch is not None else max(a.nbatch, b.nbatch))
@@ -575,7 +592,8 @@ def gemm_i8(a: I8Operand, b: I8Operand, out: torch.Tensor, c_bstride: int, ldc: 
     _check(load().b200qc_gemm_i8(_ptr(a.planes), _ptr(a.scales), 0 if a_shared else a.bstride, 0 if a_shared else a.Rpad,
                                  _ptr(b.planes), _ptr(b.scales), 0 if b_shared else b.bstride, 0 if b_shared else b.Rpad,
                                  nb, a.rtiles, b.rtiles, a.nk, a.nk_last, a.S, int(M), int(N), float(alpha),
-                                 _ptr(out), int(c_bstride), int(ldc), int(mode), _stream()), "gemm_i8")
+                                 _ptr(out), int(c_bstride), int(ldc), int(mode), _ptr(rowmax), int(rm_bstride),
+                                 int(rm_div), _stream()), "gemm_i8")
     return out
 
 

@@ -131,6 +131,79 @@ i8_slice_kc_kernel(I8SliceArgs a) {
     }
 }
 
+// K-contiguous source with KNOWN row maxima (from the producing GEMM's epilogue): one pass, both operand forms.
+// Source element (batch b, row r, k) at src[b * sb + r * sr + k]; rowmax[b_row * ... ] is indexed [r][b] with
+// stride rm_ld (the producing GEMM had the roles of batch and row swapped).  A CTA = 8 consecutive rows x one
+// 512-column segment per iteration: coalesced fp64 loads (lane = column), bytes staged in shared memory by
+// column, then 16-byte chunks written so that 8 rows x 16 bytes form one contiguous 128-byte line of a plane.
+struct I8Slice2Args {
+    const double *src;
+    int64_t sb, sr;
+    const double *rowmax;      // non-negative doubles, [r * rm_ld + b]
+    int64_t rm_ld;
+    int nbatch, R, K, K_last, Kpad;
+    int RpadA, RpadB;          // multiples of 128 / 64
+    signed char *planesA, *planesB;
+    double *scalesA, *scalesB; // [batch][RpadA], [batch][RpadB]
+};
+
+template <int S>
+__global__ void __launch_bounds__(256)
+i8_slice_dual_kernel(I8Slice2Args a) {
+    __shared__ __align__(16) signed char sm[8][S][512];
+    __shared__ double sinv[8];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * 8;
+    const int r = r0 + warp;
+    const int Kb = (b == a.nbatch - 1) ? a.K_last : a.K;
+    const bool rv = r < a.R;
+    if (lane == 0) {
+        const double m = rv ? a.rowmax[(int64_t)r * a.rm_ld + b] : 0.0;
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);
+        sinv[warp] = ldexp(64.0, -e);
+        const double sc = ldexp(1.0, e);
+        if (r < a.RpadA) a.scalesA[(int64_t)b * a.RpadA + r] = sc;
+        if (r < a.RpadB) a.scalesB[(int64_t)b * a.RpadB + r] = sc;
+    }
+    __syncwarp();
+    const double inv = sinv[warp];
+    const double *X = a.src + (int64_t)b * a.sb + (int64_t)r * a.sr;
+    const int nk = a.Kpad / 32;
+    const bool wa = r0 < a.RpadA, wb = r0 < a.RpadB;     // 8-row groups never straddle a padded size
+    // writer mapping: 8 consecutive lanes = the 8 rows of one 16-column group
+    const int wrow = threadIdx.x & 7, wgrp = threadIdx.x >> 3;          // 32 groups per 512-column segment
+    const int rr = r0 + wrow;
+    signed char *PA = a.planesA + ((int64_t)b * (a.RpadA / 128) + rr / 128) * nk * S * 4096 + ((rr % 128) >> 3) * 128 + (rr & 7) * 16;
+    signed char *PB = a.planesB + ((int64_t)b * (a.RpadB / 64) + rr / 64) * nk * S * 2048 + ((rr % 64) >> 3) * 128 + (rr & 7) * 16;
+    for (int seg = 0; seg * 512 < a.Kpad; seg++) {
+        const int k0 = seg * 512;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            const int k = k0 + t * 32 + lane;
+            double y = (rv && k < Kb) ? __ldcs(X + k) * inv : 0.0;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const double q = rint(y);
+                sm[warp][s][t * 32 + lane] = (signed char)(int)q;
+                y = (y - q) * 128.0;
+            }
+        }
+        __syncthreads();
+        const int kg = (k0 >> 4) + wgrp;                 // 16-column group of this writer
+        if (kg * 16 < a.Kpad) {
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(&sm[wrow][s][wgrp * 16]);
+                if (wa) *reinterpret_cast<uint4 *>(PA + (int64_t)(kg >> 1) * S * 4096 + s * 4096 + (kg & 1) * 2048) = v;
+                if (wb) *reinterpret_cast<uint4 *>(PB + (int64_t)(kg >> 1) * S * 2048 + s * 2048 + (kg & 1) * 1024) = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- the GEMM ------------------------------------------------------------------------------------------
 struct I8GemmArgs {
     const signed char *A, *B;
@@ -144,6 +217,11 @@ struct I8GemmArgs {
     int mode;                          // 0 store, 1 atomic add, 2 atomic add of the lower-triangle tiles only
     double alpha;
     int units_per_batch;
+    // optional (mode 0): running maxima of |C| per (batch, row / rm_div), as the bit patterns of non-negative
+    // doubles (atomicMax on them is monotone) -- the row scales of a following slicing pass, for free
+    unsigned long long *rowmax;
+    int64_t rm_bstride;
+    int rm_div;
 };
 
 // unit -> (batch, M tile, N tile); mode 2 enumerates only tiles with tn * 64 < (tm + 1) * 128
@@ -270,17 +348,25 @@ gemm_i8_kernel(I8GemmArgs g) {
             double *crow = g.C + b * g.c_bstride + (int64_t)m * g.ldc + n0;
             if (g.mode == 0) {
                 const bool vec = ((g.ldc | g.c_bstride) & 1) == 0 && n0 + 64 <= g.N;
+                double vmax = 0.0;
                 if (vec) {
 #pragma unroll
                     for (int j = 0; j < 64; j += 2) {
                         const double2 s2 = *reinterpret_cast<const double2 *>(cs + j);
-                        __stcs(reinterpret_cast<double2 *>(crow + j), make_double2(x[j] * sa_ * s2.x, x[j + 1] * sa_ * s2.y));
+                        const double v0 = x[j] * sa_ * s2.x, v1 = x[j + 1] * sa_ * s2.y;
+                        vmax = fmax(vmax, fmax(fabs(v0), fabs(v1)));
+                        *reinterpret_cast<double2 *>(crow + j) = make_double2(v0, v1);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 64; j++)
-                        if (n0 + j < g.N) crow[j] = x[j] * sa_ * cs[j];
+                        if (n0 + j < g.N) {
+                            const double v0 = x[j] * sa_ * cs[j];
+                            vmax = fmax(vmax, fabs(v0));
+                            crow[j] = v0;
+                        }
                 }
+                if (g.rowmax) atomicMax(g.rowmax + b * g.rm_bstride + m / g.rm_div, (unsigned long long)__double_as_longlong(vmax));
             } else {
 #pragma unroll
                 for (int j = 0; j < 64; j++)
@@ -331,11 +417,35 @@ extern "C" int b200qc_i8_slice(const double *src, int nbatch, int64_t sb, int64_
     return 0;
 }
 
+extern "C" int b200qc_i8_slice_dual(const double *src, int nbatch, int64_t sb, int64_t sr, const double *rowmax,
+                                    int64_t rm_ld, int R, int K, int K_last, int Kpad, int nslice,
+                                    signed char *planesA, double *scalesA, signed char *planesB, double *scalesB,
+                                    void *stream) {
+    QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE(Kpad % 32 == 0 && K <= Kpad && K_last <= K && K_last >= 0, "Kpad must be a multiple of 32");
+    QC_REQUIRE(nbatch >= 1 && nbatch <= 65535, "1..65535 batches");
+    I8Slice2Args a;
+    a.src = src; a.sb = sb; a.sr = sr; a.rowmax = rowmax; a.rm_ld = rm_ld;
+    a.nbatch = nbatch; a.R = R; a.K = K; a.K_last = K_last; a.Kpad = Kpad;
+    a.RpadA = (R + 127) / 128 * 128; a.RpadB = (R + 63) / 64 * 64;
+    a.planesA = planesA; a.planesB = planesB; a.scalesA = scalesA; a.scalesB = scalesB;
+    cudaStream_t st = as_stream(stream);
+    dim3 grid((unsigned)(a.RpadA / 8), (unsigned)nbatch);
+    prof_begin(PROF_I8_SLICE, st);
+    if (nslice == 5) i8_slice_dual_kernel<5><<<grid, 256, 0, st>>>(a);
+    else i8_slice_dual_kernel<6><<<grid, 256, 0, st>>>(a);
+    prof_end(st);
+    QC_LAUNCHED(1);
+    return 0;
+}
+
 extern "C" int b200qc_gemm_i8(const signed char *aplanes, const double *ascale, int64_t a_bstride, int64_t as_bstride,
                               const signed char *bplanes, const double *bscale, int64_t b_bstride, int64_t bs_bstride,
                               int nbatch, int mtiles, int ntiles, int nk, int nk_last, int nslice, int M, int N,
-                              double alpha, double *C, int64_t c_bstride, int64_t ldc, int mode, void *stream) {
+                              double alpha, double *C, int64_t c_bstride, int64_t ldc, int mode, double *rowmax,
+                              int64_t rm_bstride, int rm_div, void *stream) {
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE(rowmax == nullptr || (mode == 0 && rm_div >= 1), "rowmax needs mode 0 and rm_div >= 1");
     QC_REQUIRE(mode >= 0 && mode <= 2, "mode: 0 store, 1 atomic add, 2 atomic add of lower-triangle tiles");
     QC_REQUIRE(nk >= 1 && nk_last >= 1 && nk_last <= nk, "every batch needs at least one K step");
     // exactness: |anti-diagonal sum| <= S * 64 * 64 * K < 2^31 and the int64 merge needs K * 2^(12 + 7 (S - 1)) < 2^63
@@ -346,6 +456,7 @@ extern "C" int b200qc_gemm_i8(const signed char *aplanes, const double *ascale, 
     g.a_bstride = a_bstride; g.b_bstride = b_bstride; g.as_bstride = as_bstride; g.bs_bstride = bs_bstride;
     g.nbatch = nbatch; g.mtiles = mtiles; g.ntiles = ntiles; g.nk = nk; g.nk_last = nk_last;
     g.M = M; g.N = N; g.C = C; g.c_bstride = c_bstride; g.ldc = ldc; g.mode = mode; g.alpha = alpha;
+    g.rowmax = reinterpret_cast<unsigned long long *>(rowmax); g.rm_bstride = rm_bstride; g.rm_div = rm_div > 0 ? rm_div : 1;
     if (mode == 2) {
         int c = 0;
         for (int tm = 0; tm < mtiles; tm++) c += std::min(ntiles, 2 * tm + 2);

@@ -135,21 +135,23 @@ class DFMol(BaseDF):
             return kmat
         cw = cw.contiguous()
         npad = _lib.round_up(nocc, 64)
-        # stage 1: Y[i][P][o] = sum_j B[i][P][j] cw[j][o]      (batch i; M = P, N = o, K = j)
-        cop = _lib.I8Operand("B", 1, nocc, nao, S, device=dev).fill(cw, 0, 1, nocc)
-        y = torch.empty(nao, nl, npad, dtype=torch.float64, device=dev)
-        _lib.gemm_i8(self._k_planes, cop, y, nl * npad, npad, nl, npad, mode=0, nbatch=nao, b_shared=True)
-        # stage 2: K[i][k] = sum_(P,o) Y[i][(P,o)] Y[k][(P,o)]   (split-K chunks as batches, lower-triangle tiles)
-        ktot = nl * npad
+        # K chunks of stage 2 = whole aux functions: pc of them (pc * npad columns) per chunk, >= ~4 waves of tiles
         mt = (nao + 127) // 128
         ntl = sum(min((nao + 63) // 64, 2 * t + 2) for t in range(mt))
-        want = max(1, (4 * 148 + ntl - 1) // ntl)                       # >= ~4 waves of tiles over the SMs
-        kc = min(_lib.I8_KCHUNK[S], max(2048, _lib.round_up((ktot + want - 1) // want, 32)))
-        kc = min(kc, _lib.round_up(ktot, 32))
-        nchunk = (ktot + kc - 1) // kc
+        want = max(1, (4 * 148 + ntl - 1) // ntl)
+        pc = max(1, min(_lib.I8_KCHUNK[S] // npad, (nl + want - 1) // want))
+        nchunk = (nl + pc - 1) // pc
+        kc, ktot = pc * npad, nl * npad
         k_last = ktot - (nchunk - 1) * kc
-        ya = _lib.I8Operand("A", nchunk, nao, kc, S, K_last=k_last, device=dev).fill(y, kc, ktot, 1)
-        yb = _lib.I8Operand("B", nchunk, nao, kc, S, K_last=k_last, device=dev).fill(y, kc, ktot, 1)
+        # stage 1: Y[i][P][o] = sum_j B[i][P][j] cw[j][o]      (batch i; M = P, N = o, K = j); the epilogue also
+        # leaves max |Y| per (i, chunk of P) -- the row scales of the stage-2 operands
+        cop = _lib.I8Operand("B", 1, nocc, nao, S, device=dev).fill(cw, 0, 1, nocc)
+        y = torch.empty(nao, nl, npad, dtype=torch.float64, device=dev)
+        ymax = torch.zeros(nao, nchunk, dtype=torch.float64, device=dev)
+        _lib.gemm_i8(self._k_planes, cop, y, nl * npad, npad, nl, npad, mode=0, nbatch=nao, b_shared=True,
+                     rowmax=ymax, rm_bstride=nchunk, rm_div=pc)
+        # stage 2: K[i][k] = sum_(P,o) Y[i][(P,o)] Y[k][(P,o)]   (split-K chunks as batches, lower-triangle tiles)
+        ya, yb = _lib.i8_slice_dual(y, nchunk, kc, ktot, ymax, nchunk, nao, kc, k_last, S)
         _lib.gemm_i8(ya, yb, kmat, 0, nao, nao, nao, mode=2)
         low = torch.tril(kmat)
         return low + torch.tril(kmat, -1).t()

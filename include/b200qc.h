@@ -233,14 +233,23 @@ int b200qc_pack_tril(const double *full, int64_t nao, int64_t naux, int64_t ld, 
  * bs_bstride the scale entries between batches; nk = K steps of 32 per batch (nk_last in the last batch; the
  * planes of every batch still span nk steps).  mode 0 stores C[b * c_bstride + m * ldc + n]; mode 1 adds
  * atomically (split-K: batches = K chunks, c_bstride = 0); mode 2 = mode 1 restricted to the tiles that touch
- * the lower triangle (symmetric results: the caller mirrors). */
+ * the lower triangle (symmetric results: the caller mirrors).  rowmax (optional, mode 0): see below. */
 int b200qc_i8_slice(const double *src, int nbatch, int64_t sb, int64_t sr, int64_t sk, int pair_mode,
                     int64_t pair_ld, int R, int K, int K_last, int Rpad, int Kpad, int tile_rows, int nslice,
                     signed char *planes, double *scales, void *stream);
 int b200qc_gemm_i8(const signed char *aplanes, const double *ascale, int64_t a_bstride, int64_t as_bstride,
                    const signed char *bplanes, const double *bscale, int64_t b_bstride, int64_t bs_bstride,
                    int nbatch, int mtiles, int ntiles, int nk, int nk_last, int nslice, int M, int N, double alpha,
-                   double *C, int64_t c_bstride, int64_t ldc, int mode, void *stream);
+                   double *C, int64_t c_bstride, int64_t ldc, int mode, double *rowmax, int64_t rm_bstride, int rm_div,
+                   void *stream);
+/* One-pass slicing of a K-contiguous operand into BOTH forms (128- and 64-row tiles) when the row maxima are
+ * already known: element (b, r, k) at src[b * sb + r * sr + k], max_k |.| of (b, r) at rowmax[r * rm_ld + b]
+ * (what b200qc_gemm_i8 leaves in its optional `rowmax` output: the bit patterns of non-negative doubles,
+ * [batch * rm_bstride + row / rm_div], zero-initialised by the caller).  Padded sizes: rows to 128 (A form) and 64
+ * (B form), K to Kpad. */
+int b200qc_i8_slice_dual(const double *src, int nbatch, int64_t sb, int64_t sr, const double *rowmax, int64_t rm_ld,
+                         int R, int K, int K_last, int Kpad, int nslice, signed char *planesA, double *scalesA,
+                         signed char *planesB, double *scalesB, void *stream);
 
 #ifdef __cplusplus
 }

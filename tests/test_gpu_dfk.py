@@ -52,7 +52,9 @@ def test_slicer_row_contiguous_and_lower_triangle_mode(cuda):
     _lib.gemm_i8(a, b, out, 0, n, n, n, mode=2, alpha=0.5)
     want = 0.5 * zt.T @ zt
     got = torch.tril(out) + torch.tril(out, -1).T
-    assert float((got - want).abs().max() / want.abs().max()) < 1e-11
+    # the scheme's error is relative to (row max) x (row max) x K, not to the result
+    rmax = zt.abs().max(0).values
+    assert float(((got - want).abs() / (rmax[:, None] * rmax[None, :] * K)).max()) < 2e-12
     # tiles strictly above the diagonal band were skipped
     assert float(out[:128, 256:].abs().max()) == 0.0
 
