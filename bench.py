@@ -30,6 +30,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+B3LYP_SL = "0.08*lda_x + 0.72*gga_x_b88 + 0.19*lda_c_vwn_rpa + 0.81*gga_c_lyp"
 WORKLOADS = {
     # name: (system, basis, xc, df aux basis or None, exx fraction, grid)
     "c60-pbe-df": ("c60", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
@@ -42,6 +43,10 @@ WORKLOADS = {
     "c60-pbe0-df": ("c60", "def2-svp", "0.75*gga_x_pbe + gga_c_pbe", "etb-jfit", 0.25, "sg3"),
     "benzene-pbe0-df": ("benzene", "cc-pvdz", "0.75*gga_x_pbe + gga_c_pbe", "etb-jfit", 0.25, "sg3"),
     "taxol-like-pbe0-df": ("taxol_like", "def2-svp", "0.75*gga_x_pbe + gga_c_pbe", "etb-jfit", 0.25, "sg3"),
+    # B3LYP as libxc composes it (0.08 Slater + 0.72 B88 + 0.19 VWN-RPA + 0.81 LYP + 0.20 exact exchange)
+    "c60-b3lyp-df": ("c60", "def2-svp", B3LYP_SL, "etb-jfit", 0.20, "sg3"),
+    "taxol-like-b3lyp-df": ("taxol_like", "def2-svp", B3LYP_SL, "etb-jfit", 0.20, "sg3"),
+    "taxol-like-b3lyp-4c": ("taxol_like", "def2-svp", B3LYP_SL, None, 0.20, "sg3"),
 }
 METRIC = "fock_build_wall_ms_per_scf_iter"
 

@@ -19,8 +19,9 @@ _rys_loaded = False
 GRID_ALIGN = 128  # leading dimension of the grid axis (K2/K4 CTA tile)
 AO_ALIGN = 64     # leading dimension of the AO axis
 
-FUNC_IDS = {"lda_x": 1, "lda_c_pw": 2, "lda_c_pw_mod": 3, "gga_x_pbe": 101, "gga_c_pbe": 102}
-FUNC_FAMILY = {"lda_x": 1, "lda_c_pw": 1, "lda_c_pw_mod": 1, "gga_x_pbe": 2, "gga_c_pbe": 2}
+FUNC_IDS = {"lda_x": 1, "lda_c_pw": 2, "lda_c_pw_mod": 3, "lda_c_vwn": 4, "lda_c_vwn_rpa": 5,
+            "gga_x_pbe": 101, "gga_c_pbe": 102, "gga_x_b88": 103, "gga_c_lyp": 104}
+FUNC_FAMILY = {name: (2 if fid >= 100 else 1) for name, fid in FUNC_IDS.items()}
 
 _SIGS = {
     # name: (restype, argtypes)

@@ -13,6 +13,10 @@
 #define XC_LDA_C_PW_MOD 3
 #define XC_GGA_X_PBE 101
 #define XC_GGA_C_PBE 102
+#define XC_LDA_C_VWN 4       // VWN5 (libxc lda_c_vwn)
+#define XC_LDA_C_VWN_RPA 5   // VWN-RPA (libxc lda_c_vwn_rpa, the LDA part of libxc's B3LYP)
+#define XC_GGA_X_B88 103
+#define XC_GGA_C_LYP 104
 #define XC_MAX_TERMS 8
 #define XC_RHO_CUT 1e-15   // densities at or below this contribute exactly zero (libxc-style threshold)
 
@@ -84,6 +88,133 @@ __device__ __forceinline__ void pw_eps(bool mod, double rs, double zeta, double 
     eps = g0 + z4 * f * w - f * g2 / p.fz20;
     deps_drs = d0 + z4 * f * (d1 - d0 + d2 / p.fz20) - f * d2 / p.fz20;
     deps_dz = (4 * z3 * f + z4 * df) * w - df * g2 / p.fz20;
+}
+
+// ---- forward-mode duals: functionals written once as an energy expression, derivatives by the chain rule ----
+// (B88, LYP, VWN: the libxc forms are restated from the original papers; the kernel's derivatives are checked
+// against torch autograd of the oracle's expressions, the reference's own default route, base_xc.py:39-125.)
+template <int N>
+struct Dual {
+    double v, d[N];
+};
+#define DUAL_OP __device__ __forceinline__
+template <int N> DUAL_OP Dual<N> dconst(double c) { Dual<N> r; r.v = c;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = 0.0; return r; }
+template <int N> DUAL_OP Dual<N> dvar(double c, int k, double seed = 1.0) { Dual<N> r = dconst<N>(c); r.d[k] = seed; return r; }
+template <int N> DUAL_OP Dual<N> operator+(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v + b.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int N> DUAL_OP Dual<N> operator-(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v - b.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int N> DUAL_OP Dual<N> operator*(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v * b.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+template <int N> DUAL_OP Dual<N> operator/(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; const double ib = 1.0 / b.v; r.v = a.v * ib;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r; }
+template <int N> DUAL_OP Dual<N> operator+(const Dual<N> &a, double c) { Dual<N> r = a; r.v += c; return r; }
+template <int N> DUAL_OP Dual<N> operator+(double c, const Dual<N> &a) { return a + c; }
+template <int N> DUAL_OP Dual<N> operator-(const Dual<N> &a, double c) { Dual<N> r = a; r.v -= c; return r; }
+template <int N> DUAL_OP Dual<N> operator-(double c, const Dual<N> &a) { Dual<N> r; r.v = c - a.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = -a.d[i]; return r; }
+template <int N> DUAL_OP Dual<N> operator-(const Dual<N> &a) { return 0.0 - a; }
+template <int N> DUAL_OP Dual<N> operator*(const Dual<N> &a, double c) { Dual<N> r; r.v = a.v * c;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = a.d[i] * c; return r; }
+template <int N> DUAL_OP Dual<N> operator*(double c, const Dual<N> &a) { return a * c; }
+template <int N> DUAL_OP Dual<N> operator/(const Dual<N> &a, double c) { return a * (1.0 / c); }
+template <int N> DUAL_OP Dual<N> operator/(double c, const Dual<N> &a) { return dconst<N>(c) / a; }
+// f(a) with derivative df
+template <int N> DUAL_OP Dual<N> dchain(const Dual<N> &a, double f, double df) { Dual<N> r; r.v = f;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = df * a.d[i]; return r; }
+template <int N> DUAL_OP Dual<N> dsqrt(const Dual<N> &a) { const double f = sqrt(a.v); return dchain(a, f, a.v > 0.0 ? 0.5 / f : 0.0); }
+template <int N> DUAL_OP Dual<N> dcbrt(const Dual<N> &a) { const double f = cbrt(a.v); return dchain(a, f, a.v != 0.0 ? f / (3.0 * a.v) : 0.0); }
+template <int N> DUAL_OP Dual<N> dlog(const Dual<N> &a) { return dchain(a, log(a.v), 1.0 / a.v); }
+template <int N> DUAL_OP Dual<N> dexp(const Dual<N> &a) { const double f = exp(a.v); return dchain(a, f, f); }
+template <int N> DUAL_OP Dual<N> datan(const Dual<N> &a) { return dchain(a, atan(a.v), 1.0 / (1.0 + a.v * a.v)); }
+template <int N> DUAL_OP Dual<N> dasinh(const Dual<N> &a) { return dchain(a, asinh(a.v), 1.0 / sqrt(1.0 + a.v * a.v)); }
+
+// Becke 88 exchange of ONE spin channel: e_s = -rho_s^(4/3) [ (3/2)(3/4pi)^(1/3) + beta x^2 / (1 + 6 beta x asinh x) ],
+// x = |grad rho_s| / rho_s^(4/3), beta = 0.0042 (Becke, PRA 38, 3098 (1988))
+template <int N> DUAL_OP Dual<N> b88_spin(const Dual<N> &rs, const Dual<N> &sss) {
+    const double BETA88 = 0.0042, CX88 = 0.93052573634910002;   // (3/2) (3 / 4 pi)^(1/3)
+    const Dual<N> c = dcbrt(rs);
+    const Dual<N> r43 = rs * c;
+    const Dual<N> x = dsqrt(sss) / r43;
+    return -(r43 * (CX88 + BETA88 * x * x / (1.0 + 6.0 * BETA88 * x * dasinh(x))));
+}
+// Lee-Yang-Parr correlation in the gradient-only form of Miehlich, Savin, Stoll, Preuss, CPL 157, 200 (1989)
+template <int N> DUAL_OP Dual<N> lyp_energy(const Dual<N> &ra, const Dual<N> &rb, const Dual<N> &saa, const Dual<N> &sab,
+                                            const Dual<N> &sbb) {
+    const double A = 0.04918, B = 0.132, C = 0.2533, Dd = 0.349;
+    const double CF = 2.8712340001881918;                        // (3/10) (3 pi^2)^(2/3)
+    const Dual<N> rho = ra + rb;
+    const Dual<N> c13 = dcbrt(rho);
+    const Dual<N> rm13 = 1.0 / c13;
+    const Dual<N> den = 1.0 + Dd * rm13;
+    const Dual<N> r2 = rho * rho;
+    const Dual<N> omega = dexp(-(C * rm13)) / den / (r2 * rho * c13 * c13);         // rho^(-11/3)
+    const Dual<N> delta = C * rm13 + Dd * rm13 / den;
+    const Dual<N> ca = dcbrt(ra), cb = dcbrt(rb);
+    const Dual<N> ra83 = ra * ra * ca * ca, rb83 = rb * rb * cb * cb;
+    const Dual<N> stot = saa + 2.0 * sab + sbb;
+    const Dual<N> rab = ra * rb;
+    const Dual<N> t1 = 12.699208415745595 * CF * (ra83 + rb83);                       // 2^(11/3) CF (...)
+    const Dual<N> t2 = (47.0 / 18.0 - (7.0 / 18.0) * delta) * stot;
+    const Dual<N> t3 = (2.5 - delta / 18.0) * (saa + sbb);
+    const Dual<N> t4 = ((delta - 11.0) / 9.0) * ((ra * saa + rb * sbb) / rho);
+    const Dual<N> inner = rab * (t1 + t2 - t3 - t4) - (2.0 / 3.0) * r2 * stot + ((2.0 / 3.0) * r2 - ra * ra) * sbb +
+                          ((2.0 / 3.0) * r2 - rb * rb) * saa;
+    return -(A * 4.0 * rab / (den * rho)) - (A * B) * omega * inner;
+}
+// Vosko-Wilk-Nusair: eps(x = sqrt(rs)) of one parameter set (VWN, Can. J. Phys. 58, 1200 (1980), eq. 4.4)
+template <int N> DUAL_OP Dual<N> vwn_aux(const Dual<N> &x, double A, double x0, double b, double c) {
+    const double Q = sqrt(4.0 * c - b * b), X0 = x0 * x0 + b * x0 + c;
+    const Dual<N> X = x * x + b * x + c;
+    const Dual<N> at = datan(Q / (2.0 * x + b));
+    const Dual<N> xm = x - x0;
+    return A * (dlog(x * x / X) + (2.0 * b / Q) * at -
+                (b * x0 / X0) * (dlog(xm * xm / X) + (2.0 * (b + 2.0 * x0) / Q) * at));
+}
+// energy per volume; rpa = false: VWN5 with the spin-stiffness interpolation, true: the RPA parameter sets with
+// the plain f(zeta) interpolation between para- and ferromagnetic (libxc lda_c_vwn / lda_c_vwn_rpa)
+template <int N> DUAL_OP Dual<N> vwn_energy(bool rpa, const Dual<N> &ra, const Dual<N> &rb) {
+    const Dual<N> rho = ra + rb;
+    const Dual<N> x = dsqrt(0.62035049089940009 / dcbrt(rho));                       // sqrt(rs), rs = (3 / 4 pi rho)^(1/3)
+    Dual<N> zeta = (ra - rb) / rho;
+    const Dual<N> opz = 1.0 + zeta, omz = 1.0 - zeta;
+    const Dual<N> fz = (opz * dcbrt(opz) + omz * dcbrt(omz) - 2.0) / FZ_DEN;
+    Dual<N> eps;
+    if (rpa) {
+        const Dual<N> ep = vwn_aux(x, 0.0310907, -0.409286, 13.0720, 42.7198);
+        const Dual<N> ef = vwn_aux(x, 0.01554535, -0.743294, 20.1231, 101.578);
+        eps = ep + (ef - ep) * fz;
+    } else {
+        const Dual<N> ep = vwn_aux(x, 0.0310907, -0.10498, 3.72744, 12.9352);
+        const Dual<N> ef = vwn_aux(x, 0.01554535, -0.32500, 7.06042, 18.0578);
+        const Dual<N> ac = vwn_aux(x, -1.0 / (6.0 * PI * PI), -0.0047584, 1.13107, 13.0045);
+        const Dual<N> z2 = zeta * zeta, z4 = z2 * z2;
+        eps = ep + ac * fz * (1.0 - z4) / 1.7099209341613657 + (ef - ep) * fz * z4;
+    }
+    return rho * eps;
+}
+// unpolarised front ends of the dual-number functionals: (rho, sigma) -> e, de/drho, de/dsigma
+__device__ __forceinline__ void dual_unpol(int id, double rho, double sigma, double &e, double &vr, double &vs) {
+    typedef Dual<2> T;
+    // spin-resolved inputs of the closed-shell point: rho_s = rho / 2, sigma_ss' = sigma / 4
+    const T ra = dvar<2>(0.5 * rho, 0, 0.5), sq = dvar<2>(0.25 * sigma, 1, 0.25);
+    T r;
+    switch (id) {
+        case XC_GGA_X_B88: r = 2.0 * b88_spin(ra, sq); break;
+        case XC_GGA_C_LYP: r = lyp_energy(ra, ra, sq, sq, sq); break;
+        case XC_LDA_C_VWN: r = vwn_energy(false, ra, ra); break;
+        default: r = vwn_energy(true, ra, ra); break;
+    }
+    e = r.v; vr = r.d[0]; vs = r.d[1];
 }
 
 // ---- unpolarised: (rho, sigma) -> e (per volume), de/drho, de/dsigma ----
@@ -187,6 +318,7 @@ __global__ void xc_unpol_kernel(XCTerms terms, int64_t n, int64_t ld, const doub
                     xc::gga_c_pbe_core(r, 0.0, sigma, ek, vrk, vd, vsk);
                     break;
                 }
+                default: xc::dual_unpol(terms.id[k], r, sigma, ek, vrk, vsk); break;
             }
             e += terms.coef[k] * ek;
             vr += terms.coef[k] * vrk;
@@ -225,13 +357,14 @@ __global__ void xc_pol_kernel(XCTerms terms, int64_t n, int64_t ld, const double
     for (int k = 0; k < terms.n; k++) {
         double ek = 0, vuk = 0, vdk = 0, suuk = 0, sudk = 0, sddk = 0;
         const int id = terms.id[k];
-        if (id == XC_LDA_X || id == XC_GGA_X_PBE) {
+        if (id == XC_LDA_X || id == XC_GGA_X_PBE || id == XC_GGA_X_B88) {
             // spin scaling: E[ru, rd] = (E[2 ru] + E[2 rd]) / 2
             for (int s = 0; s < 2; s++) {
                 const double r2 = 2.0 * (s ? rd : ru);
                 if (!(r2 > XC_RHO_CUT)) continue;
                 double es, vr, vs = 0;
                 if (id == XC_LDA_X) xc::lda_x_unpol(r2, es, vr);
+                else if (id == XC_GGA_X_B88) xc::dual_unpol(id, r2, 4.0 * (s ? sdd : suu), es, vr, vs);
                 else xc::gga_x_pbe_unpol(r2, 4.0 * (s ? sdd : suu), es, vr, vs);
                 ek += 0.5 * es;
                 // d/dr_s [0.5 E(2 r_s, 4 sigma_ss)] = vr ; d/dsigma_ss = 2 vs
@@ -251,6 +384,15 @@ __global__ void xc_pol_kernel(XCTerms terms, int64_t n, int64_t ld, const double
                 double vs;
                 xc::gga_c_pbe_core(rt, zeta, suu + 2.0 * sud + sdd, ek, vuk, vdk, vs);
                 suuk = vs; sudk = 2.0 * vs; sddk = vs;
+            } else if (id == XC_GGA_C_LYP) {
+                typedef xc::Dual<5> T;
+                const T r = xc::lyp_energy(xc::dvar<5>(ru, 0), xc::dvar<5>(rd, 1), xc::dvar<5>(suu, 2),
+                                           xc::dvar<5>(sud, 3), xc::dvar<5>(sdd, 4));
+                ek = r.v; vuk = r.d[0]; vdk = r.d[1]; suuk = r.d[2]; sudk = r.d[3]; sddk = r.d[4];
+            } else if (id == XC_LDA_C_VWN || id == XC_LDA_C_VWN_RPA) {
+                typedef xc::Dual<2> T;
+                const T r = xc::vwn_energy(id == XC_LDA_C_VWN_RPA, xc::dvar<2>(ru, 0), xc::dvar<2>(rd, 1));
+                ek = r.v; vuk = r.d[0]; vdk = r.d[1];
             }
         }
         const double c = terms.coef[k];
@@ -277,7 +419,8 @@ static int xc_pack_terms(int nterm, const int *ids, const double *coefs, XCTerms
     for (int k = 0; k < nterm; k++) {
         const int id = ids[k];
         QC_REQUIRE(id == XC_LDA_X || id == XC_LDA_C_PW || id == XC_LDA_C_PW_MOD || id == XC_GGA_X_PBE ||
-                       id == XC_GGA_C_PBE, "unknown functional id");
+                       id == XC_GGA_C_PBE || id == XC_LDA_C_VWN || id == XC_LDA_C_VWN_RPA || id == XC_GGA_X_B88 ||
+                       id == XC_GGA_C_LYP, "unknown functional id");
         gga = gga || id >= 100;
         t.id[k] = id;
         t.coef[k] = coefs[k];

@@ -26,7 +26,24 @@ PBE_KAPPA = 0.8040
 PBE_BETA = 0.06672455060314922
 PBE_MU = PBE_BETA * PI * PI / 3.0
 PBE_GAMMA = (1.0 - math.log(2.0)) / (PI * PI)
-FAMILY = {"lda_x": 1, "lda_c_pw": 1, "lda_c_pw_mod": 1, "gga_x_pbe": 2, "gga_c_pbe": 2}
+FAMILY = {"lda_x": 1, "lda_c_pw": 1, "lda_c_pw_mod": 1, "gga_x_pbe": 2, "gga_c_pbe": 2,
+          "lda_c_vwn": 1, "lda_c_vwn_rpa": 1, "gga_x_b88": 2, "gga_c_lyp": 2}
+# B88 / LYP / VWN: PARITY UNPINNED in-tree (the reference reaches them only through libxc, absent here, and its
+# tests hold no numbers for them).  Restated from the original papers; cross-checked against literature atomic
+# energies in tests/test_oracle_golden.py (flagged there as external, not from the reference).
+_VWN5 = ((0.0310907, -0.10498, 3.72744, 12.9352), (0.01554535, -0.32500, 7.06042, 18.0578),
+         (-1.0 / (6 * math.pi ** 2), -0.0047584, 1.13107, 13.0045))
+_VWN_RPA = ((0.0310907, -0.409286, 13.0720, 42.7198), (0.01554535, -0.743294, 20.1231, 101.578))
+
+
+def _vwn_aux(x, A, x0, b, c):
+    """VWN, Can. J. Phys. 58, 1200 (1980), eq. 4.4; x = sqrt(rs)."""
+    Q = math.sqrt(4 * c - b * b)
+    X = x * x + b * x + c
+    X0 = x0 * x0 + b * x0 + c
+    at = torch.atan(Q / (2 * x + b))
+    return A * (torch.log(x * x / X) + 2 * b / Q * at
+                - b * x0 / X0 * (torch.log((x - x0) ** 2 / X) + 2 * (b + 2 * x0) / Q * at))
 
 
 def _lda_x_unpol(rho):
@@ -76,6 +93,38 @@ def edens_pol(name, ru, rd, gu=None, gd=None):
         At2 = A * t2
         H = gp3 * torch.log1p(PBE_BETA / PBE_GAMMA * t2 * (1 + At2) / (1 + At2 + At2 * At2))
         return rho * (eps + H)
+    if name in ("lda_c_vwn", "lda_c_vwn_rpa"):
+        x = torch.sqrt((3.0 / (4 * PI * rho)) ** (1.0 / 3))
+        zeta = (ru - rd) / rho
+        fz = ((1 + zeta) ** (4.0 / 3) + (1 - zeta) ** (4.0 / 3) - 2) / (2 ** (4.0 / 3) - 2)
+        if name == "lda_c_vwn_rpa":     # libxc lda_c_vwn_rpa: plain f(zeta) interpolation of the RPA fits
+            ep, ef = (_vwn_aux(x, *p) for p in _VWN_RPA)
+            return rho * (ep + (ef - ep) * fz)
+        ep, ef, ac = (_vwn_aux(x, *p) for p in _VWN5)   # libxc lda_c_vwn = VWN5
+        fpp0 = 4.0 / (9.0 * (2 ** (1.0 / 3) - 1))
+        z4 = zeta ** 4
+        return rho * (ep + ac * fz * (1 - z4) / fpp0 + (ef - ep) * fz * z4)
+    if name == "gga_x_b88":
+        def one(r, g):   # one spin channel (Becke, PRA 38, 3098 (1988)), beta = 0.0042
+            r43 = r ** (4.0 / 3)
+            x = torch.sqrt((g * g).sum(0)) / r43
+            return -r43 * (1.5 * (3.0 / (4 * PI)) ** (1.0 / 3) + 0.0042 * x * x / (1 + 6 * 0.0042 * x * torch.asinh(x)))
+        return one(ru, gu) + one(rd, gd)
+    if name == "gga_c_lyp":
+        # Miehlich, Savin, Stoll, Preuss, CPL 157, 200 (1989), eq. 2 (LYP without the Laplacian)
+        a, b, c, d = 0.04918, 0.132, 0.2533, 0.349
+        cf = 0.3 * (3 * PI * PI) ** (2.0 / 3)
+        saa, sbb, sab = (gu * gu).sum(0), (gd * gd).sum(0), (gu * gd).sum(0)
+        stot = saa + 2 * sab + sbb
+        rm13 = rho ** (-1.0 / 3)
+        den = 1 + d * rm13
+        omega = torch.exp(-c * rm13) / den * rho ** (-11.0 / 3)
+        delta = c * rm13 + d * rm13 / den
+        inner = ru * rd * (2 ** (11.0 / 3) * cf * (ru ** (8.0 / 3) + rd ** (8.0 / 3))
+                           + (47.0 / 18 - 7 * delta / 18) * stot - (2.5 - delta / 18) * (saa + sbb)
+                           - (delta - 11) / 9 * (ru / rho * saa + rd / rho * sbb)) \
+            - 2.0 / 3 * rho * rho * stot + (2.0 / 3 * rho * rho - ru * ru) * sbb + (2.0 / 3 * rho * rho - rd * rd) * saa
+        return -a * 4 / den * ru * rd / rho - a * b * omega * inner
     raise KeyError(name)
 
 
