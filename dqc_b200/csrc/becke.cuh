@@ -22,25 +22,26 @@ __global__ void __launch_bounds__(BECKE_THREADS)
 becke_weights_kernel(const double *__restrict__ xyz, const int *__restrict__ owner, int64_t ngrid,
                      const double *__restrict__ pos, int nat, const double *__restrict__ rinv,
                      const double *__restrict__ aij, double *__restrict__ w) {
-    extern __shared__ double rg[];  // [nat][BECKE_THREADS]
+    extern __shared__ double rg[];  // [nat][blockDim.x]
     const int tid = threadIdx.x;
-    const int64_t g = (int64_t)blockIdx.x * BECKE_THREADS + tid;
+    const int BT = blockDim.x;       // 128, or fewer points per CTA when many atoms must fit in shared memory
+    const int64_t g = (int64_t)blockIdx.x * BT + tid;
     if (g >= ngrid) return;  // no block-wide barrier below
     const double x = xyz[3 * g], y = xyz[3 * g + 1], z = xyz[3 * g + 2];
     for (int k = 0; k < nat; k++) {
         const double dx = x - pos[3 * k], dy = y - pos[3 * k + 1], dz = z - pos[3 * k + 2];
-        rg[k * BECKE_THREADS + tid] = sqrt(dx * dx + dy * dy + dz * dz);
+        rg[k * BT + tid] = sqrt(dx * dx + dy * dy + dz * dz);
     }
     const int own = owner[g];
     const double sdiag = 0.5 * (1.0 + 1e-12) + 0.5;  // the i == j factor, kept for fidelity (:259)
     double psum = 0.0, pown = 0.0;
     for (int j = 0; j < nat; j++) {
-        const double rj = rg[j * BECKE_THREADS + tid];
+        const double rj = rg[j * BT + tid];
         double P = sdiag;
         bool keep = true;
         for (int i = 0; i < nat; i++) {
             if (i == j) continue;
-            double mu = (rj - rg[i * BECKE_THREADS + tid]) / rinv[i * nat + j];
+            double mu = (rj - rg[i * BT + tid]) / rinv[i * nat + j];
             if (aij) mu += aij[i * nat + j] * (1.0 - mu * mu);
             if (!(mu < 0.74)) {
                 keep = false;
@@ -69,12 +70,14 @@ extern "C" int b200qc_becke_weights(const double *xyz, const int *owner, int64_t
     QC_CHECK(cudaMallocAsync(&rinv, sizeof(double) * natom * natom, st));
     becke_pairs_kernel<<<(natom * natom + 255) / 256, 256, 0, st>>>(atompos, natom, rinv);
     QC_LAUNCHED(1);
-    const size_t smem = sizeof(double) * natom * BECKE_THREADS;
-    QC_REQUIRE(smem <= 200 * 1024, "too many atoms for the shared-memory distance column");
+    int bt = BECKE_THREADS;          // points per CTA: halve until the distance column fits (<= 800 atoms)
+    while (bt > 32 && sizeof(double) * natom * bt > 200 * 1024) bt >>= 1;
+    const size_t smem = sizeof(double) * natom * bt;
+    QC_REQUIRE(smem <= 200 * 1024, "too many atoms for the shared-memory distance column (> 800)");
     QC_CHECK(cudaFuncSetAttribute(becke_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int nblk = (int)((ngrid + BECKE_THREADS - 1) / BECKE_THREADS);
+    const int nblk = (int)((ngrid + bt - 1) / bt);
     prof_begin(PROF_BECKE, st);
-    becke_weights_kernel<<<nblk, BECKE_THREADS, smem, st>>>(xyz, owner, ngrid, atompos, natom, rinv, aij, w);
+    becke_weights_kernel<<<nblk, bt, smem, st>>>(xyz, owner, ngrid, atompos, natom, rinv, aij, w);
     prof_end(st);
     QC_LAUNCHED(1);
     QC_CHECK(cudaFreeAsync(rinv, st));
