@@ -74,8 +74,9 @@ _SIGS = {
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                                        ctypes.c_void_p, ctypes.c_void_p]),
+                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_i8_debug_variant": (ctypes.c_int, [ctypes.c_int]),
+    "b200qc_i8_mode": (ctypes.c_int, [ctypes.c_int]),
     "b200qc_rho_i8_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_rho_sb_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -692,6 +693,9 @@ class GridBlocks(object):
                                           _ptr(self.ao), _stream()), "eval_gto_sb")
         # optional tcgen05 int8 (Ozaki) form of the Vxc GEMM: the AO values are sliced once here
         self.i8_slices, self.i8_variant = int(i8_slices), int(i8_variant)
+        from dqc_b200.utils.config import config as _cfg
+        _check(lib.b200qc_i8_mode(int(_cfg.I8_MODE)), "i8_mode")
+        lib.b200qc_i8_debug_variant(self.i8_variant)
         if self.i8_slices and self.nsb:
             S = self.i8_slices
             a_bytes = S * self.sbp * ((nsp + 127) // 128 * 128)      # A operand: whole 128-column M tiles
@@ -699,6 +703,9 @@ class GridBlocks(object):
             ntile = ((nsp + 127) // 128) * (nsp // 64)
             self.d_tile_off = tt(excl(ntile), torch.int32)
             self.ntiles = int(ntile.sum())
+            nptile = ((nsp + 127) // 128) ** 2                        # cluster mode: (M tile, pair of N tiles) units
+            self.d_ptile_off = tt(excl(nptile), torch.int32)
+            self.nptiles = int(nptile.sum())
             self.d_a_off = tt(excl(a_bytes), torch.int64)
             self.d_b_off = tt(excl(b_bytes), torch.int64)
             self.aplanes = torch.zeros(int(a_bytes.sum()), dtype=torch.int8, device=dev)
@@ -750,7 +757,8 @@ class GridBlocks(object):
                                         _ptr(self.d_idx), _ptr(self.ao), _ptr(self.w), _ptr(vrho.contiguous()),
                                         _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(self.vb), _ptr(self.aplanes),
                                         _ptr(self.d_a_off), _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.d_b_off),
-                                        _ptr(self.bscale), _ptr(self.d_tile_off), self.ntiles, _ptr(mat), _stream()),
+                                        _ptr(self.bscale), _ptr(self.d_tile_off), self.ntiles, _ptr(self.d_ptile_off),
+                                        self.nptiles, _ptr(mat), _stream()),
                    "vxc_sb_i8")
             return mat
         _check(lib.b200qc_vxc_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),

@@ -12,6 +12,7 @@
 #include "vxc_i8.cuh"
 
 #define RI8_STAGES 5      // no staging tile here: 5 x 36 KB ring
+#define RI8_THREADS 384   // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue
 
 // ---- A operand: phi rows -> S int8 planes, K-major tiles; scale per grid row ----
 // out (per SB, bytes): [row tile = g / 128][k tile = mu / 32][slice][(mu % 32) / 16][(g % 128) / 8][g % 8][mu % 16]
@@ -92,25 +93,40 @@ sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict_
 // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
 #define RI8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((I8_BN >> 3) << 17) | ((I8_BM >> 4) << 24))
 
-template <int S, int NCOMP>
-__global__ void __launch_bounds__(I8_THREADS, 1)
+// MC = 1: launched in 2-CTA clusters; both CTAs work on the same (superblock, 128-row block), CTA r takes the N
+// tiles 2 p + r, every A stage is fetched half by each CTA and multicast to both, and the two partial row sums
+// are added atomically into the zero-initialised outputs (two addends: the sum does not depend on the order).
+__device__ __forceinline__ void ldcs_f64x4(const double *p, double &a, double &b, double &c, double &d) {
+    // one full 32-byte sector per lane (rows of different lanes are 4 KB apart: nothing else to coalesce)
+    asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// EH = number of column halves the epilogue splits an N tile into (1: 4 epilogue warps x 64 columns,
+// 2: 8 warps x 32 columns); the CTA has 128 + 128 EH threads.
+template <int S, int NCOMP, int MC, int EH>
+__global__ void __launch_bounds__(128 + 128 * EH, 1)
 rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__restrict__ ao,
               const signed char *__restrict__ aplanes, const int64_t *__restrict__ a_off,
               const signed char *__restrict__ bplanes, const int64_t *__restrict__ b_off,
               const double *__restrict__ rscale, const double *__restrict__ cscale, int64_t ngrid_ld,
-              double *__restrict__ rho, double *__restrict__ grad) {
+              double *__restrict__ rho, double *__restrict__ grad, int l2hint) {
+    // (l2hint: bit 0 = L2 evict_last on the A planes; bits 8.. = timing-experiment variant)
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * I8_B_PLANE, STAGE = A_STAGE + B_STAGE;
     __shared__ uint64_t full_bar[RI8_STAGES], empty_bar[RI8_STAGES], accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ double comb[I8_BM][NCOMP];     // row sums of the second column half, handed to the first
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mtiles = sbp / I8_BM;
     const int nunits = nsb * mtiles;
+    const int crank = MC ? (int)cluster_ctarank() : 0;
+    const int u0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustep = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int A_HALF = A_STAGE / 2;
 
     if (tid == 0) {
         for (int i = 0; i < RI8_STAGES; i++) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], MC ? 2 : 1);
         }
         mbar_init(&accum_full, 1);
         mbar_init(&accum_empty, 1);
@@ -122,28 +138,47 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_smem;
     const uint32_t sbase = smem_u32(i8_smem);
+    const int tstep = MC ? 2 : 1;        // N tiles per step of the (pair of) CTA(s)
+    const int variant = l2hint >> 8;     // timing experiments (b200qc_i8_debug_variant): 1 no AO loads, 2 no MMAs, 3 no epilogue work
+    l2hint &= 1;
 
     if (warp == 0) {
         // ===== producer =====
         if (lane == 0) {
             int it = 0;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const uint64_t pol = l2_policy_evict_last();
+            for (int u = u0; u < nunits; u += ustep) {
                 const int sb = u / mtiles, mt = u - sb * mtiles;
                 const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = nsp / I8_BN;
                 const signed char *A = aplanes + a_off[sb] + (int64_t)mt * nkt * A_STAGE;
                 const signed char *B = bplanes + b_off[sb];
-                for (int tn = 0; tn < ntn; tn++)
+                for (int t0 = 0; t0 < ntn; t0 += tstep) {
+                    const int tn = t0 + crank;
+                    const bool active = tn < ntn;
                     for (int kt = 0; kt < nkt; kt++, it++) {
                         const int slot = it % RI8_STAGES;
                         mbar_wait(&empty_bar[slot], ((it / RI8_STAGES) & 1) ^ 1);
-                        mbar_expect_tx(&full_bar[slot], STAGE);
-                        bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
-                        bulk_g2s(sbase + slot * STAGE + A_STAGE, B + ((int64_t)tn * nkt + kt) * B_STAGE, B_STAGE,
-                                 &full_bar[slot]);
+                        if (MC) {
+                            mbar_expect_tx(&full_bar[slot], A_STAGE + (active ? B_STAGE : 0));
+                            bulk_g2s_mc(sbase + slot * STAGE + crank * A_HALF, A + (int64_t)kt * A_STAGE + crank * A_HALF,
+                                        A_HALF, &full_bar[slot], (uint16_t)3);
+                            if (active)
+                                bulk_g2s(sbase + slot * STAGE + A_STAGE, B + ((int64_t)tn * nkt + kt) * B_STAGE, B_STAGE,
+                                         &full_bar[slot]);
+                        } else {
+                            mbar_expect_tx(&full_bar[slot], STAGE);
+                            // the A tile of a unit is read once per N tile: ask L2 to keep it (mode bit 1)
+                            if (l2hint) bulk_g2s_hint(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot], pol);
+                            else bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
+                            bulk_g2s(sbase + slot * STAGE + A_STAGE, B + ((int64_t)tn * nkt + kt) * B_STAGE, B_STAGE,
+                                     &full_bar[slot]);
+                        }
                     }
+                }
             }
         }
     } else if (warp == 1) {
@@ -153,36 +188,47 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
             // (A: 2048 B, B: 1024 B), SBO = stride between 8-row groups (128 B)
             const uint64_t da0 = umma_desc(sbase, 2048, 128), db0 = umma_desc(sbase + A_STAGE, 1024, 128);
             int it = 0, nt = 0;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            for (int u = u0; u < nunits; u += ustep) {
                 const int sb = u / mtiles;
                 const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = nsp / I8_BN;
-                for (int tn = 0; tn < ntn; tn++, nt++) {
-                    mbar_wait(&accum_empty, (nt & 1) ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int t0 = 0; t0 < ntn; t0 += tstep) {
+                    const bool active = t0 + crank < ntn;
+                    if (active) {
+                        mbar_wait(&accum_empty, (nt & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     for (int kt = 0; kt < nkt; kt++, it++) {
                         const int slot = it % RI8_STAGES;
                         mbar_wait(&full_bar[slot], (it / RI8_STAGES) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
+                        if (active && variant != 2) {
 #pragma unroll
-                        for (int dd = 0; dd < S; dd++)
+                            for (int dd = 0; dd < S; dd++)
 #pragma unroll
-                            for (int s2 = 0; s2 <= dd; s2++)
-                                umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
-                                        db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), RI8_IDESC,
-                                        (kt > 0 || s2 > 0) ? 1u : 0u);
-                        umma_commit(&empty_bar[slot]);
+                                for (int s2 = 0; s2 <= dd; s2++)
+                                    umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                            db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), RI8_IDESC,
+                                            (kt > 0 || s2 > 0) ? 1u : 0u);
+                        }
+                        if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3); else umma_commit(&empty_bar[slot]);
                     }
-                    umma_commit(&accum_full);
+                    if (active) {
+                        umma_commit(&accum_full);
+                        nt++;
+                    }
                 }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue warps: thread = grid row (TMEM lane) =====
-        const int lg = warp & 3;
+        // ===== epilogue: 8 warps; thread = grid row (TMEM lane quarter = warp % 4) x one 32-column half of the N tile.
+        // The dot products stream the fp64 AO values straight from HBM: twice the warps = twice the loads in flight.
+        constexpr int NC = I8_BN / EH;          // columns of the N tile per thread
+        const int lg = warp & 3, half = (warp - 4) >> 2;
         const int r = lg * 32 + lane;
+        const int c0 = half * NC;
         int nt = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        for (int u = u0; u < nunits; u += ustep) {
             const int sb = u / mtiles, mt = u - sb * mtiles;
             const SBDesc d = sbd[sb];
             const int ntn = d.nsp / I8_BN;
@@ -192,26 +238,44 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
             double part[NCOMP];
 #pragma unroll
             for (int c = 0; c < NCOMP; c++) part[c] = 0.0;
-            for (int tn = 0; tn < ntn; tn++, nt++) {
+            for (int tn = crank; tn < ntn; tn += tstep, nt++) {
+                // the AO values this thread will need for the tile: pull them into L2 while the MMAs still run
+                if (variant != 1 && variant != 3) {
+#pragma unroll
+                    for (int c = 0; c < NCOMP; c++)
+#pragma unroll
+                        for (int j = 0; j < NC; j += 16)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(phi + (int64_t)c * sbp * ld + tn * I8_BN + c0 + j));
+                }
                 mbar_wait(&accum_full, nt & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                double x[64];
+                double x[NC];
+                if (variant == 3) {
 #pragma unroll
-                for (int ch = 0; ch < 4; ch++) {
-                    double acc[16];
-                    i8_recombine16<S>(tmem + ((uint32_t)(lg * 32) << 16), ch * 16, acc);
+                    for (int j = 0; j < NC; j++) x[j] = 1.0;
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) x[ch * 16 + j] = acc[j];
+                    for (int ch = 0; ch < NC / 8; ch++) {
+                        double acc[8];
+                        i8_recombine8<S>(tmem + ((uint32_t)(lg * 32) << 16), I8_BN, c0 + ch * 8, acc);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) x[ch * 8 + j] = acc[j];
+                    }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");          // all four warps have drained TMEM
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * EH) : "memory");   // all epilogue warps have drained TMEM
                 if (warp == 4 && lane == 0)
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
                 // column scales, then the row dots with the fp64 AO values of this row
-                const int n0 = tn * I8_BN;
+                const int n0 = tn * I8_BN + c0;
                 const double *cs = cscale + d.idx_off + n0;
+                if (variant == 1 || variant == 3) {
 #pragma unroll
-                for (int j = 0; j < 64; j += 2) {
+                    for (int j = 0; j < NC; j++) part[0] += x[j];
+                    continue;
+                }
+#pragma unroll
+                for (int j = 0; j < NC; j += 2) {
                     const double2 s2 = *reinterpret_cast<const double2 *>(cs + j);
                     x[j] *= s2.x;
                     x[j + 1] *= s2.y;
@@ -221,25 +285,50 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                     const double *row = phi + (int64_t)c * sbp * ld + n0;
                     double s = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 64; j += 2) {
-                        // streaming, zero-reuse read: keep it from evicting the re-used int8 operand planes from L2
-                        const double2 v2 = __ldcs(reinterpret_cast<const double2 *>(row + j));
-                        s += x[j] * v2.x + x[j + 1] * v2.y;
+                    for (int j = 0; j < NC; j += 4) {
+                        // streaming, zero-reuse 256-bit reads (kept from evicting the re-used int8 planes from L2)
+                        double v0, v1, v2, v3;
+                        ldcs_f64x4(row + j, v0, v1, v2, v3);
+                        s += x[j] * v0 + x[j + 1] * v1 + x[j + 2] * v2 + x[j + 3] * v3;
                     }
                     part[c] += s;
                 }
             }
-            const double sa_ = rscale[(int64_t)sb * sbp + grow];
-            const int64_t g = (int64_t)sb * sbp + grow;
-            rho[g] = sa_ * part[0];
-            if (NCOMP == 4) {
+            // the two column halves of a row meet in shared memory (the next write of `comb` is ordered behind this
+            // read by the bar.sync 1 of the next unit's first N tile)
+            if (EH == 2) {
+                if (half == 1) {
 #pragma unroll
-                for (int dd = 0; dd < 3; dd++) grad[(int64_t)dd * ngrid_ld + g] = 2.0 * sa_ * part[dd + 1];
+                    for (int c = 0; c < NCOMP; c++) comb[r][c] = part[c];
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
+            if (half == 0) {
+                if (EH == 2) {
+#pragma unroll
+                    for (int c = 0; c < NCOMP; c++) part[c] += comb[r][c];
+                }
+                const double sa_ = rscale[(int64_t)sb * sbp + grow];
+                const int64_t g = (int64_t)sb * sbp + grow;
+                if (MC) {
+                    atomicAdd(rho + g, sa_ * part[0]);
+                    if (NCOMP == 4) {
+#pragma unroll
+                        for (int dd = 0; dd < 3; dd++) atomicAdd(grad + (int64_t)dd * ngrid_ld + g, 2.0 * sa_ * part[dd + 1]);
+                    }
+                } else {
+                    rho[g] = sa_ * part[0];
+                    if (NCOMP == 4) {
+#pragma unroll
+                        for (int dd = 0; dd < 3; dd++) grad[(int64_t)dd * ngrid_ld + g] = 2.0 * sa_ * part[dd + 1];
+                    }
+                }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_all();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -270,16 +359,34 @@ static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     QC_LAUNCHED(1);
     const size_t smem = (size_t)RI8_STAGES * S * (I8_A_PLANE + I8_B_PLANE);
     const int64_t ngl = (int64_t)nsb * sbp;
-    prof_begin(PROF_RHO, st);
-    if (grad) {
-        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rho_i8_kernel<S, 4><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off, bplanes, b_off, rscale,
-                                                              cscale, ngl, rho, grad);
-    } else {
-        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rho_i8_kernel<S, 1><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off, bplanes, b_off, rscale,
-                                                              cscale, ngl, rho, grad);
+    const bool mc = (g_i8_mode & 4) != 0;
+    const int l2hint = (g_i8_mode & 1) | (g_i8_variant << 8);
+    if (mc) {   // partial row sums of the two CTAs of a pair are added atomically
+        QC_CHECK(cudaMemsetAsync(rho, 0, sizeof(double) * ngl, st));
+        if (grad) QC_CHECK(cudaMemsetAsync(grad, 0, sizeof(double) * 3 * ngl, st));
     }
+    prof_begin(PROF_RHO, st);
+#define RHO_I8_LAUNCH(NCOMP_, MC_, EH_)                                                                                      \
+    do {                                                                                                                    \
+        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, NCOMP_, MC_, EH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)smem));                                                                          \
+        if (MC_)                                                                                                            \
+            QC_CHECK(launch_cluster2(rho_i8_kernel<S, NCOMP_, MC_, EH_>, NUM_SMS, 128 + 128 * EH_, smem, st, sbd, nsb, sbp, ao, \
+                                     aplanes, a_off, (const signed char *)bplanes, b_off, rscale, (const double *)cscale,   \
+                                     ngl, rho, grad, l2hint));                                                              \
+        else                                                                                                                \
+            rho_i8_kernel<S, NCOMP_, MC_, EH_><<<NUM_SMS, 128 + 128 * EH_, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off,     \
+                                                                                     bplanes, b_off, rscale, cscale, ngl,   \
+                                                                                     rho, grad, l2hint);                    \
+    } while (0)
+    // EH = 1: four epilogue warps.  (Eight warps x 32 columns measured the same 8.5 ms at C60 once the AO rows
+    // are prefetched into L2 and read with 256-bit loads, so the smaller CTA is used.)
+    if (grad) {
+        if (mc) RHO_I8_LAUNCH(4, 1, 1); else RHO_I8_LAUNCH(4, 0, 1);
+    } else {
+        if (mc) RHO_I8_LAUNCH(1, 1, 1); else RHO_I8_LAUNCH(1, 0, 1);
+    }
+#undef RHO_I8_LAUNCH
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;

@@ -124,6 +124,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Recombination of the S anti-diagonal accumulators of 16 columns: the int32 partial sums are merged exactly
@@ -144,12 +149,80 @@ __device__ __forceinline__ void i8_recombine16(uint32_t tmem_lane_base, int col0
     }
 }
 
+// 8-column variant (fewer live registers: kernels with more epilogue warps); acc_stride = TMEM columns between
+// the accumulators of consecutive anti-diagonals
+template <int S>
+__device__ __forceinline__ void i8_recombine8(uint32_t tmem_lane_base, int acc_stride, int col0, double (&out)[8]) {
+    uint32_t v[S][8];
+#pragma unroll
+    for (int dd = 0; dd < S; dd++) tmem_ld8_nowait(tmem_lane_base + dd * acc_stride + col0, v[dd]);
+    tmem_wait_ld();
+    const double sc = ldexp(1.0, -12 - 7 * (S - 1));
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        long long t = (long long)(int)v[0][j];
+#pragma unroll
+        for (int dd = 1; dd < S; dd++) t = (t << 7) + (long long)(int)v[dd][j];
+        out[j] = __ll2double_rn(t) * sc;
+    }
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- L2 cache hints and 2-CTA cluster multicast ----
+// mode bits (b200qc_i8_mode): 1 = L2 evict_last hint on the re-used A planes, 2 = K4 in 2-CTA clusters with the A
+// stage multicast to both CTAs (each CTA fetches half of it; the pair works on two N tiles of the same M tile),
+// 4 = the same for K2 (the pair splits the N tiles of one 128-row block and adds its partial row sums atomically)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// the data AND the complete_tx land at the same CTA-relative offsets in every CTA of `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+static int g_i8_mode = 0;
+extern "C" int b200qc_i8_mode(int flags) { g_i8_mode = flags; return 0; }
+
+template <typename K, typename... Args>
+static cudaError_t launch_cluster2(K kernel, int grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 // instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = 64, M = 128 (dense)
@@ -161,7 +234,10 @@ extern "C" int b200qc_i8_debug_variant(int v) { g_i8_variant = v; return 0; }
 // Persistent kernel: one CTA per SM walks tiles cta, cta + gridDim.x, ... of the flattened (superblock, M tile,
 // N tile) list; the epilogue of tile i (fp64 recombination already staged in shared memory, atomics still to
 // do) overlaps the main loop of tile i + 1.
-template <int S>
+// MC = 1: launched in 2-CTA clusters; `tile_off` / `ntiles` then describe PAIR units (superblock, M tile, pair of
+// N tiles); CTA r of the cluster owns N tile 2 p + r (idle when the superblock has an odd number of N tiles and
+// this is the missing one -- it still fetches and multicasts its half of every A stage).
+template <int S, int MC>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_off, int nsb, int ntiles,
                    const int *__restrict__ idx, const signed char *__restrict__ aplanes,
@@ -176,11 +252,14 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = sbp / I8_KT;
     double *tile = reinterpret_cast<double *>(i8_smem + I8_STAGES * STAGE);   // epilogue staging, after the ring
+    const int crank = MC ? (int)cluster_ctarank() : 0;
+    const int u0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustep = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int A_HALF = A_STAGE / 2;
 
     if (tid == 0) {
         for (int i = 0; i < I8_STAGES; i++) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], MC ? 2 : 1);     // MC: both CTAs of the pair release a stage
         }
         mbar_init(&accum_full, 1);
         mbar_init(&accum_empty, 1);
@@ -192,12 +271,14 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_all();      // the peer's barriers are initialised before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_smem;
     const uint32_t sbase = smem_u32(i8_smem);
 
-    // tile t -> (superblock, M tile, N tile); tile_off is the exclusive prefix of tiles per superblock
-    auto locate = [&](int t, int &sb, int &tm, int &tn) {
+    // tile t -> (superblock, M tile, N tile); tile_off is the exclusive prefix of tiles (MC: pair units) per
+    // superblock.  Returns false when this CTA has no N tile in the unit (MC, odd tile count).
+    auto locate = [&](int t, int &sb, int &tm, int &tn) -> bool {
         int lo = 0, hi = nsb;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -206,25 +287,41 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
         sb = lo;
         const int ntn = sbd[sb].nsp / I8_BN;
         const int r = t - tile_off[sb];
+        if (MC) {
+            const int ntp = (ntn + 1) >> 1;
+            tm = r / ntp;
+            tn = 2 * (r - tm * ntp) + crank;
+            return tn < ntn;
+        }
         tm = r / ntn;
         tn = r - tm * ntn;
+        return true;
     };
 
     if (warp == 0) {
         // ===== producer: two contiguous blocks per stage =====
         if (lane == 0) {
             int it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = u0; t < ntiles; t += ustep) {
                 int sb, tm, tn;
-                locate(t, sb, tm, tn);
+                const bool active = locate(t, sb, tm, tn);
                 const signed char *A = aplanes + a_off[sb] + (int64_t)tm * nk * A_STAGE;
                 const signed char *B = bplanes + b_off[sb] + (int64_t)tn * nk * B_STAGE;
                 for (int kt = 0; kt < nk; kt++, it++) {
                     const int slot = it % I8_STAGES;
                     mbar_wait(&empty_bar[slot], ((it / I8_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&full_bar[slot], STAGE);
-                    bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
-                    bulk_g2s(sbase + slot * STAGE + A_STAGE, B + (int64_t)kt * B_STAGE, B_STAGE, &full_bar[slot]);
+                    if (MC) {
+                        // this CTA's half of the A stage goes to both CTAs; the other half arrives from the peer
+                        mbar_expect_tx(&full_bar[slot], A_STAGE + (active ? B_STAGE : 0));
+                        bulk_g2s_mc(sbase + slot * STAGE + crank * A_HALF, A + (int64_t)kt * A_STAGE + crank * A_HALF, A_HALF,
+                                    &full_bar[slot], (uint16_t)3);
+                        if (active)
+                            bulk_g2s(sbase + slot * STAGE + A_STAGE, B + (int64_t)kt * B_STAGE, B_STAGE, &full_bar[slot]);
+                    } else {
+                        mbar_expect_tx(&full_bar[slot], STAGE);
+                        bulk_g2s(sbase + slot * STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
+                        bulk_g2s(sbase + slot * STAGE + A_STAGE, B + (int64_t)kt * B_STAGE, B_STAGE, &full_bar[slot]);
+                    }
                 }
             }
         }
@@ -235,15 +332,19 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
             // 8-row K groups (A: 1024 B, B: 512 B)
             const uint64_t da0 = umma_desc(sbase, LBO_A, 128), db0 = umma_desc(sbase + A_STAGE, LBO_B, 128);
             int it = 0, nt = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, nt++) {
-                mbar_wait(&accum_empty, (nt & 1) ^ 1);          // the epilogue has drained the previous tile
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int t = u0; t < ntiles; t += ustep) {
+                int sb_, tm_, tn_;
+                const bool active = MC ? locate(t, sb_, tm_, tn_) : true;
+                if (active) {
+                    mbar_wait(&accum_empty, (nt & 1) ^ 1);      // the epilogue has drained the previous tile
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 for (int kt = 0; kt < nk; kt++, it++) {
                     const int slot = it % I8_STAGES;
                     mbar_wait(&full_bar[slot], (it / I8_STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
-                    if (variant != 2) {                // (variant 2: timing experiment without the MMAs)
+                    if (variant != 2 && active) {      // (variant 2: timing experiment without the MMAs)
 #pragma unroll
                     for (int dd = 0; dd < S; dd++)
 #pragma unroll
@@ -251,19 +352,24 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
                             umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
                                     db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), I8_IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[slot]);     // frees the stage when the MMAs above retire
+                    // frees the stage (in both CTAs of a pair) when the MMAs above retire
+                    if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3); else umma_commit(&empty_bar[slot]);
                 }
-                umma_commit(&accum_full);
+                if (active) {
+                    umma_commit(&accum_full);
+                    nt++;
+                }
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue warps: TMEM lanes 32 (warp % 4) .., both 32-column halves =====
         const int lg = warp & 3;
         const int r = lg * 32 + lane;
-        int nt = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, nt++) {
+        int nt = -1;
+        for (int t = u0; t < ntiles; t += ustep) {
             int sb, tm, tn;
-            locate(t, sb, tm, tn);
+            if (!locate(t, sb, tm, tn)) continue;
+            nt++;
             const SBDesc d = sbd[sb];
             const int m0 = tm * I8_BM, n0 = tn * I8_BN;
             const int row = m0 + r;
@@ -305,6 +411,7 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -331,7 +438,7 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
                       const double *weights, const double *vrho, const double *vgrad, double *vb,
                       const int64_t *vb_off, const signed char *aplanes, const int64_t *a_off, const double *ascale,
                       signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
-                      int nao, double *mat, cudaStream_t st) {
+                      const int *ptile_off, int nptiles, int nao, double *mat, cudaStream_t st) {
     // K4a: vb = w (v phi + 2 g . grad phi) in fp64 (one streaming pass at the HBM roofline), then the slicer.
     // (A fused single-pass variant that staged a 32-column slab of vb in shared memory was slower: one
     // 128 KB CTA per SM cannot keep enough loads in flight.)
@@ -351,10 +458,17 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     prof_end(st);
     QC_LAUNCHED(1);
     const size_t smem = (size_t)I8_STAGES * S * (I8_A_PLANE + I8_B_PLANE) + sizeof(double) * I8_BM * I8_EPI_LD;
-    QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(PROF_VXC_GEMM, st);
-    vxc_i8_gemm_kernel<S><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, tile_off, nsb, ntiles, idx, aplanes, a_off, bplanes,
-                                                           b_off, ascale, bscale, sbp, nao, mat, g_i8_variant);
+    if ((g_i8_mode & 2) && ptile_off != nullptr) {
+        QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QC_CHECK(launch_cluster2(vxc_i8_gemm_kernel<S, 1>, NUM_SMS, I8_THREADS, smem, st, sbd, ptile_off, nsb, nptiles, idx,
+                                 aplanes, a_off, (const signed char *)bplanes, b_off, ascale, (const double *)bscale, sbp, nao,
+                                 mat, g_i8_variant));
+    } else {
+        QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vxc_i8_gemm_kernel<S, 0><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, tile_off, nsb, ntiles, idx, aplanes, a_off, bplanes,
+                                                                  b_off, ascale, bscale, sbp, nao, mat, g_i8_variant);
+    }
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;
@@ -367,8 +481,8 @@ extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_ns
                                 const double *ao, const double *weights, const double *vrho, const double *vgrad,
                                 int nao, const int64_t *vb_off, double *vb, const signed char *aplanes,
                                 const int64_t *a_off, const double *ascale, signed char *bplanes,
-                                const int64_t *b_off, double *bscale, const int *tile_off, int ntiles, double *mat,
-                                void *stream) {
+                                const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
+                                const int *ptile_off, int nptiles, double *mat, void *stream) {
     QC_REQUIRE(sbp % I8_KT == 0 && sbp % I8_BM == 0, "superblock size must be a multiple of 128");
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
     QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
@@ -378,7 +492,7 @@ extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_ns
     const SBDesc *sbd = (const SBDesc *)sbdesc;
     if (nslice == 5)
         return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
-                             bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
+                             bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
     return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
-                         bplanes, b_off, bscale, tile_off, ntiles, nao, mat, st);
+                         bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
 }

@@ -20,6 +20,9 @@ class _Config:
     # density GEMM (K2) on tcgen05 the same way: 0 = off (fp64 DMMA), 5 or 6 slices
     RHO_I8_SLICES: int = int(os.environ.get("B200QC_RHO_I8", "6"))
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
+    # scheduling of the tcgen05 XC kernels (bit mask): 1 = L2 evict_last hint on the K2 A planes, 2 = K4 in 2-CTA
+    # clusters with multicast A stages, 4 = K2 in 2-CTA clusters
+    I8_MODE: int = int(os.environ.get("B200QC_I8_MODE", "0"))
     # density-fitted exact exchange (two batched GEMMs on tcgen05): 5 or 6 int8 slices
     DFK_I8_SLICES: int = int(os.environ.get("B200QC_DFK_I8", "6"))
     # the reference raises for exact exchange with density fitting (hcgto.py:229-230); set to 0 for that behaviour

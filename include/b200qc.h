@@ -132,7 +132,13 @@ int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nsli
                      const double *weights, const double *vrho, const double *vgrad, int nao, const int64_t *vb_off,
                      double *vb, const signed char *aplanes, const int64_t *a_off, const double *ascale,
                      signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
-                     double *mat, void *stream);
+                     const int *ptile_off, int nptiles, double *mat, void *stream);
+/* Scheduling switches of the tcgen05 kernels (bit mask; default 0): 1 = L2 evict_last hint on the re-used A planes
+ * of K2; 2 = K4 in 2-CTA thread-block clusters, every A stage fetched half by each CTA and multicast to both (the
+ * pair works on two N tiles of one M tile; needs ptile_off / nptiles = exclusive prefix and total of
+ * ceil(nsp / 128) * ceil(nsp / 128) pair units per superblock, else NULL / 0); 4 = the same for K2 (the pair splits
+ * the N tiles of one 128-row block; partial row sums are added atomically). */
+int b200qc_i8_mode(int flags);
 
 /* timing experiments on the kernel above: 0 = normal, 1 = skip the epilogue, 2 = skip the MMAs */
 int b200qc_i8_debug_variant(int v);
