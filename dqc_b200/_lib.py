@@ -73,7 +73,7 @@ _SIGS = {
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_i8_debug_variant": (ctypes.c_int, [ctypes.c_int]),
     "b200qc_i8_mode": (ctypes.c_int, [ctypes.c_int]),
@@ -698,9 +698,11 @@ class GridBlocks(object):
         lib.b200qc_i8_debug_variant(self.i8_variant)
         if self.i8_slices and self.nsb:
             S = self.i8_slices
+            # N tile of the GEMM: 96 with 5 slices (5 x 96 = 480 TMEM columns), else 64
+            self.i8_bn = bn = 96 if (S == 5 and _cfg.VXC_I8_BN == 96) else 64
             a_bytes = S * self.sbp * ((nsp + 127) // 128 * 128)      # A operand: whole 128-column M tiles
-            b_bytes = S * self.sbp * nsp
-            ntile = ((nsp + 127) // 128) * (nsp // 64)
+            b_bytes = S * self.sbp * ((nsp + bn - 1) // bn * bn)      # B operand: whole N tiles (zero padding)
+            ntile = ((nsp + 127) // 128) * ((nsp + bn - 1) // bn)
             self.d_tile_off = tt(excl(ntile), torch.int32)
             self.ntiles = int(ntile.sum())
             nptile = ((nsp + 127) // 128) ** 2                        # cluster mode: (M tile, pair of N tiles) units
@@ -709,7 +711,7 @@ class GridBlocks(object):
             self.d_a_off = tt(excl(a_bytes), torch.int64)
             self.d_b_off = tt(excl(b_bytes), torch.int64)
             self.aplanes = torch.zeros(int(a_bytes.sum()), dtype=torch.int8, device=dev)
-            self.bplanes = torch.empty(int(b_bytes.sum()), dtype=torch.int8, device=dev)
+            self.bplanes = torch.zeros(int(b_bytes.sum()), dtype=torch.int8, device=dev)
             self.ascale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
             self.bscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
             _check(lib.b200qc_vxc_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, S, _ptr(self.ao),
@@ -757,7 +759,7 @@ class GridBlocks(object):
                                         _ptr(self.d_idx), _ptr(self.ao), _ptr(self.w), _ptr(vrho.contiguous()),
                                         _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(self.vb), _ptr(self.aplanes),
                                         _ptr(self.d_a_off), _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.d_b_off),
-                                        _ptr(self.bscale), _ptr(self.d_tile_off), self.ntiles, _ptr(self.d_ptile_off),
+                                        _ptr(self.bscale), self.i8_bn, _ptr(self.d_tile_off), self.ntiles, _ptr(self.d_ptile_off),
                                         self.nptiles, _ptr(mat), _stream()),
                    "vxc_sb_i8")
             return mat

@@ -133,11 +133,11 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 // Recombination of the S anti-diagonal accumulators of 16 columns: the int32 partial sums are merged exactly
 // in int64 (sum_d acc_d 128^(S-1-d), |.| < 2^60), converted once and scaled -- 1 I2F per element instead of S.
-template <int S>
+template <int S, int ACC_STRIDE = 64>
 __device__ __forceinline__ void i8_recombine16(uint32_t tmem_lane_base, int col0, double (&out)[16]) {
     uint32_t v[S][16];
 #pragma unroll
-    for (int dd = 0; dd < S; dd++) tmem_ld16_nowait(tmem_lane_base + dd * I8_BN + col0, v[dd]);
+    for (int dd = 0; dd < S; dd++) tmem_ld16_nowait(tmem_lane_base + dd * ACC_STRIDE + col0, v[dd]);
     tmem_wait_ld();
     const double sc = ldexp(1.0, -12 - 7 * (S - 1));
 #pragma unroll
@@ -237,27 +237,37 @@ extern "C" int b200qc_i8_debug_variant(int v) { g_i8_variant = v; return 0; }
 // MC = 1: launched in 2-CTA clusters; `tile_off` / `ntiles` then describe PAIR units (superblock, M tile, pair of
 // N tiles); CTA r of the cluster owns N tile 2 p + r (idle when the superblock has an odd number of N tiles and
 // this is the missing one -- it still fetches and multicasts its half of every A stage).
-template <int S, int MC>
-__global__ void __launch_bounds__(I8_THREADS, 1)
+// BN = N tile: 64, or 96 with S = 5 (5 x 96 = 480 TMEM columns).  tcgen05.mma reads both operands from shared memory
+// for every instruction, so at N = 64 the tensor pipe waits on shared-memory bandwidth (21 x 6 KB read + 36 KB written
+// per K step); N = 96 with S = 5 moves 42 % fewer bytes per unit of work and issues 29 % fewer MMAs.
+// EW = epilogue warps: 4, or 8 (two per TMEM lane quarter, each draining half of the columns -- the drain is what
+// keeps the MMA issuer waiting between tiles -- and half of the rows of the atomic phase); CTA = 128 + 32 EW threads.
+template <int S, int MC, int BN, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_off, int nsb, int ntiles,
                    const int *__restrict__ idx, const signed char *__restrict__ aplanes,
                    const int64_t *__restrict__ a_off, const signed char *__restrict__ bplanes,
                    const int64_t *__restrict__ b_off, const double *__restrict__ ascale,
                    const double *__restrict__ bscale, int sbp, int nao, double *__restrict__ mat, int variant) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
-    constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * I8_B_PLANE, STAGE = A_STAGE + B_STAGE;
-    constexpr uint32_t LBO_A = (I8_BM / 16) * 128, LBO_B = (I8_BN / 16) * 128;   // stride between 8-row K groups
-    __shared__ uint64_t full_bar[I8_STAGES], empty_bar[I8_STAGES], accum_full, accum_empty;
+    static_assert(S * BN <= 512, "accumulators exceed the tensor memory");
+    constexpr int B_PLANE = I8_KT * BN, NSTAGE = (BN == 96) ? 3 : I8_STAGES, EPI_LD = BN + 1;
+    constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * B_PLANE, STAGE = A_STAGE + B_STAGE;
+    constexpr uint32_t LBO_A = (I8_BM / 16) * 128, LBO_B = (BN / 16) * 128;   // stride between 8-row K groups
+    // instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = BN, M = 128 (dense)
+    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(I8_BM >> 4) << 24);
+    __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = sbp / I8_KT;
-    double *tile = reinterpret_cast<double *>(i8_smem + I8_STAGES * STAGE);   // epilogue staging, after the ring
+    double *tile = reinterpret_cast<double *>(i8_smem + NSTAGE * STAGE);   // epilogue staging, after the ring
     const int crank = MC ? (int)cluster_ctarank() : 0;
     const int u0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustep = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int A_HALF = A_STAGE / 2;
 
     if (tid == 0) {
-        for (int i = 0; i < I8_STAGES; i++) {
+        for (int i = 0; i < NSTAGE; i++) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], MC ? 2 : 1);     // MC: both CTAs of the pair release a stage
         }
@@ -285,7 +295,7 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
             if (tile_off[mid] <= t) lo = mid; else hi = mid;
         }
         sb = lo;
-        const int ntn = sbd[sb].nsp / I8_BN;
+        const int ntn = (sbd[sb].nsp + BN - 1) / BN;
         const int r = t - tile_off[sb];
         if (MC) {
             const int ntp = (ntn + 1) >> 1;
@@ -308,8 +318,8 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
                 const signed char *A = aplanes + a_off[sb] + (int64_t)tm * nk * A_STAGE;
                 const signed char *B = bplanes + b_off[sb] + (int64_t)tn * nk * B_STAGE;
                 for (int kt = 0; kt < nk; kt++, it++) {
-                    const int slot = it % I8_STAGES;
-                    mbar_wait(&empty_bar[slot], ((it / I8_STAGES) & 1) ^ 1);
+                    const int slot = it % NSTAGE;
+                    mbar_wait(&empty_bar[slot], ((it / NSTAGE) & 1) ^ 1);
                     if (MC) {
                         // this CTA's half of the A stage goes to both CTAs; the other half arrives from the peer
                         mbar_expect_tx(&full_bar[slot], A_STAGE + (active ? B_STAGE : 0));
@@ -340,8 +350,8 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 for (int kt = 0; kt < nk; kt++, it++) {
-                    const int slot = it % I8_STAGES;
-                    mbar_wait(&full_bar[slot], (it / I8_STAGES) & 1);
+                    const int slot = it % NSTAGE;
+                    mbar_wait(&full_bar[slot], (it / NSTAGE) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
                     if (variant != 2 && active) {      // (variant 2: timing experiment without the MMAs)
@@ -349,8 +359,8 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
                     for (int dd = 0; dd < S; dd++)
 #pragma unroll
                         for (int s2 = 0; s2 <= dd; s2++)
-                            umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
-                                    db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), I8_IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
+                            umma_i8(tmem + dd * BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                    db + (uint64_t)(((dd - s2) * B_PLANE) >> 4), IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
                     }
                     // frees the stage (in both CTAs of a pair) when the MMAs above retire
                     if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3); else umma_commit(&empty_bar[slot]);
@@ -362,8 +372,10 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .., both 32-column halves =====
-        const int lg = warp & 3;
+        // ===== epilogue warps: TMEM lanes 32 (warp % 4) ..; with EW = 8 warp w and w + 4 share a lane quarter and
+        // split the columns of the tile =====
+        constexpr int NCW = BN / (EW / 4);            // columns drained per warp
+        const int lg = warp & 3, half = (warp - 4) >> 2;
         const int r = lg * 32 + lane;
         int nt = -1;
         for (int t = u0; t < ntiles; t += ustep) {
@@ -371,42 +383,49 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
             if (!locate(t, sb, tm, tn)) continue;
             nt++;
             const SBDesc d = sbd[sb];
-            const int m0 = tm * I8_BM, n0 = tn * I8_BN;
+            const int m0 = tm * I8_BM, n0 = tn * BN;
             const int row = m0 + r;
             const double sa_ = row < d.nsp ? ascale[d.idx_off + row] : 0.0;
             mbar_wait(&accum_full, nt & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (variant == 1) {                        // timing experiment without the epilogue
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
                 if (warp == 4 && lane == 0)
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
                 continue;
             }
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
+            for (int ch = 0; ch < NCW / 16; ch++) {
                 double acc[16];
-                i8_recombine16<S>(tmem + ((uint32_t)(lg * 32) << 16), ch * 16, acc);
+                const int c = half * NCW + ch * 16;
+                i8_recombine16<S, BN>(tmem + ((uint32_t)(lg * 32) << 16), c, acc);
 #pragma unroll
-                for (int j = 0; j < 16; j++) tile[r * I8_EPI_LD + ch * 16 + j] = acc[j] * sa_;
+                for (int j = 0; j < 16; j++) tile[r * EPI_LD + c + j] = acc[j] * sa_;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps: TMEM drained, tile staged
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");    // the epilogue warps: TMEM drained, tile staged
             if (warp == 4 && lane == 0)
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
             const int *ix = idx + d.idx_off;
-            const int c0 = n0 + lane, c1 = n0 + 32 + lane;
-            const int b0 = ix[c0], b1 = ix[c1];
-            const double s0 = bscale[d.idx_off + c0], s1 = bscale[d.idx_off + c1];
-            for (int rr = lg; rr < I8_BM; rr += 4) {
+            int bcol[BN / 32];
+            double bs[BN / 32];
+#pragma unroll
+            for (int cg = 0; cg < BN / 32; cg++) {      // the last N tile of a superblock may reach past nsp (zero planes)
+                const int c = n0 + cg * 32 + lane;
+                bcol[cg] = c < d.nsp ? ix[c] : nao;
+                bs[cg] = c < d.nsp ? bscale[d.idx_off + c] : 0.0;
+            }
+            for (int rr = warp - 4; rr < I8_BM; rr += EW) {
                 const int grow = m0 + rr;
                 if (grow >= d.nsp) break;
                 const int a = ix[grow];
                 if (a >= nao) continue;
                 double *dst = mat + (int64_t)a * nao;
-                if (b0 < nao) atomicAdd(dst + b0, tile[rr * I8_EPI_LD + lane] * s0);
-                if (b1 < nao) atomicAdd(dst + b1, tile[rr * I8_EPI_LD + 32 + lane] * s1);
+#pragma unroll
+                for (int cg = 0; cg < BN / 32; cg++)
+                    if (bcol[cg] < nao) atomicAdd(dst + bcol[cg], tile[rr * EPI_LD + cg * 32 + lane] * bs[cg]);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");    // the staging tile is free again
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");    // the staging tile is free again
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -433,7 +452,7 @@ extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int m
     return 0;
 }
 
-template <int S>
+template <int S, int BN>
 static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
                       const double *weights, const double *vrho, const double *vgrad, double *vb,
                       const int64_t *vb_off, const signed char *aplanes, const int64_t *a_off, const double *ascale,
@@ -454,20 +473,23 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     QC_LAUNCHED(1);
     dim3 gs((unsigned)(max_nsp / 64), (unsigned)nsb);
     prof_begin(PROF_I8_SLICE, st);
-    sb_slice_kernel<S, I8_BN><<<gs, 256, 0, st>>>(sbd, vb, vb_off, 0, sbp, b_off, bplanes, bscale);
+    sb_slice_kernel<S, BN><<<gs, 256, 0, st>>>(sbd, vb, vb_off, 0, sbp, b_off, bplanes, bscale);
     prof_end(st);
     QC_LAUNCHED(1);
-    const size_t smem = (size_t)I8_STAGES * S * (I8_A_PLANE + I8_B_PLANE) + sizeof(double) * I8_BM * I8_EPI_LD;
+    constexpr int NSTAGE = (BN == 96) ? 3 : I8_STAGES;
+    const size_t smem = (size_t)NSTAGE * S * (I8_A_PLANE + I8_KT * BN) + sizeof(double) * I8_BM * (BN + 1);
     prof_begin(PROF_VXC_GEMM, st);
-    if ((g_i8_mode & 2) && ptile_off != nullptr) {
-        QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        QC_CHECK(launch_cluster2(vxc_i8_gemm_kernel<S, 1>, NUM_SMS, I8_THREADS, smem, st, sbd, ptile_off, nsb, nptiles, idx,
+    if ((g_i8_mode & 2) && ptile_off != nullptr && BN == 64) {
+        QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S, 1, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QC_CHECK(launch_cluster2(vxc_i8_gemm_kernel<S, 1, 64, 4>, NUM_SMS, I8_THREADS, smem, st, sbd, ptile_off, nsb, nptiles, idx,
                                  aplanes, a_off, (const signed char *)bplanes, b_off, ascale, (const double *)bscale, sbp, nao,
                                  mat, g_i8_variant));
     } else {
-        QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        vxc_i8_gemm_kernel<S, 0><<<NUM_SMS, I8_THREADS, smem, st>>>(sbd, tile_off, nsb, ntiles, idx, aplanes, a_off, bplanes,
-                                                                  b_off, ascale, bscale, sbp, nao, mat, g_i8_variant);
+        constexpr int EW = (BN == 96) ? 8 : 4;
+        QC_CHECK(cudaFuncSetAttribute(vxc_i8_gemm_kernel<S, 0, BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vxc_i8_gemm_kernel<S, 0, BN, EW><<<NUM_SMS, 128 + 32 * EW, smem, st>>>(sbd, tile_off, nsb, ntiles, idx, aplanes, a_off,
+                                                                             bplanes, b_off, ascale, bscale, sbp, nao, mat,
+                                                                             g_i8_variant);
     }
     prof_end(st);
     QC_LAUNCHED(1);
@@ -475,24 +497,29 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
 }
 
 // Same contract as b200qc_vxc_sb, with the GEMM on tcgen05 int8 slices.  aplanes / a_off / ascale come from
-// b200qc_vxc_i8_prepare; bplanes (nslice * sum_sb sbp * nsp bytes at b_off[sb]) and bscale (sum_sb nsp) are scratch;
-// tile_off[sb] = exclusive prefix of ceil(nsp / 128) * (nsp / 64) (device int32), ntiles = its total.
+// b200qc_vxc_i8_prepare; bplanes (nslice * sum_sb sbp * ceil(nsp / bn) * bn bytes at b_off[sb], ZERO-FILLED once by the
+// caller: the columns past nsp of a last N tile are never written) and bscale (sum_sb nsp) are scratch;
+// tile_off[sb] = exclusive prefix of ceil(nsp / 128) * ceil(nsp / bn) (device int32), ntiles = its total.
 extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
                                 const double *ao, const double *weights, const double *vrho, const double *vgrad,
                                 int nao, const int64_t *vb_off, double *vb, const signed char *aplanes,
                                 const int64_t *a_off, const double *ascale, signed char *bplanes,
-                                const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
+                                const int64_t *b_off, double *bscale, int bn, const int *tile_off, int ntiles,
                                 const int *ptile_off, int nptiles, double *mat, void *stream) {
     QC_REQUIRE(sbp % I8_KT == 0 && sbp % I8_BM == 0, "superblock size must be a multiple of 128");
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE(bn == 64 || (bn == 96 && nslice == 5), "N tile: 64, or 96 with 5 slices");
     QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
     cudaStream_t st = as_stream(stream);
     QC_CHECK(cudaMemsetAsync(mat, 0, sizeof(double) * nao * nao, st));
     if (nsb == 0) return 0;
     const SBDesc *sbd = (const SBDesc *)sbdesc;
+    if (nslice == 5 && bn == 96)
+        return vxc_i8_run<5, 96>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+                                 bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
     if (nslice == 5)
-        return vxc_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+        return vxc_i8_run<5, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+                                 bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
+    return vxc_i8_run<6, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
                              bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
-    return vxc_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
-                         bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
 }

@@ -16,7 +16,9 @@ class _Config:
     # grid points per superblock of the block-sparse XC path (multiple of 128)
     SB_POINTS: int = int(os.environ.get("B200QC_SB_POINTS", "512"))
     # Vxc GEMM on tcgen05 as an error-free sliced int8 product: 0 = off (fp64 DMMA), 5 or 6 = number of slices
-    VXC_I8_SLICES: int = int(os.environ.get("B200QC_VXC_I8", "6"))
+    VXC_I8_SLICES: int = int(os.environ.get("B200QC_VXC_I8", "5"))
+    # N tile of that GEMM: 96 (only with 5 slices) or 64
+    VXC_I8_BN: int = int(os.environ.get("B200QC_VXC_I8_BN", "96"))
     # density GEMM (K2) on tcgen05 the same way: 0 = off (fp64 DMMA), 5 or 6 slices
     RHO_I8_SLICES: int = int(os.environ.get("B200QC_RHO_I8", "6"))
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))

@@ -124,14 +124,16 @@ int b200qc_vxc_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *
  * values once into the tiled operand order: aplanes = sum_sb nslice * sbp * ceil(nsp / 128) * 128 bytes
  * (zero-filled by the caller) at a_off[sb], ascale = sum_sb nsp doubles.  bplanes (sum_sb nslice * sbp * nsp
  * bytes at b_off[sb]) and bscale are per-call scratch; tile_off[sb] = exclusive prefix (device int32) of the
- * ceil(nsp / 128) * (nsp / 64) output tiles per superblock, ntiles their total (the GEMM is one persistent
- * CTA per SM walking that list). */
+ * ceil(nsp / 128) * ceil(nsp / bn) output tiles per superblock, ntiles their total (the GEMM is one persistent
+ * CTA per SM walking that list).  bn = N tile: 64, or 96 with nslice = 5 (tcgen05.mma re-reads both operands from
+ * shared memory per instruction: the wider tile with one slice less moves 42 % fewer bytes per unit of work);
+ * bplanes then holds nslice * sbp * ceil(nsp / bn) * bn bytes per superblock, zero-filled once by the caller. */
 int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const double *ao,
                           const int64_t *a_off, signed char *aplanes, double *ascale, void *stream);
 int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx, const double *ao,
                      const double *weights, const double *vrho, const double *vgrad, int nao, const int64_t *vb_off,
                      double *vb, const signed char *aplanes, const int64_t *a_off, const double *ascale,
-                     signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
+                     signed char *bplanes, const int64_t *b_off, double *bscale, int bn, const int *tile_off, int ntiles,
                      const int *ptile_off, int nptiles, double *mat, void *stream);
 /* Scheduling switches of the tcgen05 kernels (bit mask; default 0): 1 = L2 evict_last hint on the re-used A planes
  * of K2; 2 = K4 in 2-CTA thread-block clusters, every A stage fetched half by each CTA and multicast to both (the
