@@ -170,6 +170,7 @@ i8_slice_dual_kernel(I8Slice2Args a) {
     __syncwarp();
     const double inv = sinv[warp];
     const double *X = a.src + (int64_t)b * a.sb + (int64_t)r * a.sr;
+    const bool aligned4 = ((a.sb | a.sr) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 31) == 0;
     const int nk = a.Kpad / 32;
     const bool wa = r0 < a.RpadA, wb = r0 < a.RpadB;     // 8-row groups never straddle a padded size
     // writer mapping: 8 consecutive lanes = the 8 rows of one 16-column group
@@ -179,15 +180,32 @@ i8_slice_dual_kernel(I8Slice2Args a) {
     signed char *PB = a.planesB + ((int64_t)b * (a.RpadB / 64) + rr / 64) * nk * S * 2048 + ((rr % 64) >> 3) * 128 + (rr & 7) * 16;
     for (int seg = 0; seg * 512 < a.Kpad; seg++) {
         const int k0 = seg * 512;
+        // a lane takes 4 consecutive columns at a time: one 256-bit load (the source rows are 32-byte aligned when sr
+        // and sb are multiples of 4 -- else scalar loads), one 32-bit shared-memory store per slice
 #pragma unroll
-        for (int t = 0; t < 16; t++) {
-            const int k = k0 + t * 32 + lane;
-            double y = (rv && k < Kb) ? __ldcs(X + k) * inv : 0.0;
+        for (int t = 0; t < 4; t++) {
+            const int k = k0 + t * 128 + 4 * lane;
+            double y[4] = {0.0, 0.0, 0.0, 0.0};
+            if (rv && k + 3 < Kb && aligned4) {
+                asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
+                             : "=d"(y[0]), "=d"(y[1]), "=d"(y[2]), "=d"(y[3]) : "l"(X + k));
+            } else if (rv) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (k + j < Kb) y[j] = __ldcs(X + k + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) y[j] *= inv;
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const double q = rint(y);
-                sm[warp][s][t * 32 + lane] = (signed char)(int)q;
-                y = (y - q) * 128.0;
+                unsigned int w = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double q = rint(y[j]);
+                    w |= ((unsigned int)(int)q & 0xffu) << (8 * j);
+                    y[j] = (y[j] - q) * 128.0;
+                }
+                *reinterpret_cast<unsigned int *>(&sm[warp][s][t * 128 + 4 * lane]) = w;
             }
         }
         __syncthreads();

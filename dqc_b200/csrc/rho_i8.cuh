@@ -51,6 +51,8 @@ sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ 
 
 // ---- B operand: D_sb[nu][mu] = D[idx_nu][idx_mu] gathered and sliced, K-major tiles; scale per row nu ----
 // out (per SB, bytes): [n tile = nu / 64][k tile = mu / 32][slice][(mu % 32) / 16][(nu % 64) / 8][nu % 8][mu % 16]
+// (Variants that staged the bytes in shared memory for 16-byte stores, or kept the gathered row in registers between
+// the two passes, measured 2.5 - 3.9 ms against the 2.2 ms of this plain form at C60: the gathers dominate.)
 template <int S>
 __global__ void __launch_bounds__(256)
 sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const double *__restrict__ dm,

@@ -59,17 +59,37 @@ sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, co
     if (rg == 0) scales[d.idx_off + col] = ldexp(1.0, e);
     constexpr int PLANE = I8_KT * W;
     const int nk = sbp / I8_KT;
-    const int tile = col / W, wc = col % W;
-    signed char *P = planes + p_off[blockIdx.y] + (int64_t)tile * nk * S * PLANE + (wc >> 4) * 128 + (wc & 15);
-    for (int r = rg; r < sbp; r += 4) {
-        double y = X[(int64_t)r * ld + col] * inv;
+    // second pass: a thread owns 16 consecutive columns of one row -- 128 contiguous bytes in, one 16-byte store per
+    // slice out (16 columns of a row are contiguous in the MN-major plane).  The 64 column scales sit in smem.
+    __shared__ double sinv[64];
+    if (rg == 0) sinv[threadIdx.x & 63] = inv;
+    __syncthreads();
+    const int cg = threadIdx.x & 3;                          // 16-column group inside the 64-column block
+    const int cq = c0 + cg * 16;                             // first column of the group
+    const int tile = cq / W, wc = cq % W;                    // (W is a multiple of 16: a group never straddles tiles)
+    signed char *P = planes + p_off[blockIdx.y] + (int64_t)tile * nk * S * PLANE + (wc >> 4) * 128;
+    for (int r = threadIdx.x >> 2; r < sbp; r += 64) {
+        const double *src = X + (int64_t)r * ld + cq;
+        unsigned int w[S][4];
+#pragma unroll
+        for (int s = 0; s < S; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(src + j);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double y = (h ? v.y : v.x) * sinv[cg * 16 + j + h];
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    const double q = rint(y);
+                    w[s][(j + h) >> 2] |= ((unsigned int)(int)q & 0xffu) << (8 * ((j + h) & 3));
+                    y = (y - q) * 128.0;
+                }
+            }
+        }
         signed char *Q = P + (int64_t)(r >> 5) * S * PLANE + ((r & 31) >> 3) * (W / 16) * 128 + (r & 7) * 16;
 #pragma unroll
-        for (int s = 0; s < S; s++) {
-            const double q = rint(y);
-            Q[s * PLANE] = (signed char)(int)q;
-            y = (y - q) * 128.0;
-        }
+        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * PLANE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
     }
 }
 
