@@ -82,7 +82,7 @@ _SIGS = {
     "b200qc_rho_sb_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p]),
     "b200qc_int1e": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
@@ -722,10 +722,12 @@ class GridBlocks(object):
         self.rho_i8_slices = int(rho_i8_slices)
         if self.rho_i8_slices and self.nsb:
             S = self.rho_i8_slices
+            self.rho_bn = rbn = 96 if (S == 5 and _cfg.RHO_I8_BN == 96) else 64
+            rb_bytes = S * nsp * ((nsp + rbn - 1) // rbn * rbn)      # B operand: whole N tiles (zero padding)
             self.d_ra_off = tt(excl(S * self.sbp * nsp), torch.int64)
-            self.d_rb_off = tt(excl(S * nsp * nsp), torch.int64)
+            self.d_rb_off = tt(excl(rb_bytes), torch.int64)
             self.r_aplanes = torch.empty(int((S * self.sbp * nsp).sum()), dtype=torch.int8, device=dev)
-            self.r_bplanes = torch.empty(int((S * nsp * nsp).sum()), dtype=torch.int8, device=dev)
+            self.r_bplanes = torch.zeros(int(rb_bytes.sum()), dtype=torch.int8, device=dev)
             self.r_rscale = torch.empty(self.nsb * self.sbp, dtype=torch.float64, device=dev)
             self.r_cscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
             _check(lib.b200qc_rho_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, S, _ptr(self.ao),
@@ -742,8 +744,8 @@ class GridBlocks(object):
             _check(lib.b200qc_rho_sb_i8(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.rho_i8_slices,
                                         _ptr(self.d_idx), _ptr(self.ao), _ptr(dm.contiguous()), self.nao,
                                         _ptr(self.r_aplanes), _ptr(self.d_ra_off), _ptr(self.r_rscale),
-                                        _ptr(self.r_bplanes), _ptr(self.d_rb_off), _ptr(self.r_cscale), _ptr(r), _ptr(g),
-                                        _stream()), "rho_sb_i8")
+                                        _ptr(self.r_bplanes), _ptr(self.d_rb_off), _ptr(self.r_cscale), self.rho_bn,
+                                        _ptr(r), _ptr(g), _stream()), "rho_sb_i8")
             return r, g
         _check(lib.b200qc_rho_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
                                  _ptr(dm.contiguous()), self.nao, _ptr(self.dsb), _ptr(r), _ptr(g), _stream()), "rho_sb")

@@ -53,7 +53,7 @@ sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ 
 // out (per SB, bytes): [n tile = nu / 64][k tile = mu / 32][slice][(mu % 32) / 16][(nu % 64) / 8][nu % 8][mu % 16]
 // (Variants that staged the bytes in shared memory for 16-byte stores, or kept the gathered row in registers between
 // the two passes, measured 2.5 - 3.9 ms against the 2.2 ms of this plain form at C60: the gathers dominate.)
-template <int S>
+template <int S, int BN>
 __global__ void __launch_bounds__(256)
 sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const double *__restrict__ dm,
                           int nao, const int64_t *__restrict__ p_off, signed char *__restrict__ planes,
@@ -78,15 +78,16 @@ sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict_
     const double inv = ldexp(64.0, -e);
     if (lane == 0) cscale[d.idx_off + nu] = ldexp(1.0, e);
     const int nkt = d.nsp / I8_KT;
-    signed char *P = planes + p_off[sb] + (int64_t)(nu >> 6) * nkt * S * I8_B_PLANE + ((nu & 63) >> 3) * 128 + (nu & 7) * 16;
+    constexpr int B_PLANE = I8_KT * BN;      // N tiles of BN rows (the last one zero-padded by the caller's memset)
+    signed char *P = planes + p_off[sb] + (int64_t)(nu / BN) * nkt * S * B_PLANE + ((nu % BN) >> 3) * 128 + (nu & 7) * 16;
     for (int c = lane; c < d.nsp; c += 32) {
         const int b = ix[c];
         double y = (a < nao && b < nao) ? row[b] * inv : 0.0;
-        signed char *Q = P + (int64_t)(c >> 5) * S * I8_B_PLANE + ((c & 31) >> 4) * 1024 + (c & 15);
+        signed char *Q = P + (int64_t)(c >> 5) * S * B_PLANE + ((c & 31) >> 4) * (BN * 16) + (c & 15);
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const double q = rint(y);
-            Q[s * I8_B_PLANE] = (signed char)(int)q;
+            Q[s * B_PLANE] = (signed char)(int)q;
             y = (y - q) * 128.0;
         }
     }
@@ -105,7 +106,9 @@ __device__ __forceinline__ void ldcs_f64x4(const double *p, double &a, double &b
 
 // EH = number of column halves the epilogue splits an N tile into (1: 4 epilogue warps x 64 columns,
 // 2: 8 warps x 32 columns); the CTA has 128 + 128 EH threads.
-template <int S, int NCOMP, int MC, int EH>
+// BN = N tile: 64, or 96 with S = 5 and EH = 2 (480 TMEM columns): the A tile of a unit is then streamed
+// ceil(nsp / 96) instead of nsp / 64 times -- a third less of the HBM traffic that bounds this kernel.
+template <int S, int NCOMP, int MC, int EH, int BN>
 __global__ void __launch_bounds__(128 + 128 * EH, 1)
 rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__restrict__ ao,
               const signed char *__restrict__ aplanes, const int64_t *__restrict__ a_off,
@@ -114,7 +117,11 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
               double *__restrict__ rho, double *__restrict__ grad, int l2hint) {
     // (l2hint: bit 0 = L2 evict_last on the A planes; bits 8.. = timing-experiment variant)
     extern __shared__ __align__(1024) unsigned char i8_smem[];
-    constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * I8_B_PLANE, STAGE = A_STAGE + B_STAGE;
+    static_assert(S * BN <= 512 && BN % (8 * EH) == 0, "accumulators exceed the tensor memory");
+    constexpr int B_PLANE = I8_KT * BN;
+    constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * B_PLANE, STAGE = A_STAGE + B_STAGE;
+    // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = BN, M = 128
+    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
     __shared__ uint64_t full_bar[RI8_STAGES], empty_bar[RI8_STAGES], accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
     __shared__ double comb[I8_BM][NCOMP];     // row sums of the second column half, handed to the first
@@ -155,7 +162,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
             const uint64_t pol = l2_policy_evict_last();
             for (int u = u0; u < nunits; u += ustep) {
                 const int sb = u / mtiles, mt = u - sb * mtiles;
-                const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = nsp / I8_BN;
+                const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = (nsp + BN - 1) / BN;
                 const signed char *A = aplanes + a_off[sb] + (int64_t)mt * nkt * A_STAGE;
                 const signed char *B = bplanes + b_off[sb];
                 for (int t0 = 0; t0 < ntn; t0 += tstep) {
@@ -188,11 +195,11 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
         if (lane == 0) {
             // K-major, no swizzle: LBO = stride between the two 16-byte K chunks of a K = 32 step
             // (A: 2048 B, B: 1024 B), SBO = stride between 8-row groups (128 B)
-            const uint64_t da0 = umma_desc(sbase, 2048, 128), db0 = umma_desc(sbase + A_STAGE, 1024, 128);
+            const uint64_t da0 = umma_desc(sbase, 2048, 128), db0 = umma_desc(sbase + A_STAGE, BN * 16, 128);
             int it = 0, nt = 0;
             for (int u = u0; u < nunits; u += ustep) {
                 const int sb = u / mtiles;
-                const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = nsp / I8_BN;
+                const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = (nsp + BN - 1) / BN;
                 for (int t0 = 0; t0 < ntn; t0 += tstep) {
                     const bool active = t0 + crank < ntn;
                     if (active) {
@@ -209,8 +216,8 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                             for (int dd = 0; dd < S; dd++)
 #pragma unroll
                                 for (int s2 = 0; s2 <= dd; s2++)
-                                    umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
-                                            db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), RI8_IDESC,
+                                    umma_i8(tmem + dd * BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                            db + (uint64_t)(((dd - s2) * B_PLANE) >> 4), IDESC,
                                             (kt > 0 || s2 > 0) ? 1u : 0u);
                         }
                         if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3); else umma_commit(&empty_bar[slot]);
@@ -225,7 +232,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps; thread = grid row (TMEM lane quarter = warp % 4) x one 32-column half of the N tile.
         // The dot products stream the fp64 AO values straight from HBM: twice the warps = twice the loads in flight.
-        constexpr int NC = I8_BN / EH;          // columns of the N tile per thread
+        constexpr int NC = BN / EH;             // columns of the N tile per thread
         const int lg = warp & 3, half = (warp - 4) >> 2;
         const int r = lg * 32 + lane;
         const int c0 = half * NC;
@@ -233,7 +240,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
         for (int u = u0; u < nunits; u += ustep) {
             const int sb = u / mtiles, mt = u - sb * mtiles;
             const SBDesc d = sbd[sb];
-            const int ntn = d.nsp / I8_BN;
+            const int ntn = (d.nsp + BN - 1) / BN;
             const int64_t ld = d.nsp;
             const int grow = mt * I8_BM + r;                             // row inside the superblock
             const double *phi = ao + d.ao_off + (int64_t)grow * ld;      // component 0, this row
@@ -241,13 +248,16 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
 #pragma unroll
             for (int c = 0; c < NCOMP; c++) part[c] = 0.0;
             for (int tn = crank; tn < ntn; tn += tstep, nt++) {
+                // columns of this thread that exist (the last N tile may reach past nsp; multiples of 16)
+                const int nvalid = min(NC, d.nsp - (tn * BN + c0));
                 // the AO values this thread will need for the tile: pull them into L2 while the MMAs still run
                 if (variant != 1 && variant != 3) {
 #pragma unroll
                     for (int c = 0; c < NCOMP; c++)
 #pragma unroll
                         for (int j = 0; j < NC; j += 16)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(phi + (int64_t)c * sbp * ld + tn * I8_BN + c0 + j));
+                            if (j < nvalid)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(phi + (int64_t)c * sbp * ld + tn * BN + c0 + j));
                 }
                 mbar_wait(&accum_full, nt & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -259,7 +269,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
 #pragma unroll
                     for (int ch = 0; ch < NC / 8; ch++) {
                         double acc[8];
-                        i8_recombine8<S>(tmem + ((uint32_t)(lg * 32) << 16), I8_BN, c0 + ch * 8, acc);
+                        i8_recombine8<S>(tmem + ((uint32_t)(lg * 32) << 16), BN, c0 + ch * 8, acc);
 #pragma unroll
                         for (int j = 0; j < 8; j++) x[ch * 8 + j] = acc[j];
                     }
@@ -269,7 +279,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                 if (warp == 4 && lane == 0)
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
                 // column scales, then the row dots with the fp64 AO values of this row
-                const int n0 = tn * I8_BN + c0;
+                const int n0 = tn * BN + c0;
                 const double *cs = cscale + d.idx_off + n0;
                 if (variant == 1 || variant == 3) {
 #pragma unroll
@@ -278,9 +288,11 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                 }
 #pragma unroll
                 for (int j = 0; j < NC; j += 2) {
-                    const double2 s2 = *reinterpret_cast<const double2 *>(cs + j);
-                    x[j] *= s2.x;
-                    x[j + 1] *= s2.y;
+                    if (j < nvalid) {
+                        const double2 s2 = *reinterpret_cast<const double2 *>(cs + j);
+                        x[j] *= s2.x;
+                        x[j + 1] *= s2.y;
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < NCOMP; c++) {
@@ -289,9 +301,11 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
 #pragma unroll
                     for (int j = 0; j < NC; j += 4) {
                         // streaming, zero-reuse 256-bit reads (kept from evicting the re-used int8 planes from L2)
-                        double v0, v1, v2, v3;
-                        ldcs_f64x4(row + j, v0, v1, v2, v3);
-                        s += x[j] * v0 + x[j + 1] * v1 + x[j + 2] * v2 + x[j + 3] * v3;
+                        if (j < nvalid) {
+                            double v0, v1, v2, v3;
+                            ldcs_f64x4(row + j, v0, v1, v2, v3);
+                            s += x[j] * v0 + x[j + 1] * v1 + x[j + 2] * v2 + x[j + 3] * v3;
+                        }
                     }
                     part[c] += s;
                 }
@@ -349,19 +363,19 @@ extern "C" int b200qc_rho_i8_prepare(const void *sbdesc, int nsb, int sbp, int n
     return 0;
 }
 
-template <int S>
+template <int S, int BN>
 static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
                       const double *dm, int nao, const signed char *aplanes, const int64_t *a_off,
                       const double *rscale, signed char *bplanes, const int64_t *b_off, double *cscale, double *rho,
                       double *grad, cudaStream_t st) {
     dim3 gg((unsigned)(max_nsp / 8), (unsigned)nsb);
     prof_begin(PROF_SB_GATHER, st);
-    sb_gather_slice_dm_kernel<S><<<gg, 256, 0, st>>>(sbd, idx, dm, nao, b_off, bplanes, cscale);
+    sb_gather_slice_dm_kernel<S, BN><<<gg, 256, 0, st>>>(sbd, idx, dm, nao, b_off, bplanes, cscale);
     prof_end(st);
     QC_LAUNCHED(1);
-    const size_t smem = (size_t)RI8_STAGES * S * (I8_A_PLANE + I8_B_PLANE);
+    const size_t smem = (size_t)RI8_STAGES * S * (I8_A_PLANE + I8_KT * BN);
     const int64_t ngl = (int64_t)nsb * sbp;
-    const bool mc = (g_i8_mode & 4) != 0;
+    const bool mc = (g_i8_mode & 4) != 0 && BN == 64;
     const int l2hint = (g_i8_mode & 1) | (g_i8_variant << 8);
     if (mc) {   // partial row sums of the two CTAs of a pair are added atomically
         QC_CHECK(cudaMemsetAsync(rho, 0, sizeof(double) * ngl, st));
@@ -370,23 +384,25 @@ static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     prof_begin(PROF_RHO, st);
 #define RHO_I8_LAUNCH(NCOMP_, MC_, EH_)                                                                                      \
     do {                                                                                                                    \
-        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, NCOMP_, MC_, EH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, NCOMP_, MC_, EH_, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                       (int)smem));                                                                          \
         if (MC_)                                                                                                            \
-            QC_CHECK(launch_cluster2(rho_i8_kernel<S, NCOMP_, MC_, EH_>, NUM_SMS, 128 + 128 * EH_, smem, st, sbd, nsb, sbp, ao, \
+            QC_CHECK(launch_cluster2(rho_i8_kernel<S, NCOMP_, MC_, EH_, BN>, NUM_SMS, 128 + 128 * EH_, smem, st, sbd, nsb, sbp, ao, \
                                      aplanes, a_off, (const signed char *)bplanes, b_off, rscale, (const double *)cscale,   \
                                      ngl, rho, grad, l2hint));                                                              \
         else                                                                                                                \
-            rho_i8_kernel<S, NCOMP_, MC_, EH_><<<NUM_SMS, 128 + 128 * EH_, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off,     \
+            rho_i8_kernel<S, NCOMP_, MC_, EH_, BN><<<NUM_SMS, 128 + 128 * EH_, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off,     \
                                                                                      bplanes, b_off, rscale, cscale, ngl,   \
                                                                                      rho, grad, l2hint);                    \
     } while (0)
     // EH = 1: four epilogue warps.  (Eight warps x 32 columns measured the same 8.5 ms at C60 once the AO rows
     // are prefetched into L2 and read with 256-bit loads, so the smaller CTA is used.)
+    // (BN = 96: 48 columns per thread need the eight-warp epilogue.)
+    constexpr int EHB = (BN == 96) ? 2 : 1;
     if (grad) {
-        if (mc) RHO_I8_LAUNCH(4, 1, 1); else RHO_I8_LAUNCH(4, 0, 1);
+        if (mc) RHO_I8_LAUNCH(4, (BN == 64 ? 1 : 0), 1); else RHO_I8_LAUNCH(4, 0, EHB);
     } else {
-        if (mc) RHO_I8_LAUNCH(1, 1, 1); else RHO_I8_LAUNCH(1, 0, 1);
+        if (mc) RHO_I8_LAUNCH(1, (BN == 64 ? 1 : 0), 1); else RHO_I8_LAUNCH(1, 0, EHB);
     }
 #undef RHO_I8_LAUNCH
     prof_end(st);
@@ -394,19 +410,23 @@ static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     return 0;
 }
 
-// Same contract as b200qc_rho_sb with the GEMM on tcgen05 int8 slices.  bplanes (sum_sb nslice * nsp^2 bytes at
-// b_off[sb]) and cscale (sum_sb nsp doubles) are per-call scratch.
+// Same contract as b200qc_rho_sb with the GEMM on tcgen05 int8 slices.  bplanes (sum_sb nslice * nsp * ceil(nsp / bn) * bn
+// bytes at b_off[sb], ZERO-FILLED once by the caller: the rows past nsp of a last N tile are never written) and
+// cscale (sum_sb nsp doubles) are per-call scratch.  bn = N tile: 64, or 96 with nslice = 5.
 extern "C" int b200qc_rho_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
                                 const double *ao, const double *dm, int nao, const signed char *aplanes,
                                 const int64_t *a_off, const double *rscale, signed char *bplanes,
-                                const int64_t *b_off, double *cscale, double *rho, double *grad, void *stream) {
+                                const int64_t *b_off, double *cscale, int bn, double *rho, double *grad, void *stream) {
     QC_REQUIRE(sbp % I8_BM == 0, "superblock size must be a multiple of 128");
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE(bn == 64 || (bn == 96 && nslice == 5), "N tile: 64, or 96 with 5 slices");
     QC_REQUIRE((int64_t)max_nsp * 6 * 4096 < (1LL << 31), "too many AOs per superblock for exact int32 accumulation");
     if (nsb == 0) return 0;
     const SBDesc *sbd = (const SBDesc *)sbdesc;
     cudaStream_t st = as_stream(stream);
+    if (nslice == 5 && bn == 96)
+        return rho_i8_run<5, 96>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
     if (nslice == 5)
-        return rho_i8_run<5>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
-    return rho_i8_run<6>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
+        return rho_i8_run<5, 64>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
+    return rho_i8_run<6, 64>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
 }

@@ -21,6 +21,8 @@ class _Config:
     VXC_I8_BN: int = int(os.environ.get("B200QC_VXC_I8_BN", "96"))
     # density GEMM (K2) on tcgen05 the same way: 0 = off (fp64 DMMA), 5 or 6 slices
     RHO_I8_SLICES: int = int(os.environ.get("B200QC_RHO_I8", "5"))
+    # N tile of that GEMM: 64, or 96 (only with 5 slices)
+    RHO_I8_BN: int = int(os.environ.get("B200QC_RHO_I8_BN", "64"))
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
     # scheduling of the tcgen05 XC kernels (bit mask): 1 = L2 evict_last hint on the K2 A planes, 2 = K4 in 2-CTA
     # clusters with multicast A stages, 4 = K2 in 2-CTA clusters

@@ -148,14 +148,15 @@ int b200qc_i8_debug_variant(int v);
 /* K2 on tcgen05: the same contraction as b200qc_rho_sb with X = phi D as an error-free sliced int8 GEMM
  * (both operands K-major, int32 accumulators in TMEM) and the row dots with phi / grad phi fused into the
  * epilogue.  prepare slices the static AO values row-wise once: aplanes = sum_sb nslice * sbp * nsp bytes at
- * a_off[sb], rscale = nsb * sbp doubles.  bplanes (sum_sb nslice * nsp^2 bytes at b_off[sb]) and cscale
- * (sum_sb nsp doubles) are per-call scratch for the gathered, sliced density. */
+ * a_off[sb], rscale = nsb * sbp doubles.  bplanes (sum_sb nslice * nsp * ceil(nsp / bn) * bn bytes at b_off[sb],
+ * zero-filled once by the caller) and cscale (sum_sb nsp doubles) are per-call scratch for the gathered, sliced
+ * density.  bn = N tile: 64, or 96 with nslice = 5 (the A tile of a unit is streamed once per N tile). */
 int b200qc_rho_i8_prepare(const void *sbdesc, int nsb, int sbp, int nslice, const double *ao, const int64_t *a_off,
                           signed char *aplanes, double *rscale, void *stream);
 int b200qc_rho_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx, const double *ao,
                      const double *dm, int nao, const signed char *aplanes, const int64_t *a_off,
-                     const double *rscale, signed char *bplanes, const int64_t *b_off, double *cscale, double *rho,
-                     double *grad, void *stream);
+                     const double *rscale, signed char *bplanes, const int64_t *b_off, double *cscale, int bn,
+                     double *rho, double *grad, void *stream);
 
 /* ---- one- and two-electron integrals (Rys quadrature) ---------------------------------- */
 /* kind: 0 int1e_ovlp, 1 int1e_kin, 2 int1e_nuc, 3 int1e_rinv (origin rinv_orig[3], host).
