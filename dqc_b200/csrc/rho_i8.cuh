@@ -108,7 +108,10 @@ __device__ __forceinline__ void ldcs_f64x4(const double *p, double &a, double &b
 // 2: 8 warps x 32 columns); the CTA has 128 + 128 EH threads.
 // BN = N tile: 64, or 96 with S = 5 and EH = 2 (480 TMEM columns): the A tile of a unit is then streamed
 // ceil(nsp / 96) instead of nsp / 64 times -- a third less of the HBM traffic that bounds this kernel.
-template <int S, int NCOMP, int MC, int EH, int BN>
+// NCACHE > 0 (MC = 0 only): the first NCACHE K steps of the unit's A tile are fetched once, with the first N tile,
+// into a shared-memory region behind a 4-stage ring and reused by the other N tiles -- the A tile is what this
+// kernel re-reads from HBM (it does not survive in L2 between N tiles).
+template <int S, int NCOMP, int MC, int EH, int BN, int NCACHE>
 __global__ void __launch_bounds__(128 + 128 * EH, 1)
 rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__restrict__ ao,
               const signed char *__restrict__ aplanes, const int64_t *__restrict__ a_off,
@@ -122,7 +125,10 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
     constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * B_PLANE, STAGE = A_STAGE + B_STAGE;
     // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = BN, M = 128
     constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
-    __shared__ uint64_t full_bar[RI8_STAGES], empty_bar[RI8_STAGES], accum_full, accum_empty;
+    // ring depth (run-time, 2..8): what the ring does not take of the 228 KB stays L1 cache for the epilogue's AO reads
+    const int NST = NCACHE ? 4 : ((l2hint >> 16) & 15);
+    static_assert(NCACHE == 0 || MC == 0, "the A cache is not combined with the multicast pairs");
+    __shared__ uint64_t full_bar[8], empty_bar[8], accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
     __shared__ double comb[I8_BM][NCOMP];     // row sums of the second column half, handed to the first
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -133,7 +139,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
     constexpr int A_HALF = A_STAGE / 2;
 
     if (tid == 0) {
-        for (int i = 0; i < RI8_STAGES; i++) {
+        for (int i = 0; i < NST; i++) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], MC ? 2 : 1);
         }
@@ -151,8 +157,12 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_smem;
     const uint32_t sbase = smem_u32(i8_smem);
+    const uint32_t cbase = sbase + NST * STAGE;      // A cache (NCACHE x A_STAGE bytes), behind the ring
     const int tstep = MC ? 2 : 1;        // N tiles per step of the (pair of) CTA(s)
-    const int variant = l2hint >> 8;     // timing experiments (b200qc_i8_debug_variant): 1 no AO loads, 2 no MMAs, 3 no epilogue work
+    // K steps of a unit served from the cache.  A cache slot is rewritten by the first N tile of the next unit, nkt
+    // stages after its last reader: the ring's empty barrier (NST stages back) covers that only if nkt >= NST.
+    auto ncached = [&](int nkt) { return (NCACHE && nkt >= NST) ? min(NCACHE, nkt) : 0; };
+    const int variant = (l2hint >> 8) & 255;     // timing experiments (b200qc_i8_debug_variant): 1 no AO loads, 2 no MMAs, 3 no epilogue work
     l2hint &= 1;
 
     if (warp == 0) {
@@ -165,13 +175,24 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                 const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = (nsp + BN - 1) / BN;
                 const signed char *A = aplanes + a_off[sb] + (int64_t)mt * nkt * A_STAGE;
                 const signed char *B = bplanes + b_off[sb];
+                const int nc = ncached(nkt);
                 for (int t0 = 0; t0 < ntn; t0 += tstep) {
                     const int tn = t0 + crank;
                     const bool active = tn < ntn;
                     for (int kt = 0; kt < nkt; kt++, it++) {
-                        const int slot = it % RI8_STAGES;
-                        mbar_wait(&empty_bar[slot], ((it / RI8_STAGES) & 1) ^ 1);
-                        if (MC) {
+                        const int slot = it % NST;
+                        mbar_wait(&empty_bar[slot], ((it / NST) & 1) ^ 1);
+                        if (NCACHE && kt < nc) {
+                            // cached K step: the A stage travels only with the first N tile, into the cache
+                            if (t0 == 0) {
+                                mbar_expect_tx(&full_bar[slot], STAGE);
+                                bulk_g2s(cbase + kt * A_STAGE, A + (int64_t)kt * A_STAGE, A_STAGE, &full_bar[slot]);
+                            } else {
+                                mbar_expect_tx(&full_bar[slot], B_STAGE);
+                            }
+                            bulk_g2s(sbase + slot * STAGE + A_STAGE, B + ((int64_t)tn * nkt + kt) * B_STAGE, B_STAGE,
+                                     &full_bar[slot]);
+                        } else if (MC) {
                             mbar_expect_tx(&full_bar[slot], A_STAGE + (active ? B_STAGE : 0));
                             bulk_g2s_mc(sbase + slot * STAGE + crank * A_HALF, A + (int64_t)kt * A_STAGE + crank * A_HALF,
                                         A_HALF, &full_bar[slot], (uint16_t)3);
@@ -200,6 +221,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
             for (int u = u0; u < nunits; u += ustep) {
                 const int sb = u / mtiles;
                 const int nsp = sbd[sb].nsp, nkt = nsp / I8_KT, ntn = (nsp + BN - 1) / BN;
+                const int nc = ncached(nkt);
                 for (int t0 = 0; t0 < ntn; t0 += tstep) {
                     const bool active = t0 + crank < ntn;
                     if (active) {
@@ -207,10 +229,12 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     for (int kt = 0; kt < nkt; kt++, it++) {
-                        const int slot = it % RI8_STAGES;
-                        mbar_wait(&full_bar[slot], (it / RI8_STAGES) & 1);
+                        const int slot = it % NST;
+                        mbar_wait(&full_bar[slot], (it / NST) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
+                        const uint64_t db = db0 + (uint64_t)((slot * STAGE) >> 4);
+                        const uint64_t da = (NCACHE && kt < nc) ? umma_desc(cbase + kt * A_STAGE, 2048, 128)
+                                                                : da0 + (uint64_t)((slot * STAGE) >> 4);
                         if (active && variant != 2) {
 #pragma unroll
                             for (int dd = 0; dd < S; dd++)
@@ -373,25 +397,33 @@ static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     sb_gather_slice_dm_kernel<S, BN><<<gg, 256, 0, st>>>(sbd, idx, dm, nao, b_off, bplanes, cscale);
     prof_end(st);
     QC_LAUNCHED(1);
-    const size_t smem = (size_t)RI8_STAGES * S * (I8_A_PLANE + I8_KT * BN);
+    // mode bit 16: A cache (4-stage ring + 5 (S = 5) or 3 (S = 6) cached K steps of the A tile), 128 x 64 tiles only
+    constexpr int NCA = (BN == 64) ? (S == 5 ? 5 : 3) : 0;
+    const bool acache = (g_i8_mode & 16) != 0 && NCA > 0 && (g_i8_mode & 4) == 0;
+    // ring depth: B200QC_I8_MODE bits 8..11 when set (experiments), else 5 stages
+    int nst = (g_i8_mode >> 8) & 15;
+    if (nst < 2 || nst > 8 || (size_t)nst * S * (I8_A_PLANE + I8_KT * BN) > 227 * 1024 - 2048) nst = RI8_STAGES;
+    const size_t smem = acache ? (size_t)4 * S * (I8_A_PLANE + I8_KT * BN) + (size_t)NCA * S * I8_A_PLANE
+                               : (size_t)nst * S * (I8_A_PLANE + I8_KT * BN);
     const int64_t ngl = (int64_t)nsb * sbp;
     const bool mc = (g_i8_mode & 4) != 0 && BN == 64;
-    const int l2hint = (g_i8_mode & 1) | (g_i8_variant << 8);
+    const int l2hint = (g_i8_mode & 1) | ((g_i8_variant & 255) << 8) | (nst << 16);
     if (mc) {   // partial row sums of the two CTAs of a pair are added atomically
         QC_CHECK(cudaMemsetAsync(rho, 0, sizeof(double) * ngl, st));
         if (grad) QC_CHECK(cudaMemsetAsync(grad, 0, sizeof(double) * 3 * ngl, st));
     }
     prof_begin(PROF_RHO, st);
-#define RHO_I8_LAUNCH(NCOMP_, MC_, EH_)                                                                                      \
+#define RHO_I8_LAUNCH(NCOMP_, MC_, EH_) RHO_I8_LAUNCH_C(NCOMP_, MC_, EH_, 0)
+#define RHO_I8_LAUNCH_C(NCOMP_, MC_, EH_, NC_)                                                                               \
     do {                                                                                                                    \
-        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, NCOMP_, MC_, EH_, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+        QC_CHECK(cudaFuncSetAttribute(rho_i8_kernel<S, NCOMP_, MC_, EH_, BN, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)smem));                                                                          \
         if (MC_)                                                                                                            \
-            QC_CHECK(launch_cluster2(rho_i8_kernel<S, NCOMP_, MC_, EH_, BN>, NUM_SMS, 128 + 128 * EH_, smem, st, sbd, nsb, sbp, ao, \
+            QC_CHECK(launch_cluster2(rho_i8_kernel<S, NCOMP_, MC_, EH_, BN, NC_>, NUM_SMS, 128 + 128 * EH_, smem, st, sbd, nsb, sbp, ao, \
                                      aplanes, a_off, (const signed char *)bplanes, b_off, rscale, (const double *)cscale,   \
                                      ngl, rho, grad, l2hint));                                                              \
         else                                                                                                                \
-            rho_i8_kernel<S, NCOMP_, MC_, EH_, BN><<<NUM_SMS, 128 + 128 * EH_, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off,     \
+            rho_i8_kernel<S, NCOMP_, MC_, EH_, BN, NC_><<<NUM_SMS, 128 + 128 * EH_, smem, st>>>(sbd, nsb, sbp, ao, aplanes, a_off, \
                                                                                      bplanes, b_off, rscale, cscale, ngl,   \
                                                                                      rho, grad, l2hint);                    \
     } while (0)
@@ -399,12 +431,15 @@ static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     // are prefetched into L2 and read with 256-bit loads, so the smaller CTA is used.)
     // (BN = 96: 48 columns per thread need the eight-warp epilogue.)
     constexpr int EHB = (BN == 96) ? 2 : 1;
-    if (grad) {
+    if (acache) {
+        if (grad) RHO_I8_LAUNCH_C(4, 0, 1, NCA); else RHO_I8_LAUNCH_C(1, 0, 1, NCA);
+    } else if (grad) {
         if (mc) RHO_I8_LAUNCH(4, (BN == 64 ? 1 : 0), 1); else RHO_I8_LAUNCH(4, 0, EHB);
     } else {
         if (mc) RHO_I8_LAUNCH(1, (BN == 64 ? 1 : 0), 1); else RHO_I8_LAUNCH(1, 0, EHB);
     }
 #undef RHO_I8_LAUNCH
+#undef RHO_I8_LAUNCH_C
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;

@@ -1,6 +1,8 @@
 """Pins the CPU oracle (oracle/) against the golden numbers the reference's own tests hold for the
 Fock-build path.  Every constant below is copied from the cited reference test, nothing else.
 These are CPU tests (-m "not gpu")."""
+import json
+import os
 import numpy as np
 import pytest
 import torch
@@ -8,6 +10,7 @@ from tests import util
 from oracle import fock_ref, scf_ref, xc_ref, cint
 
 dtype = torch.float64
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.json")))
 
 
 def _diatomic(atomzs, dist, basis="3-21g"):
@@ -17,8 +20,7 @@ def _diatomic(atomzs, dist, basis="3-21g"):
 
 
 # dqc/test/test_hf.py:17-31 (RHF/3-21G from PySCF, rtol 1e-7 at :42-45)
-RHF = [([1, 1], 1.0, -1.07195346e+00), ([3, 3], 5.0, -1.47683688e+01), ([7, 7], 2.0, -1.08298897e+02),
-       ([9, 9], 2.5, -1.97636373e+02), ([6, 8], 2.0, -1.12078732e+02)]
+RHF = [(c["atomzs"], c["dist"], c["energy"]) for c in GOLDEN["rhf_321g"]["cases"]]
 
 
 @pytest.mark.parametrize("atomzs,dist,etrue", RHF)
@@ -30,7 +32,7 @@ def test_rhf_321g_golden(atomzs, dist, etrue):
 
 
 # dqc/test/test_hf.py:141-153 (UHF atoms, rtol 1e-7 at :177-189)
-UHF_ATOMS = [(1, 1, -4.96198609e-01), (3, 1, -7.38151326e+00), (5, 1, -2.43897617e+01), (8, 2, -7.43936572e+01)]
+UHF_ATOMS = [(c["z"], c["spin"], c["energy"]) for c in GOLDEN["uhf_atoms_321g"]["cases"]]
 
 
 @pytest.mark.parametrize("z,spin,etrue", UHF_ATOMS)
@@ -46,7 +48,7 @@ def test_uhf_no_golden():
     w, pos = _diatomic([7, 8], 2.0)
     h = fock_ref.RefHamilton(w).build_eri()
     e, _ = scf_ref.run_scf(h, [7, 8], pos, 15, spin=1)
-    assert abs(e - (-1.28477807e+02)) <= 1e-8 * 128.477807 * 10  # constant is printed to 9 digits
+    assert abs(e - GOLDEN["uhf_no_321g"]["energy"]) <= 1e-8 * 128.477807 * 10  # constant is printed to 9 digits
 
 
 def test_h2_density_points_golden():
@@ -55,9 +57,9 @@ def test_h2_density_points_golden():
     w, pos = util.make_wrapper([1, 1], [[0.0, 0.0, 0.8], [0.0, 0.0, -0.8]], "3-21g")
     h = fock_ref.RefHamilton(w).build_eri()
     _, dm = scf_ref.run_scf(h, [1, 1], pos.numpy(), 2)
-    xyz = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.4], [0.0, 0.0, 0.8], [0.0, 0.0, -0.4], [0.0, 0.0, -0.8]])
+    xyz = np.array(GOLDEN["h2_density_points"]["xyz"])
     dens = h.aodm2dens(dm, xyz).numpy()
-    true = np.array([0.18742819, 0.23469519, 0.30250292, 0.23469519, 0.30250292])
+    true = np.array(GOLDEN["h2_density_points"]["density"])
     assert np.allclose(dens, true, rtol=1e-5, atol=1e-8)
 
 
