@@ -381,8 +381,17 @@ def main():
             nprod = nsl * (nsl + 1) // 2
             ops = xc_flops * nprod
             peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+            # the same launch seen from HBM: every operand once (fp64 AO rows of the epilogue, int8 planes, outputs)
+            nsp_ = gb.nsp.astype(np.float64)
+            if kname == "rho_kernel":
+                hb = gb.ao_bytes + nsl * gb.sbp * nsp_.sum() + nsl * (nsp_ ** 2).sum() + 8.0 * ncomp * gb.ngl
+            else:
+                hb = nsl * gb.sbp * (np.ceil(nsp_ / 128) * 128).sum() + nsl * gb.sbp * nsp_.sum() + 8.0 * (nsp_ ** 2).sum()
+            hbm_view = {"algorithmic_bytes_per_launch": hb, "achieved_GBps": hb / t / 1e9, "peak_GBps": hbm_peak,
+                        "frac": hb / t / 1e9 / hbm_peak,
+                        "measured_traffic_frac_of_peak": (traffic.get(kname) / t / 1e9 / hbm_peak) if traffic.get(kname) else None}
             return {"kernel": kname, "bound": "tensor", "achieved": ops / t / 1e12, "peak": peak, "unit": "TOP/s (int8)",
-                    "frac": ops / t / 1e12 / peak, "traffic": traffic.get(kname),
+                    "frac": ops / t / 1e12 / peak, "traffic": traffic.get(kname), "hbm_view": hbm_view,
                     "peak_source": "tcgen05.mma.kind::i8: 2 x bf16_tflops of MEASURED_PEAKS.json%s (int8 runs at twice the "
                                    "bf16 rate on sm_100; no int8 entry in the file)" % ("" if "bf16_tflops" in peaks else " FALLBACK 1590"),
                     "algorithmic_ops_per_launch": ops, "int8_slice_products": nprod,
