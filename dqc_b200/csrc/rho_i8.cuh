@@ -4,15 +4,18 @@
 // GEMM roles: M = 128 grid points (TMEM lanes), N = 64 AOs per tile, K = the kept AOs of the superblock.
 // Both operands are K-major: A = phi rows (sliced once at set-up, scale per grid point), B = rows of the
 // gathered symmetric density D_sb (gathered + sliced every call, scale per row).  A work unit is one
-// (superblock, 128-row block); its CTA walks the N tiles, the epilogue warps drain the six int32
+// (superblock, 128-row block); its CTA walks the N tiles, the epilogue warps drain the S int32
 // accumulators to fp64 registers (freeing TMEM for the next N tile at once), then multiply with the fp64
-// AO values of the same rows and keep the four row sums in registers across N tiles -- X never leaves the
-// SM, exactly like the DMMA kernel (rho.cuh), and no atomics are needed.
+// AO values of the same rows (prefetched into L2 while the MMAs of the tile still run, read with 256-bit
+// streaming loads) and keep the four row sums in registers across N tiles -- X never leaves the SM, exactly
+// like the DMMA kernel (rho.cuh), and no atomics are needed.  S = 5 by default (E_xc to 3e-10 Ha of the fp64
+// kernel at C60).  The kernel is HBM-bound at C60: the A tile of a unit is streamed once per N tile and does
+// not survive in L2 in between (ncu: 46.8 GB at 94 % of the HBM peak against 23.5 GB algorithmic; the
+// variants tried against that are listed in DESIGN.md section 7).
 #pragma once
 #include "vxc_i8.cuh"
 
-#define RI8_STAGES 5      // no staging tile here: 5 x 36 KB ring
-#define RI8_THREADS 384   // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue
+#define RI8_STAGES 5      // no staging tile here: 5-stage ring (3..5 measure the same; 7 starves L1)
 
 // ---- A operand: phi rows -> S int8 planes, K-major tiles; scale per grid row ----
 // out (per SB, bytes): [row tile = g / 128][k tile = mu / 32][slice][(mu % 32) / 16][(g % 128) / 8][g % 8][mu % 16]

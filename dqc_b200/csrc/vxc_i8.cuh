@@ -7,19 +7,22 @@
 //     x = 2^e * sum_s q_s 2^(-6 - 7 s),   q_s in [-64, 64],   e = exponent of the column maximum,
 // every slice product sum_g q_s^A q_t^B is EXACT in int32 (|.| <= 512 * 4096 per product, <= 2^24 per
 // anti-diagonal), products with s + t = d share the scale 2^(-12 - 7 d) and one TMEM accumulator, and the
-// S accumulators are recombined in fp64 in the epilogue.  Truncation at s + t < S leaves a relative
+// S accumulators are recombined exactly (int64) in the epilogue.  Truncation at s + t < S leaves a relative
 // error of ~(S + 1) 2^(-7 S - 5) of (column max x column max x K): S = 6 reproduces the fp64 Vxc matrix
-// to ~1e-12 (tools/ozaki_emul.py), five orders inside the 1e-6 parity bar, with S (S + 1) / 2 = 21 int8
-// MMAs per fp64 one.
+// to ~1e-12 (tools/ozaki_emul.py), S = 5 -- the default -- to 1e-10 at the full C60 size (bar: 1e-6), with
+// S (S + 1) / 2 = 21 / 15 int8 MMAs per fp64 one.
 //
-// Kernel layout: CTA tile 128 (mu) x 64 (nu), K tile = 32 grid rows (one MMA K step), 5-stage ring.
+// Kernel layout: CTA tile 128 (mu) x BN (nu), BN = 96 with S = 5 (480 of the 512 TMEM columns; 3-stage ring,
+// 8 epilogue warps) or 64 (4-stage ring, 4 epilogue warps); K tile = 32 grid rows (one MMA K step).  tcgen05.mma
+// reads both operands from shared memory for every instruction, so bytes per MMA -- not L2 or HBM -- bound the
+// main loop: the wide tile with one slice less moves 42 % fewer of them.
 // Operands are MN-major (the AO index is the contiguous one) in the no-swizzle canonical UMMA layout
 // (core matrix = 16 bytes of MN x 8 rows of K).  The slicing kernels write the planes to global memory
 // ALREADY in that tiled order, so a pipeline stage is two contiguous blocks and the producer is one
 // thread issuing two 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) -- no tensor maps, no
 // per-thread address arithmetic.  Warp-specialised: warp 0 = producer, warp 1 = MMA issuer (one thread,
-// S (S + 1) / 2 MMAs per stage, tcgen05.commit frees the stage), warps 4-7 = epilogue (tcgen05.ld 32x32b,
-// fp64 recombination, tile staged in shared memory, row-wise coalesced fp64 atomics into M[idx][idx]).
+// S (S + 1) / 2 MMAs per stage, tcgen05.commit frees the stage), warps 4.. = epilogue (tcgen05.ld 32x32b,
+// recombination, tile staged in shared memory, row-wise coalesced fp64 atomics into M[idx][idx]).
 #pragma once
 #include "sb_common.cuh"
 
@@ -27,8 +30,7 @@
 #define I8_BN 64
 #define I8_KT 32          // one MMA K step (32 int8) per pipeline stage
 #define I8_THREADS 256
-#define I8_STAGES 4       // S = 6: 4 x 36 KB of operands in flight per SM (+ 66.5 KB epilogue staging tile)
-#define I8_EPI_LD 65      // padded row stride (doubles) of the epilogue staging tile
+#define I8_STAGES 4       // BN = 64: 4 stages of operands in flight per SM (+ the epilogue staging tile)
 #define I8_A_PLANE (I8_KT * I8_BM)   // 4096 bytes: [4 K groups][8 MN chunks][8 rows][16 bytes]
 #define I8_B_PLANE (I8_KT * I8_BN)   // 2048 bytes: [4 K groups][4 MN chunks][8 rows][16 bytes]
 
@@ -245,8 +247,6 @@ static cudaError_t launch_cluster2(K kernel, int grid, int threads, size_t smem,
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-// instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = 64, M = 128 (dense)
-#define I8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((I8_BN >> 3) << 17) | ((I8_BM >> 4) << 24))
 
 static int g_i8_variant = 0;   // timing experiments only (b200qc_i8_debug_variant)
 extern "C" int b200qc_i8_debug_variant(int v) { g_i8_variant = v; return 0; }

@@ -20,7 +20,21 @@ from dqc_b200.utils.linop import LinearOperator
 from dqc_b200.utils.dist import ParallelContext, get_context
 from dqc_b200.utils.misc import logger
 
-__all__ = ["DFMol"]
+__all__ = ["DFMol", "dfk_chunking"]
+
+
+def dfk_chunking(nao: int, nl: int, npad: int, kchunk_max: int, nsm: int = 148):
+    """Split-K plan of DF-K stage 2, K_ik = sum_(P,o) Y_i(P,o) Y_k(P,o): the contraction index runs over the rank's
+    ``nl`` aux functions times ``npad`` (padded) occupied orbitals and is cut into chunks of whole aux functions,
+    ``pc`` per chunk -- short enough for exact integer accumulation (``pc * npad <= kchunk_max``) and numerous
+    enough for ~4 waves of lower-triangle output tiles over the SMs.  Returns (pc, nchunk, kc, ktot, k_last)."""
+    mt = (nao + 127) // 128
+    ntl = sum(min((nao + 63) // 64, 2 * t + 2) for t in range(mt))       # 128 x 64 tiles touching the lower triangle
+    want = max(1, (4 * nsm + ntl - 1) // ntl)
+    pc = max(1, min(kchunk_max // npad, (nl + want - 1) // want))
+    nchunk = (nl + pc - 1) // pc
+    kc, ktot = pc * npad, nl * npad
+    return pc, nchunk, kc, ktot, ktot - (nchunk - 1) * kc
 
 
 class DFMol(BaseDF):
@@ -135,14 +149,8 @@ class DFMol(BaseDF):
             return kmat
         cw = cw.contiguous()
         npad = _lib.round_up(nocc, 64)
-        # K chunks of stage 2 = whole aux functions: pc of them (pc * npad columns) per chunk, >= ~4 waves of tiles
-        mt = (nao + 127) // 128
-        ntl = sum(min((nao + 63) // 64, 2 * t + 2) for t in range(mt))
-        want = max(1, (4 * 148 + ntl - 1) // ntl)
-        pc = max(1, min(_lib.I8_KCHUNK[S] // npad, (nl + want - 1) // want))
-        nchunk = (nl + pc - 1) // pc
-        kc, ktot = pc * npad, nl * npad
-        k_last = ktot - (nchunk - 1) * kc
+        # K chunks of stage 2 = whole aux functions: pc of them (pc * npad columns) per chunk
+        pc, nchunk, kc, ktot, k_last = dfk_chunking(nao, nl, npad, _lib.I8_KCHUNK[S])
         # stage 1: Y[i][P][o] = sum_j B[i][P][j] cw[j][o]      (batch i; M = P, N = o, K = j); the epilogue also
         # leaves max |Y| per (i, chunk of P) -- the row scales of the stage-2 operands
         cop = _lib.I8Operand("B", 1, nocc, nao, S, device=dev).fill(cw, 0, 1, nocc)

@@ -226,3 +226,16 @@ def test_benchmark_geometries():
     zs2, pos2 = systems.taxol_like()
     assert np.array_equal(pos, pos2)
     assert len(systems.carbon_cluster(36)[0]) == 36
+
+
+def test_dfk_split_k_plan():
+    """Host logic of the density-fitted exchange: the split-K chunks of stage 2 cover the contraction exactly, stay
+    inside the exact-integer-accumulation limit and are multiples of the MMA K step."""
+    from dqc_b200.df.dfmol import dfk_chunking
+    for nao, nl, nocc, lim in [(840, 3420, 180, 32768), (1123, 4299, 226, 32768), (24, 84, 5, 32768), (7, 1, 1, 32768),
+                               (840, 428, 180, 32768), (3010, 12255, 645, 32768), (840, 3420, 180, 65536)]:
+        npad = (nocc + 63) // 64 * 64
+        pc, nchunk, kc, ktot, k_last = dfk_chunking(nao, nl, npad, lim)
+        assert pc >= 1 and kc == pc * npad and kc <= lim and kc % 32 == 0
+        assert ktot == nl * npad and (nchunk - 1) * kc + k_last == ktot and 0 < k_last <= kc and k_last % 32 == 0
+        assert nchunk == -(-nl // pc)
