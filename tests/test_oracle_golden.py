@@ -183,3 +183,22 @@ def test_potential_is_derivative_of_energy(name):
     ep = xc_ref.edens_unpol(name, rho + h, g if fam == 2 else None)
     em = xc_ref.edens_unpol(name, rho - h, g if fam == 2 else None)
     assert torch.allclose(v, (ep - em) / (2 * h), rtol=1e-6, atol=1e-9)
+
+
+# ---- KS energies of dqc/test/test_ks.py:40-111 (H2, 6-311++G**, PySCF values, atol 1.3e-3 there because the grids
+# differ): pins the oracle's whole XC chain -- atomic grids, Becke weights, AO values, rho / grad rho, functional,
+# Vxc integration, SCF -- the same numbers the CUDA path reproduces in tests/test_gpu_hamilton.py
+@pytest.mark.parametrize("xc,etrue", [("lda_x", -0.979143262), ("gga_x_pbe", -1.068217310366847)])
+def test_rks_h2_golden_oracle(xc, etrue):
+    from dqc_b200.grid.factory import get_predefined_grid
+    from oracle import becke_ref
+    pos = np.array([[-0.5, 0.0, 0.0], [0.5, 0.0, 0.0]])
+    w, _ = util.make_wrapper([1, 1], pos.tolist(), "6-311++G**")
+    one = get_predefined_grid("sg2", [1], torch.zeros(1, 3, dtype=dtype), device=torch.device("cpu"))
+    n1 = one.get_rgrid().shape[0]
+    pts = np.concatenate([one.get_rgrid().numpy() + p for p in pos])
+    dvol = np.concatenate([one.get_dvolume().numpy()] * 2) * becke_ref.becke_weights(pts, np.repeat([0, 1], n1), pos)
+    h = fock_ref.RefHamilton(w).build_eri()
+    h.setup_grid(pts, dvol, xc)
+    e, _ = scf_ref.run_scf(h, [1, 1], pos, 2, method="ks")
+    assert abs(e - etrue) < 1.3e-3
