@@ -227,8 +227,11 @@ class HamiltonCGTO(BaseHamilton):
         """Orthogonal-basis density (nao, nao) -> [(sign, cw)] with X (scale dm) X^T = sum sign cw cw^T, cw in the
         AO basis.  Densities made by ``ao_orb2dm`` carry their orbitals; anything else is eigen-decomposed."""
         fac = getattr(dm, "_b200_orb", None)
+        # the tag is only trusted while neither the density nor its orbitals were modified in place since ao_orb2dm
+        if fac is not None and (dm._version, fac[0]._version, fac[1]._version) != fac[2]:
+            fac = None
         if fac is not None and bool((fac[1] >= 0).all()):
-            orb, w = fac
+            orb, w = fac[0], fac[1]
             cw = self._orthozer.convert_ortho_orb(orb * torch.sqrt(scale * w).unsqueeze(-2))
             return [(1.0, cw[:, w > 0].contiguous())]
         dmao = self._orthozer.unconvert_dm(_symm(dm)) * scale
@@ -374,7 +377,9 @@ class HamiltonCGTO(BaseHamilton):
         orb_w = orb * orb_weight.unsqueeze(-2)
         dm = torch.matmul(orb, orb_w.transpose(-2, -1))
         if orb.ndim == 2 and orb_weight.ndim == 1:
-            dm._b200_orb = (orb, orb_weight)     # lets the DF-K build skip the eigen-decomposition of dm
+            # lets the DF-K build skip the eigen-decomposition of dm (with the tensor versions: an in-place edit of
+            # any of the three invalidates the tag)
+            dm._b200_orb = (orb, orb_weight, (dm._version, orb._version, orb_weight._version))
         return dm
 
     def aodm2dens(self, dm: torch.Tensor, xyz: torch.Tensor) -> torch.Tensor:

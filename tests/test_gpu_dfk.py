@@ -106,6 +106,10 @@ def test_dfk_orbital_tag_and_spin(cuda):
     k_tag = h.get_exchange(du).fullmatrix()
     k_eig = h.get_exchange(du.clone()).fullmatrix()
     assert float((k_tag - k_eig).abs().max()) < 1e-10
+    # an in-place edit invalidates the tag (tensor versions are part of it): K is linear in D
+    du_half = h.ao_orb2dm(orb, wu)
+    du_half.mul_(0.5)
+    assert float((h.get_exchange(du_half).fullmatrix() - 0.5 * k_tag).abs().max()) < 1e-10
     ks = h.get_exchange(SpinParam(u=du, d=dd))
     # compare in the AO basis (the orthogonaliser's eigenvectors are defined up to sign / rotation)
     Xg, Xr = h._orthozer._orthozer.cpu(), ref.X
