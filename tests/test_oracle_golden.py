@@ -202,3 +202,31 @@ def test_rks_h2_golden_oracle(xc, etrue):
     h.setup_grid(pts, dvol, xc)
     e, _ = scf_ref.run_scf(h, [1, 1], pos, 2, method="ks")
     assert abs(e - etrue) < 1.3e-3
+
+
+@pytest.mark.parametrize("name", ["gga_x_pbe", "gga_c_pbe", "gga_x_b88", "gga_c_lyp"])
+def test_gradient_potential_is_derivative_of_energy(name):
+    # the gradient part of the potential, d e / d(grad rho) = 2 (de/dsigma) grad rho, by central
+    # finite differences of the energy density (unpolarised and one spin channel of the polarised form)
+    rho = torch.logspace(-2, 1, 10, dtype=dtype)
+    g = torch.stack([0.4 * rho, 0.1 * rho ** 1.1, -0.3 * rho ** 0.9])
+    _, _, vg = xc_ref.eval_unpol(name, rho, g)
+    for d in range(3):
+        h = 1e-6 * (g[d].abs() + 1e-3)
+        gp, gm = g.clone(), g.clone()
+        gp[d] += h
+        gm[d] -= h
+        fd = (xc_ref.edens_unpol(name, rho, gp) - xc_ref.edens_unpol(name, rho, gm)) / (2 * h)
+        assert torch.allclose(vg[d], fd, rtol=1e-6, atol=1e-9)
+    ru, rd = 0.7 * rho, 0.3 * rho
+    gu, gd = 0.6 * g, 0.4 * g.flip(0)
+    _, (vu, vd), (vgu, vgd) = xc_ref.eval_pol(name, ru, rd, gu, gd)
+    h = 1e-6 * ru
+    fd = (xc_ref.edens_pol(name, ru + h, rd, gu, gd) - xc_ref.edens_pol(name, ru - h, rd, gu, gd)) / (2 * h)
+    assert torch.allclose(vu, fd, rtol=1e-6, atol=1e-9)
+    h = 1e-6 * (gd[1].abs() + 1e-3)
+    gp, gm = gd.clone(), gd.clone()
+    gp[1] += h
+    gm[1] -= h
+    fd = (xc_ref.edens_pol(name, ru, rd, gu, gp) - xc_ref.edens_pol(name, ru, rd, gu, gm)) / (2 * h)
+    assert torch.allclose(vgd[1], fd, rtol=1e-6, atol=1e-9)
