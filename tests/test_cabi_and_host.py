@@ -36,6 +36,33 @@ def test_library_exports_every_declared_symbol():
     assert _lib.launch_count() == 0
 
 
+def test_binding_argument_counts_match_the_header():
+    """Every prototype of include/b200qc.h against the ctypes table of dqc_b200/_lib.py: same number of arguments,
+    pointer arguments bound as pointers, 64-bit sizes as c_int64 (an ABI drift here corrupts the stack silently)."""
+    from dqc_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "b200qc.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = re.findall(r"\b(b200qc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S)
+    assert len(protos) >= 30
+    seen = set()
+    for name, args in protos:
+        seen.add(name)
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        _, argtypes = _lib._SIGS[name]
+        assert len(params) == len(argtypes), "%s: header has %d arguments, the binding %d" % (name, len(params), len(argtypes))
+        for prm, ct in zip(params, argtypes):
+            if "*" in prm:
+                assert ct in (ctypes.c_void_p, ctypes.c_char_p), "%s: '%s' must be bound as a pointer" % (name, prm)
+            elif prm.startswith("int64_t"):
+                assert ct is ctypes.c_int64, "%s: '%s' must be bound as c_int64" % (name, prm)
+            elif prm.startswith("double"):
+                assert ct is ctypes.c_double, "%s: '%s' must be bound as c_double" % (name, prm)
+            elif prm.startswith("int "):
+                assert ct is ctypes.c_int, "%s: '%s' must be bound as c_int" % (name, prm)
+    assert seen == set(_lib._SIGS)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     from dqc_b200 import _lib, Mol
