@@ -46,6 +46,8 @@ WORKLOADS = {
     # B3LYP as libxc composes it (0.08 Slater + 0.72 B88 + 0.19 VWN-RPA + 0.81 LYP + 0.20 exact exchange)
     "c60-b3lyp-df": ("c60", "def2-svp", B3LYP_SL, "etb-jfit", 0.20, "sg3"),
     "taxol-like-b3lyp-df": ("taxol_like", "def2-svp", B3LYP_SL, "etb-jfit", 0.20, "sg3"),
+    # the same with the direct 4-centre J/K engine (no density fitting): seconds per build -- the weak kernel of
+    # DESIGN.md section 7; use --steps 1 --warmup 3
     "taxol-like-b3lyp-4c": ("taxol_like", "def2-svp", B3LYP_SL, None, 0.20, "sg3"),
 }
 METRIC = "fock_build_wall_ms_per_scf_iter"
