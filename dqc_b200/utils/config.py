@@ -24,8 +24,10 @@ class _Config:
     # N tile of that GEMM: 64, or 96 (only with 5 slices)
     RHO_I8_BN: int = int(os.environ.get("B200QC_RHO_I8_BN", "64"))
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
-    # scheduling of the tcgen05 XC kernels (bit mask): 1 = L2 evict_last hint on the K2 A planes, 2 = K4 in 2-CTA
-    # clusters with multicast A stages, 4 = K2 in 2-CTA clusters
+    # experimental scheduling of the tcgen05 XC kernels (bit mask, default 0; all measured slower or equal, DESIGN.md
+    # section 7): 1 = L2 evict_last hint on the K2 A planes, 2 = K4 in 2-CTA clusters with multicast A stages
+    # (64-wide tiles only), 4 = the same for K2, 16 = K2 with the first K steps of the A tile cached in shared
+    # memory, bits 8..11 = depth of the K2 operand ring (2..8 stages, 0 = the default 5)
     I8_MODE: int = int(os.environ.get("B200QC_I8_MODE", "0"))
     # density-fitted exact exchange (two batched GEMMs on tcgen05): 5 or 6 int8 slices
     DFK_I8_SLICES: int = int(os.environ.get("B200QC_DFK_I8", "6"))

@@ -139,7 +139,9 @@ int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nsli
  * of K2; 2 = K4 in 2-CTA thread-block clusters, every A stage fetched half by each CTA and multicast to both (the
  * pair works on two N tiles of one M tile; needs ptile_off / nptiles = exclusive prefix and total of
  * ceil(nsp / 128) * ceil(nsp / 128) pair units per superblock, else NULL / 0); 4 = the same for K2 (the pair splits
- * the N tiles of one 128-row block; partial row sums are added atomically). */
+ * the N tiles of one 128-row block; partial row sums are added atomically); 16 = K2 keeps the first K steps of a
+ * unit's A tile in shared memory behind a 4-stage ring; bits 8..11 = depth of the K2 operand ring (2..8, 0 = 5).
+ * All of these measured slower than or equal to the default on a B200. */
 int b200qc_i8_mode(int flags);
 
 /* timing experiments on the kernel above: 0 = normal, 1 = skip the epilogue, 2 = skip the MMAs */
