@@ -127,13 +127,65 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the reference's per-iteration torch-CPU ops (oracle/fock_ref.py) on a bounded sample
-def cpu_reference_step_factory(workload, grid_sample=65536, aux_sample=96):
-    """Builds the sampled CPU problem with the ORACLE only (no CUDA kernel on this path) and returns
-    (step_fn, scale_info).  step_fn() runs one sampled Fock build; full-size time is extrapolated
-    linearly in ngrid (XC part) and naux (DF-J part) -- both are exactly linear in those sizes in the
-    reference (hcgto.py:399-418,461-481 chunk loops; dfmol.py:70-75 einsums)."""
-    from oracle import fock_ref, cint, xc_ref
+# Workload description shared by both arms (the driver compares the two `config` objects)
+BASIS_PROVENANCE = {
+    "sto-3g": "embedded table pinned by the H2O RHF energy of the Crawford project (tests/test_oracle_golden.py)",
+    "cc-pvdz": "embedded table; H and O pinned by a literature H2O RHF energy to 2e-6 Ha, C typed and unverified by energy",
+    "def2-svp": "embedded table typed from the published one; NOT verified against an independent energy (no def2-SVP "
+                "energy is known offline to better than 1e-3 Ha)",
+    "3-21g": "embedded table pinned by the reference's RHF/UHF golden energies (rtol 1e-7)",
+}
+
+
+def workload_config(workload, world):
+    """Everything that defines the measured problem -- identical for `--impl b200` and `--impl reference`."""
+    from dqc_b200.grid.factory import get_predefined_grid
+    from dqc_b200.api.loadbasis import loadbasis
+    sysname, basis, xc, aux, exx, gridname = WORKLOADS[workload]
+    zs, pos = geometry(sysname)
+    shells = {z: loadbasis("%d:%s" % (z, basis)) for z in set(zs)}
+    nao = sum(sum(2 * b.angmom + 1 for b in shells[z]) for z in zs)
+    naux = None
+    if aux is not None:
+        ashells = {z: loadbasis("%d:%s" % (z, aux)) for z in set(zs)}
+        naux = sum(sum(2 * b.angmom + 1 for b in ashells[z]) for z in zs)
+    ngrid = 0
+    if xc is not None:
+        for z in set(zs):
+            g1 = get_predefined_grid(gridname, [z], torch.zeros(1, 3, dtype=torch.float64), device=torch.device("cpu"))
+            ngrid += g1.get_rgrid().shape[0] * zs.count(z)
+    return {"workload": "%s: %s / %s / xc=%s / %s / grid %s" % (
+        workload, sysname, basis, xc, ("DF-J aux=" + aux) if aux else "4-centre J/K", gridname),
+        "exx_fraction": exx, "nao": nao, "ngrid": ngrid, "naux": naux, "natoms": len(zs),
+        "density": "D = 2 C C^T, C = first nocc columns of qr(randn(nao, nao)) under manual_seed(0)",
+        "basis_tables": BASIS_PROVENANCE.get(basis, "embedded table"),
+        "geometry": "synthetic 113-atom C47H51NO14 skeleton (dqc_b200/utils/systems.py: no Taxol structure file offline)"
+                    if sysname == "taxol_like" else "closed-formula geometry (dqc_b200/utils/systems.py)",
+        "l2_policy": "inputs (AO values, (ij|P)) larger than L2; no flush",
+        "parallelism": "grid rows + aux shells (or J/K work items) sharded over %d GPU(s), one packed all-reduce" % world}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's per-iteration torch-CPU ops (oracle/fock_ref.py) at the FULL problem size
+def _host_mem_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 0
+
+
+def cpu_reference_step_factory(workload, grid_sample=None, aux_sample=None, j3c_oracle_seconds=25.0):
+    """Builds the CPU problem with the ORACLE only (no CUDA kernel on this path) and returns (step_fn, info).
+
+    Full size by default: AO values / gradients of every grid point (oracle/cint_oracle.c) and the dense
+    (nao, nao, naux) 3-centre tensor, exactly the tensors the reference keeps (hcgto.py:168-186, dfmol.py:38-55);
+    step_fn() is then one real reference-equivalent Fock build and nothing is extrapolated.  The one-off 3-centre
+    integrals would take minutes on the oracle, so only the first aux shells (about `j3c_oracle_seconds` of work) are
+    integrated and the remaining aux columns repeat them cyclically -- the per-iteration einsums are dense and do not
+    depend on the values.  When the host lacks the memory (about 60 GB at C60) the sample falls back to
+    `grid_sample` points / `aux_sample` aux functions with linear extrapolation, and says so."""
+    from oracle import fock_ref, cint
     from dqc_b200.hamilton.intor.lcintwrap import LibcintWrapper
     from dqc_b200.grid.factory import get_predefined_grid
     from tests import util
@@ -143,44 +195,80 @@ def cpu_reference_step_factory(workload, grid_sample=65536, aux_sample=96):
     w, _ = util.make_wrapper(zs, pos.tolist(), basis)
     nao = w.nao()
     info = {"nao": nao, "cores": torch.get_num_threads()}
-    # grid sample: every k-th point of the real sg3 grid positions (weights irrelevant for timing: 1e-3)
     per_atom = {}
-    ngrid_full = 0
     pts = []
     for z, p in zip(zs, pos):
         if z not in per_atom:
             g1 = get_predefined_grid(gridname, [z], torch.zeros(1, 3, dtype=torch.float64), device=torch.device("cpu"))
             per_atom[z] = g1.get_rgrid().numpy()
-        ngrid_full += per_atom[z].shape[0]
         pts.append(per_atom[z] + p)
-    pts = np.concatenate(pts)
-    stride = max(1, ngrid_full // grid_sample)
-    sample = np.ascontiguousarray(pts[::stride])
-    info.update(ngrid_full=ngrid_full, ngrid_sample=int(sample.shape[0]))
-    h = fock_ref.RefHamilton(w, orthozer=True)
-    if xc is not None:
-        h.setup_grid(sample, np.full(sample.shape[0], 1e-3), xc)
+    pts = np.concatenate(pts) if xc is not None else np.zeros((0, 3))
+    ngrid_full = int(pts.shape[0])
     naux_full = 0
+    auxw = None
     if aux is not None:
         auxw, _ = util.make_wrapper(zs, pos.tolist(), aux)
         naux_full = auxw.nao()
+    ncomp = 1 if xc is None else (4 if any(t in xc for t in ("gga", "b88", "lyp", "pbe")) else 1)
+    need = 8.0 * ngrid_full * nao * (ncomp + 1) + 8.0 * nao * nao * naux_full + 4e9
+    avail = _host_mem_available()
+    full = (grid_sample is None and aux_sample is None) and (avail == 0 or avail > need * 1.1)
+    if not full:
+        grid_sample = grid_sample or 65536
+        aux_sample = aux_sample or 96
+        info["fallback"] = "host memory %.0f GB < %.0f GB needed for the full-size tensors" % (avail / 1e9, need / 1e9)
+    stride = 1 if full else max(1, ngrid_full // grid_sample)
+    sample = np.ascontiguousarray(pts[::stride])
+    info.update(ngrid_full=ngrid_full, ngrid_sample=int(sample.shape[0]), full=full)
+    h = fock_ref.RefHamilton(w, orthozer=True)
+    if xc is not None:
+        # weights do not influence the timing: a constant stands in for the Becke-weighted volumes
+        h.setup_grid(sample, np.full(sample.shape[0], 1e-3), xc)
+    if aux is not None:
         bw, aw = LibcintWrapper.concatenate(w, auxw)
         atm, bas, env = aw.atm_bas_env
         a0, a1 = aw.shell_idxs
         b0, b1 = bw.shell_idxs
-        # first aux shells up to ~aux_sample functions
         loc = aw.full_shell_to_aoloc
+        # integrate aux shells until the time budget (full mode) or the sample size (fallback) is reached
+        target = naux_full if full else aux_sample
+        cols, a_lo, t0 = [], a0, time.perf_counter()
+        while a_lo < a1 and sum(c.shape[-1] for c in cols) < target:
+            a_hi = a_lo + 1
+            while a_hi < a1 and loc[a_hi] - loc[a_lo] < 64:
+                a_hi += 1
+            cols.append(torch.as_tensor(cint.int3c2e(atm, bas, env, (b0, b1, b0, b1, a_lo, a_hi))))
+            a_lo = a_hi
+            if time.perf_counter() - t0 > j3c_oracle_seconds:
+                break
+        blk = torch.cat(cols, dim=-1)
+        n_int = int(blk.shape[-1])
+        if full and n_int < naux_full:
+            j3c = torch.empty(nao, nao, naux_full, dtype=torch.float64)
+            for c0 in range(0, naux_full, n_int):
+                c1 = min(naux_full, c0 + n_int)
+                j3c[:, :, c0:c1] = blk[:, :, :c1 - c0]
+        else:
+            j3c = blk[:, :, :target] if not full else blk
+        del blk, cols
+        n_used = int(j3c.shape[-1])
+        # the (P|Q) metric of the same number of functions (values irrelevant for the timing of temp @ inv)
         a_hi = a0 + 1
-        while a_hi < a1 and loc[a_hi] - loc[a0] < aux_sample:
+        while a_hi < a1 and loc[a_hi] - loc[a0] < min(n_used, 256):
             a_hi += 1
-        j3c = torch.as_tensor(cint.int3c2e(atm, bas, env, (b0, b1, b0, b1, a0, a_hi)))
-        j2c = torch.as_tensor(cint.int2c2e(atm, bas, env, (a0, a_hi, a0, a_hi)))
-        h.j3c, h.j2c, h.inv_j2c = j3c, j2c, torch.inverse(j2c)
-        info.update(naux_full=naux_full, naux_sample=int(j3c.shape[-1]))
+        j2c_small = torch.as_tensor(cint.int2c2e(atm, bas, env, (a0, a_hi, a0, a_hi)))
+        inv = torch.zeros(n_used, n_used, dtype=torch.float64)
+        ns = j2c_small.shape[0]
+        inv_small = torch.inverse(j2c_small)
+        for c0 in range(0, n_used, ns):
+            c1 = min(n_used, c0 + ns)
+            inv[c0:c1, c0:c1] = inv_small[:c1 - c0, :c1 - c0]
+        h.j3c, h.j2c, h.inv_j2c = j3c, None, inv
+        info.update(naux_full=naux_full, naux_sample=n_used, naux_integrated=n_int)
         if exx != 0.0:
-            info["note"] = "the reference has no density-fitted exchange (hcgto.py:229-230 raises): K is not in the CPU sample"
-    elif exx != 0.0 or xc is None or aux is None:
-        info["note"] = "dense-ERI J/K of this workload is not part of the CPU sample (nao^4 tensor)"
+            info["note"] = "the reference has no density-fitted exchange (hcgto.py:229-230 raises): K is not in the CPU step"
+    elif exx != 0.0 or xc is None:
+        info["note"] = "dense-ERI J/K of this workload is not part of the CPU step (nao^4 tensor)"
     nocc = max(1, int(sum(zs)) // 2)
     dm = seeded_dm(h.nao, min(nocc, h.nao), torch.device("cpu"))
 
@@ -198,8 +286,8 @@ def cpu_reference_step_factory(workload, grid_sample=65536, aux_sample=96):
     return step, info
 
 
-def run_cpu_reference(workload, steps, warmup):
-    step, info = cpu_reference_step_factory(workload)
+def run_cpu_reference(workload, steps, warmup, **kw):
+    step, info = cpu_reference_step_factory(workload, **kw)
     for _ in range(warmup):
         step()
     acc = {"dfj_s": 0.0, "xc_s": 0.0}
@@ -209,14 +297,24 @@ def run_cpu_reference(workload, steps, warmup):
             acc[k] += t[k]
     dfj = acc["dfj_s"] / steps
     xcs = acc["xc_s"] / steps
-    full = xcs * info["ngrid_full"] / max(1, info["ngrid_sample"])
-    if info.get("naux_full"):
-        full += dfj * info["naux_full"] / info["naux_sample"]
-    sample = "XC ops on %d of %d grid points" % (info["ngrid_sample"], info["ngrid_full"])
-    if info.get("naux_full"):
-        sample += ", DF-J ops on %d of %d aux functions" % (info["naux_sample"], info["naux_full"])
-    sample += "; per-step time extrapolated linearly to the full sizes"
-    return full * 1e3, info, sample
+    if info["full"]:
+        total = xcs + dfj
+        sample = "FULL size, measured: XC ops on all %d grid points" % info["ngrid_full"]
+        if info.get("naux_full"):
+            sample += ", DF-J ops on the dense (nao, nao, %d) tensor (%d aux functions integrated by the oracle, the " \
+                      "other columns repeat them: dense einsums, timing independent of the values)" % (
+                          info["naux_full"], info["naux_integrated"])
+        sample += "; nothing extrapolated"
+    else:
+        total = xcs * info["ngrid_full"] / max(1, info["ngrid_sample"])
+        if info.get("naux_full"):
+            total += dfj * info["naux_full"] / info["naux_sample"]
+        sample = "FALLBACK (%s): XC ops on %d of %d grid points" % (info.get("fallback"), info["ngrid_sample"], info["ngrid_full"])
+        if info.get("naux_full"):
+            sample += ", DF-J ops on %d of %d aux functions" % (info["naux_sample"], info["naux_full"])
+        sample += "; per-step time extrapolated linearly to the full sizes"
+    info.update(xc_ms=xcs * 1e3, dfj_ms=dfj * 1e3)
+    return total * 1e3, info, sample
 
 
 # ---------------------------------------------------------------------------------------------
@@ -233,10 +331,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     sysname, basis, xc, aux, exx, gridname = WORKLOADS[args.workload]
-    config = {"workload": "%s: %s / %s / xc=%s / %s / grid %s" % (
-        args.workload, sysname, basis, xc, ("DF-J aux=" + aux) if aux else "4-centre J/K", gridname),
-        "exx_fraction": exx, "l2_policy": "inputs (AO values, packed (ij|P)) larger than L2; no flush",
-        "parallelism": "grid rows + aux shells (or J/K work items) sharded over %d GPU(s), one packed all-reduce" % world}
+    config = workload_config(args.workload, world)      # the same object in both arms
+    impl_config = {}                                    # how THIS arm runs it (kernels, storage, set-up time)
 
     if args.impl == "reference":
         if rank != 0:
@@ -245,7 +341,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config,
+                "config": config, "impl_config": {"xc_ms": info["xc_ms"], "dfj_ms": info["dfj_ms"]},
                 "cpu_baseline": {"value": ms, "unit": "ms", "cores": info["cores"], "kind": "port", "sample": sample},
                 "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -282,11 +378,12 @@ def main():
     dm = h.ao_orb2dm(orb_host.to(dev), occ)
     ngrid = int(mol.get_grid().get_rgrid().shape[0]) if xc is not None else 0
     if aux is None:
-        config["jk_engine"] = type(h._jkplan).__name__ + (
+        impl_config["jk_engine"] = type(h._jkplan).__name__ + (
             " (both dense (ij|kl) layouts resident in HBM, J/K = GEMVs)" if type(h._jkplan).__name__ == "StoredERI"
             else " (Schwarz-screened direct build, %d unique shell quartets)" % h._jkplan.nquartets)
-    config.update(nao=nao, nao_ao=h._nao_ao, ngrid=ngrid, natoms=len(zs),
-                  naux=(h.df._naux if h.df is not None else None), setup_s=round(t_setup, 2))
+    assert (config["nao"], config["ngrid"], config["naux"]) == (
+        h._nao_ao, ngrid, h.df._naux if h.df is not None else None), "workload_config disagrees with the built system"
+    impl_config.update(nao_orthogonal=nao, setup_s=round(t_setup, 2))
 
     def step():
         return h.get_fock_2e(dm, exx=exx, with_xc=xc is not None).fullmatrix()
@@ -362,12 +459,21 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     dmma_peak = _lib.peak_fp64_dmma(20000)
+    # int8 tensor peak: measured here with the library's own tcgen05.mma.kind::i8 issue-rate microbenchmark
+    # (MEASURED_PEAKS.json has no int8 entry; round 1 assumed 2 x bf16_tflops)
+    i8_peak = max(_lib.peak_i8_mma(40000) for _ in range(3))
+    i8_src = ("tcgen05.mma.kind::i8 issue-rate microbenchmark run in this process (b200qc_peak_i8_mma: M = 128, N = 256, "
+              "K = 32, operands resident in shared memory, best of 3); for comparison 2 x bf16_tflops of "
+              "MEASURED_PEAKS.json = %.0f" % (2.0 * peaks.get("bf16_tflops", 1590.0)))
     gb = h._gb if xc is not None else None
     ncomp = 4 if (xc is not None and h.xcfamily == 2) else 1
     xc_flops = gb.flops_per_pass if gb is not None else 0.0      # 2 * sum_sb SBP * nsp^2 (K2 and K4 GEMM each)
     if gb is not None:
-        config.update(sb_points=gb.sbp, ao_screen=gb.eps, kept_ao_fraction=round(gb.kept_fraction, 4),
+        impl_config.update(sb_points=gb.sbp, ao_screen=gb.eps, kept_ao_fraction=round(gb.kept_fraction, 4),
                       vxc_gemm=("tcgen05 int8 x%d slices" % gb.i8_slices) if gb.i8_slices else "fp64 DMMA",
+                      vxc_operand_prep="fused vb slicer" if getattr(gb, "colmax", None) is not None else "fp64 vb + slicer",
+                      rho_form=("point-stationary (64-point phi tiles resident in shared memory)"
+                                if getattr(gb, "rho_bn", 0) == 128 else "row-tile streaming") if gb.rho_i8_slices else "fp64",
                       rho_gemm=("tcgen05 int8 x%d slices" % gb.rho_i8_slices) if gb.rho_i8_slices else "fp64 DMMA",
                       ao_resident_gb=round(gb.ao_bytes / 1e9, 2),
                       dense_equiv_flops_per_pass=2.0 * ngrid * h._nao_ao ** 2 / world)
@@ -382,7 +488,7 @@ def main():
         if nsl:
             nprod = nsl * (nsl + 1) // 2
             ops = xc_flops * nprod
-            peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+            peak = i8_peak
             # the same launch seen from HBM: every operand once (fp64 AO rows of the epilogue, int8 planes, outputs)
             nsp_ = gb.nsp.astype(np.float64)
             if kname == "rho_kernel":
@@ -394,8 +500,7 @@ def main():
                         "measured_traffic_frac_of_peak": (traffic.get(kname) / t / 1e9 / hbm_peak) if traffic.get(kname) else None}
             return {"kernel": kname, "bound": "tensor", "achieved": ops / t / 1e12, "peak": peak, "unit": "TOP/s (int8)",
                     "frac": ops / t / 1e12 / peak, "traffic": traffic.get(kname), "hbm_view": hbm_view,
-                    "peak_source": "tcgen05.mma.kind::i8: 2 x bf16_tflops of MEASURED_PEAKS.json%s (int8 runs at twice the "
-                                   "bf16 rate on sm_100; no int8 entry in the file)" % ("" if "bf16_tflops" in peaks else " FALLBACK 1590"),
+                    "peak_source": i8_src,
                     "algorithmic_ops_per_launch": ops, "int8_slice_products": nprod,
                     "fp64_equivalent_tflops": xc_flops / t / 1e12,
                     "fp64_equivalent_vs_dmma_peak": xc_flops / t / 1e12 / dmma_peak}
@@ -414,10 +519,10 @@ def main():
         nocc_ = orb_host.shape[1]
         fl = 3.0 * h._nao_ao ** 2 * h.df._naux_local * nocc_ * (c / (2.0 * args.steps))   # per build
         t = ms / args.steps * 1e-3
-        peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+        peak = i8_peak
         return {"kernel": "gemm_i8_kernel", "bound": "tensor", "achieved": fl * nprod / t / 1e12, "peak": peak,
                 "unit": "TOP/s (int8)", "frac": fl * nprod / t / 1e12 / peak, "traffic": traffic.get("gemm_i8_kernel"),
-                "peak_source": "tcgen05.mma.kind::i8: 2 x bf16_tflops of MEASURED_PEAKS.json (no int8 entry in the file)",
+                "peak_source": i8_src,
                 "algorithmic_ops_per_launch": fl * nprod / 2.0, "launches_per_build": c / args.steps,
                 "int8_slice_products": nprod, "fp64_equivalent_tflops": fl / t / 1e12,
                 "fp64_equivalent_vs_dmma_peak": fl / t / 1e12 / dmma_peak}
@@ -455,7 +560,10 @@ def main():
             extra[k] = {"GB/s": nb / (kern[k]["ms_per_launch"] * 1e-3) / 1e9, "frac_of_hbm": nb / (
                 kern[k]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     if "vxc_vb_kernel" in kern:
-        nb = (ncomp + 1) * gb.ao_bytes / ncomp
+        if getattr(gb, "colmax", None) is not None:     # fused: fp64 AO values in, int8 planes out
+            nb = gb.ao_bytes + gb.i8_slices * gb.sbp * float(gb.nsp.sum())
+        else:                                           # fp64 vb out (sliced by a second kernel)
+            nb = (ncomp + 1) * gb.ao_bytes / ncomp
         extra["vxc_vb_kernel"] = {"GB/s": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9,
                                   "frac_of_hbm": nb / (kern["vxc_vb_kernel"]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     if "gemm_i8_kernel" in kern and h.df is not None and getattr(h.df, "_k_planes", None) is not None:
@@ -479,13 +587,14 @@ def main():
     line = {"metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config, "clocks": clocks,
+            "config": config, "impl_config": impl_config, "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(orb_host.numel() * 8),
                     "d2h_bytes_per_step": int(fock_host.numel() * 8)},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "xc_grid_points_per_s": (ngrid / (xc_ms * 1e-3)) if xc_ms > 0 else None,
-            "fp64_dmma_peak_tflops": dmma_peak, "kernels": kern, "kernel_rooflines": extra}
+            "fp64_dmma_peak_tflops": dmma_peak, "int8_mma_peak_tops": i8_peak, "kernels": kern,
+            "kernel_rooflines": extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.realpath(__file__))
 _SO_PATH = os.path.join(_HERE, "libb200qc.so")
 _lib = None
-_rys_loaded = False
+_rys_loaded = set()      # CUDA device indices that hold the Rys table (constant memory is per device)
 
 GRID_ALIGN = 128  # leading dimension of the grid axis (K2/K4 CTA tile)
 AO_ALIGN = 64     # leading dimension of the AO axis
@@ -33,6 +33,7 @@ _SIGS = {
     "b200qc_profile_name": (ctypes.c_char_p, [ctypes.c_int]),
     "b200qc_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_peak_fp64_dmma": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_peak_i8_mma": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_free": (ctypes.c_int, [ctypes.c_void_p]),
@@ -67,18 +68,19 @@ _SIGS = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_vxc_i8_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                             ctypes.c_void_p]),
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_vxc_sb_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_i8_debug_variant": (ctypes.c_int, [ctypes.c_int]),
     "b200qc_i8_mode": (ctypes.c_int, [ctypes.c_int]),
-    "b200qc_rho_i8_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_rho_i8_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     "b200qc_rho_sb_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -209,14 +211,22 @@ def peak_fp64_dmma(iters: int = 20000) -> float:
     return float(out.value)
 
 
+def peak_i8_mma(iters: int = 40000) -> float:
+    """Measured tcgen05 int8 tensor-pipe peak (TOP/s, 2 ops per multiply-add) of the current device."""
+    lib = load()
+    out = ctypes.c_double(0.0)
+    _check(lib.b200qc_peak_i8_mma(iters, ctypes.byref(out), _stream()), "peak_i8_mma")
+    return float(out.value)
+
+
 def round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
 def ensure_rys_table():
-    """Upload the Rys interpolation table (dqc_b200/data/rys_table.npz) once per process."""
-    global _rys_loaded
-    if _rys_loaded:
+    """Upload the Rys interpolation table (dqc_b200/data/rys_table.npz) once per process and device."""
+    dev = torch.cuda.current_device()
+    if dev in _rys_loaded:
         return
     lib = load()
     with np.load(os.path.join(_HERE, "data", "rys_table.npz")) as z:
@@ -227,7 +237,7 @@ def ensure_rys_table():
     cptr = (ctypes.c_void_p * nmax)(*[c.ctypes.data for c in coefs])
     hptr = (ctypes.c_void_p * nmax)(*[c.ctypes.data for c in herms])
     _check(lib.b200qc_rys_upload(nmax, float(h), deg, float(xmax), cptr, hptr), "rys_upload")
-    _rys_loaded = True
+    _rys_loaded.add(dev)
 
 
 class DeviceBasis(object):
@@ -683,8 +693,7 @@ class GridBlocks(object):
         self.d_shell_col = tt(col, torch.int32)
         self.d_vb_off = tt(vb_off, torch.int64)
         self.ao = torch.zeros(int(self.ncomp * self.sbp * nsp.sum()), dtype=torch.float64, device=dev)
-        self.dsb = torch.empty(int((nsp * nsp).sum()), dtype=torch.float64, device=dev)
-        self.vb = torch.empty(int(self.sbp * nsp.sum()), dtype=torch.float64, device=dev)
+        self._dsb = self._vb = None      # fp64 scratch of the fp64-DMMA / unfused kernels, allocated on first use
         self.w = torch.zeros(self.ngl, dtype=torch.float64, device=dev)
         self.w[:self.ngrid] = weights
         if self.nsb:
@@ -714,25 +723,43 @@ class GridBlocks(object):
             self.bplanes = torch.zeros(int(b_bytes.sum()), dtype=torch.int8, device=dev)
             self.ascale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
             self.bscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
-            _check(lib.b200qc_vxc_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, S, _ptr(self.ao),
-                                             _ptr(self.d_a_off), _ptr(self.aplanes), _ptr(self.ascale), _stream()),
+            # fused operand preparation (vb cut into int8 planes as it is formed): static column maxima per superblock
+            self.colmax = torch.empty(int(nsp.sum()) * self.ncomp, dtype=torch.float64, device=dev) \
+                if (_cfg.VXC_FUSED_VB and self.sbp <= 1536) else None
+            _check(lib.b200qc_vxc_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, S, self.ncomp,
+                                             _ptr(self.ao), _ptr(self.d_a_off), _ptr(self.aplanes), _ptr(self.ascale),
+                                             _ptr(self.colmax), _stream()),
                    "vxc_i8_prepare")
 
         # optional tcgen05 int8 form of the density GEMM: AO rows sliced once here
         self.rho_i8_slices = int(rho_i8_slices)
         if self.rho_i8_slices and self.nsb:
             S = self.rho_i8_slices
-            self.rho_bn = rbn = 96 if (S == 5 and _cfg.RHO_I8_BN == 96) else 64
-            rb_bytes = S * nsp * ((nsp + rbn - 1) // rbn * rbn)      # B operand: whole N tiles (zero padding)
+            # row tile of the sliced density: 128 = point-stationary kernel (phi planes in 64-row tiles, read from HBM
+            # once), 64 / 96 = the round-1 kernel (phi planes in 128-row tiles, streamed once per N tile)
+            self.rho_bn = rbn = _cfg.RHO_I8_BN if (_cfg.RHO_I8_BN in (64, 128) or (S == 5 and _cfg.RHO_I8_BN == 96)) else 128
+            rb_bytes = S * nsp * ((nsp + rbn - 1) // rbn * rbn)      # sliced density: whole row tiles (zero padding)
             self.d_ra_off = tt(excl(S * self.sbp * nsp), torch.int64)
             self.d_rb_off = tt(excl(rb_bytes), torch.int64)
             self.r_aplanes = torch.empty(int((S * self.sbp * nsp).sum()), dtype=torch.int8, device=dev)
             self.r_bplanes = torch.zeros(int(rb_bytes.sum()), dtype=torch.int8, device=dev)
             self.r_rscale = torch.empty(self.nsb * self.sbp, dtype=torch.float64, device=dev)
             self.r_cscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
-            _check(lib.b200qc_rho_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, S, _ptr(self.ao),
+            _check(lib.b200qc_rho_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, S, 64 if rbn == 128 else 128, _ptr(self.ao),
                                              _ptr(self.d_ra_off), _ptr(self.r_aplanes), _ptr(self.r_rscale), _stream()),
                    "rho_i8_prepare")
+
+    @property
+    def dsb(self) -> torch.Tensor:
+        if self._dsb is None:
+            self._dsb = torch.empty(int((self.nsp * self.nsp).sum()), dtype=torch.float64, device=self.ao.device)
+        return self._dsb
+
+    @property
+    def vb(self) -> torch.Tensor:
+        if self._vb is None:
+            self._vb = torch.empty(int(self.sbp * self.nsp.sum()), dtype=torch.float64, device=self.ao.device)
+        return self._vb
 
     def rho(self, dm: torch.Tensor, with_grad: bool):
         """dm (nao, nao) symmetric AO-basis density -> rho (ngl,), grad (3, ngl) | None (zero in the padding)."""
@@ -757,9 +784,13 @@ class GridBlocks(object):
         assert vrho.shape[0] == self.ngl and (vgrad is None or self.deriv)
         mat = torch.empty((self.nao, self.nao), dtype=torch.float64, device=vrho.device)
         if self.i8_slices and self.nsb:
+            # the fused slicer bounds vb with the maxima of ALL stored components: an LDA potential on a GGA grid
+            # (vgrad None, 4 components stored) takes the two-pass form
+            fused = self.colmax is not None and (vgrad is not None or self.ncomp == 1)
             _check(lib.b200qc_vxc_sb_i8(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.i8_slices,
                                         _ptr(self.d_idx), _ptr(self.ao), _ptr(self.w), _ptr(vrho.contiguous()),
-                                        _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(self.vb), _ptr(self.aplanes),
+                                        _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(None if fused else self.vb),
+                                        _ptr(self.colmax if fused else None), _ptr(self.aplanes),
                                         _ptr(self.d_a_off), _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.d_b_off),
                                         _ptr(self.bscale), self.i8_bn, _ptr(self.d_tile_off), self.ntiles, _ptr(self.d_ptile_off),
                                         self.nptiles, _ptr(mat), _stream()),

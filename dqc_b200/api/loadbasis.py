@@ -9,7 +9,7 @@ from typing import List
 import torch
 from dqc_b200.utils.datastruct import CGTOBasis
 
-__all__ = ["loadbasis"]
+__all__ = ["loadbasis", "has_basis"]
 
 _SPDF = {c: l for l, c in enumerate("spdfghi")}
 _DATADIR = os.path.join(os.path.dirname(os.path.realpath(__file__)), "..", "data", "basis")
@@ -60,6 +60,11 @@ def _normalize_basisname(name: str) -> str:
     for ch in "(),":
         b = b.replace(ch, "_")
     return b
+
+
+def has_basis(z: int, name: str) -> bool:
+    """True when the table of basis `name` for element `z` is embedded under data/basis."""
+    return os.path.exists(os.path.join(_DATADIR, _normalize_basisname(name.strip()), "%02d.gaussian94" % int(z)))
 
 
 def _basis_path(cmd: str) -> str:

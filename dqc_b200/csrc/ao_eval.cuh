@@ -131,6 +131,7 @@ ao_eval_kernel(const ShellRec *__restrict__ shells, const double *__restrict__ e
 extern "C" int b200qc_eval_gto(const b200qc_basis *basis, int sh0, int sh1, int deriv,
                                const double *coords, int64_t ngrid, double *ao, int64_t ngrid_ld,
                                int64_t ao_ld, void *stream) {
+    if (qc_require_basis_device(basis)) return 2;
     QC_REQUIRE(basis != nullptr, "null basis");
     QC_REQUIRE(0 <= sh0 && sh0 < sh1 && sh1 <= basis->nbas, "bad shell range");
     QC_REQUIRE(deriv == 0 || deriv == 1, "deriv must be 0 or 1");

@@ -5,4 +5,6 @@
 #include "sb_common.cuh"
 #include "vxc_i8.cuh"
 #include "rho_i8.cuh"
+#include "rho_i8_ps.cuh"
 #include "gemm_i8.cuh"
+#include "peak_i8.cuh"

@@ -17,7 +17,7 @@ if newer build/b200qc.o b200qc.cu common.cuh tables.cuh ao_eval.cuh becke.cuh xc
         sb_common.cuh xc_sb.cuh rys.cuh ints.cuh jk.cuh dfj.cuh ../../include/b200qc.h build.sh; then
     $NVCC $FLAGS -c -o build/b200qc.o b200qc.cu & PIDS="$PIDS $!"
 fi
-if newer build/b200qc_tc.o b200qc_tc.cu common.cuh sb_common.cuh vxc_i8.cuh rho_i8.cuh gemm_i8.cuh \
+if newer build/b200qc_tc.o b200qc_tc.cu common.cuh sb_common.cuh vxc_i8.cuh rho_i8.cuh rho_i8_ps.cuh gemm_i8.cuh peak_i8.cuh \
         ../../include/b200qc.h build.sh; then
     $NVCC $FLAGS -c -o build/b200qc_tc.o b200qc_tc.cu & PIDS="$PIDS $!"
 fi

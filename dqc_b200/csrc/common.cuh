@@ -62,6 +62,7 @@ struct ShellRec {
 };
 
 struct b200qc_basis {
+    int device = -1;   // the CUDA device its arrays (and the constant tables uploaded with it) live on
     int natm, nbas, nenv;
     std::vector<int> h_atm, h_bas, h_ao_loc;
     std::vector<double> h_env;
@@ -104,7 +105,7 @@ struct RysTable {
     double herm[RYS_NMAX][2][RYS_NMAX];
 };
 static __constant__ RysTable c_rys;
-static bool g_rys_ready = false;
+static bool g_rys_ready[64] = {};   // per device (tables.cuh)
 
 static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 

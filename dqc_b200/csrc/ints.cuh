@@ -531,7 +531,10 @@ static void make_pair_lists(const b200qc_basis *B, int a0, int a1, int b0, int b
 
 static int int_require_ready(const b200qc_basis *basis) {
     QC_REQUIRE(basis != nullptr, "null basis");
-    QC_REQUIRE(g_rys_ready, "Rys table not uploaded (b200qc_rys_upload)");
+    const int dev = qc_current_device();
+    QC_REQUIRE(dev >= 0 && dev == basis->device,
+               "the current CUDA device is not the one this basis was uploaded on (wrap the call in torch.cuda.device)");
+    QC_REQUIRE(g_rys_ready[dev], "Rys table not uploaded on this device (b200qc_rys_upload)");
     return 0;
 }
 

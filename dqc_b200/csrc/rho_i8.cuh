@@ -17,9 +17,10 @@
 
 #define RI8_STAGES 5      // no staging tile here: 5-stage ring (3..5 measure the same; 7 starves L1)
 
-// ---- A operand: phi rows -> S int8 planes, K-major tiles; scale per grid row ----
-// out (per SB, bytes): [row tile = g / 128][k tile = mu / 32][slice][(mu % 32) / 16][(g % 128) / 8][g % 8][mu % 16]
-template <int S>
+// ---- phi rows -> S int8 planes, K-major tiles of RT grid rows; scale per grid row ----
+// RT = 128: the A operand (M tile) of rho_i8_kernel; RT = 64: the stationary B operand (N tile) of rho_i8_ps_kernel
+// out (per SB, bytes): [row tile = g / RT][k tile = mu / 32][slice][(mu % 32) / 16][(g % RT) / 8][g % 8][mu % 16]
+template <int S, int RT>
 __global__ void __launch_bounds__(256)
 sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp,
                      const int64_t *__restrict__ p_off, signed char *__restrict__ planes, double *__restrict__ rscale) {
@@ -39,14 +40,15 @@ sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ 
     const double inv = ldexp(64.0, -e);
     if (lane == 0) rscale[(int64_t)sb * sbp + g] = ldexp(1.0, e);
     const int nkt = d.nsp / I8_KT;
-    signed char *P = planes + p_off[sb] + (int64_t)(g >> 7) * nkt * S * I8_A_PLANE + ((g & 127) >> 3) * 128 + (g & 7) * 16;
+    constexpr int PLANE = I8_KT * RT;
+    signed char *P = planes + p_off[sb] + (int64_t)(g / RT) * nkt * S * PLANE + ((g % RT) >> 3) * 128 + (g & 7) * 16;
     for (int c = lane; c < d.nsp; c += 32) {
         double y = X[c] * inv;
-        signed char *Q = P + (int64_t)(c >> 5) * S * I8_A_PLANE + ((c & 31) >> 4) * 2048 + (c & 15);
+        signed char *Q = P + (int64_t)(c >> 5) * S * PLANE + ((c & 31) >> 4) * (RT * 16) + (c & 15);
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const double q = rint(y);
-            Q[s * I8_A_PLANE] = (signed char)(int)q;
+            Q[s * PLANE] = (signed char)(int)q;
             y = (y - q) * 128.0;
         }
     }
@@ -375,17 +377,22 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// Slices the static AO values (component 0) of every superblock once, row-wise, into the K-major tiled
-// A-operand order: aplanes = sum_sb nslice * sbp * nsp bytes at a_off[sb]; rscale = nsb * sbp doubles.
-extern "C" int b200qc_rho_i8_prepare(const void *sbdesc, int nsb, int sbp, int nslice, const double *ao,
+// Slices the static AO values (component 0) of every superblock once, row-wise, into K-major tiles of `row_tile`
+// grid rows (128: A operand of rho_i8_kernel; 64: stationary B operand of rho_i8_ps_kernel):
+// aplanes = sum_sb nslice * sbp * nsp bytes at a_off[sb]; rscale = nsb * sbp doubles.
+extern "C" int b200qc_rho_i8_prepare(const void *sbdesc, int nsb, int sbp, int nslice, int row_tile, const double *ao,
                                      const int64_t *a_off, signed char *aplanes, double *rscale, void *stream) {
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
+    QC_REQUIRE(row_tile == 128 || row_tile == 64, "row tile must be 128 or 64");
     QC_REQUIRE(sbp % I8_BM == 0, "superblock size must be a multiple of 128");
     if (nsb == 0) return 0;
     dim3 grid((unsigned)(sbp / 8), (unsigned)nsb);
     const SBDesc *sbd = (const SBDesc *)sbdesc;
-    if (nslice == 5) sb_slice_rows_kernel<5><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, a_off, aplanes, rscale);
-    else sb_slice_rows_kernel<6><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, a_off, aplanes, rscale);
+    cudaStream_t st = as_stream(stream);
+    if (nslice == 5 && row_tile == 128) sb_slice_rows_kernel<5, 128><<<grid, 256, 0, st>>>(sbd, ao, sbp, a_off, aplanes, rscale);
+    else if (nslice == 5) sb_slice_rows_kernel<5, 64><<<grid, 256, 0, st>>>(sbd, ao, sbp, a_off, aplanes, rscale);
+    else if (row_tile == 128) sb_slice_rows_kernel<6, 128><<<grid, 256, 0, st>>>(sbd, ao, sbp, a_off, aplanes, rscale);
+    else sb_slice_rows_kernel<6, 64><<<grid, 256, 0, st>>>(sbd, ao, sbp, a_off, aplanes, rscale);
     QC_LAUNCHED(1);
     return 0;
 }
@@ -448,23 +455,3 @@ static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     return 0;
 }
 
-// Same contract as b200qc_rho_sb with the GEMM on tcgen05 int8 slices.  bplanes (sum_sb nslice * nsp * ceil(nsp / bn) * bn
-// bytes at b_off[sb], ZERO-FILLED once by the caller: the rows past nsp of a last N tile are never written) and
-// cscale (sum_sb nsp doubles) are per-call scratch.  bn = N tile: 64, or 96 with nslice = 5.
-extern "C" int b200qc_rho_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
-                                const double *ao, const double *dm, int nao, const signed char *aplanes,
-                                const int64_t *a_off, const double *rscale, signed char *bplanes,
-                                const int64_t *b_off, double *cscale, int bn, double *rho, double *grad, void *stream) {
-    QC_REQUIRE(sbp % I8_BM == 0, "superblock size must be a multiple of 128");
-    QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
-    QC_REQUIRE(bn == 64 || (bn == 96 && nslice == 5), "N tile: 64, or 96 with 5 slices");
-    QC_REQUIRE((int64_t)max_nsp * 6 * 4096 < (1LL << 31), "too many AOs per superblock for exact int32 accumulation");
-    if (nsb == 0) return 0;
-    const SBDesc *sbd = (const SBDesc *)sbdesc;
-    cudaStream_t st = as_stream(stream);
-    if (nslice == 5 && bn == 96)
-        return rho_i8_run<5, 96>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
-    if (nslice == 5)
-        return rho_i8_run<5, 64>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
-    return rho_i8_run<6, 64>(sbd, nsb, sbp, max_nsp, idx, ao, dm, nao, aplanes, a_off, rscale, bplanes, b_off, cscale, rho, grad, st);
-}

@@ -92,12 +92,29 @@ void h_fill_c2s(int l, double *M) {
                 }
     }
 }
-std::once_flag g_tables_once;
-int g_tables_status = 0;
+// __constant__ symbols live once PER DEVICE: the tables are uploaded on first use on every device a basis is
+// created on (a second Hamiltonian on another GPU of the same process would otherwise read zero-filled tables).
+#define QC_MAX_DEVICES 64
+std::mutex g_tables_mutex;
+bool g_tables_ready[QC_MAX_DEVICES] = {};
 }  // namespace
 
+static int qc_current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= QC_MAX_DEVICES) return -1;
+    return dev;
+}
+
 static int qc_init_tables() {
-    std::call_once(g_tables_once, [] {
+    const int dev = qc_current_device();
+    if (dev < 0) {
+        b200qc_set_error("no current CUDA device");
+        return 1;
+    }
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    if (g_tables_ready[dev]) return 0;
+    int status = 0;
+    {
         C2STables t;
         h_fill_c2s(0, t.s0);
         h_fill_c2s(1, t.s1);
@@ -119,10 +136,19 @@ static int qc_init_tables() {
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_cart_pow, pw, sizeof(pw));
         if (e != cudaSuccess) {
             b200qc_set_error(std::string("constant table upload failed: ") + cudaGetErrorString(e));
-            g_tables_status = 1;
+            status = 1;
         }
-    });
-    return g_tables_status;
+    }
+    if (status == 0) g_tables_ready[dev] = true;
+    return status;
+}
+
+// Kernels that read the per-device constant tables refuse a basis that lives on another device.
+static int qc_require_basis_device(const b200qc_basis *b) {
+    QC_REQUIRE(b != nullptr, "null basis");
+    QC_REQUIRE(qc_current_device() == b->device,
+               "the current CUDA device is not the one this basis was uploaded on (wrap the call in torch.cuda.device)");
+    return 0;
 }
 
 extern "C" int b200qc_basis_upload(const int *h_atm, int natm, const int *h_bas, int nbas,
@@ -131,6 +157,7 @@ extern "C" int b200qc_basis_upload(const int *h_atm, int natm, const int *h_bas,
     QC_REQUIRE(out != nullptr && natm > 0 && nbas > 0, "bad arguments");
     if (qc_init_tables()) return 1;
     auto *b = new b200qc_basis();
+    b->device = qc_current_device();
     b->natm = natm;
     b->nbas = nbas;
     b->nenv = nenv;
@@ -188,13 +215,16 @@ extern "C" int b200qc_basis_free(b200qc_basis *b) {
     return 0;
 }
 
-static std::vector<double *> g_rys_dev;
+static std::vector<double *> g_rys_dev[QC_MAX_DEVICES];   // per device, like the __constant__ RysTable that points at them
 
 extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
                                  const double *const *h_coef, const double *const *h_herm) {
     QC_REQUIRE(nmax >= 1 && nmax <= RYS_NMAX, "nmax out of range");
-    for (double *p : g_rys_dev) cudaFree(p);
-    g_rys_dev.clear();
+    const int dev = qc_current_device();
+    QC_REQUIRE(dev >= 0, "no current CUDA device");
+    for (double *p : g_rys_dev[dev]) cudaFree(p);
+    g_rys_dev[dev].clear();
+    g_rys_ready[dev] = false;
     RysTable t = {};
     t.nmax = nmax;
     t.deg = deg;
@@ -206,7 +236,7 @@ extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
         double *d = nullptr;
         QC_CHECK(cudaMalloc(&d, cnt * sizeof(double)));
         QC_CHECK(cudaMemcpy(d, h_coef[n - 1], cnt * sizeof(double), cudaMemcpyHostToDevice));
-        g_rys_dev.push_back(d);
+        g_rys_dev[dev].push_back(d);
         t.coef[n - 1] = d;
         for (int r = 0; r < n; r++) {
             t.herm[n - 1][0][r] = h_herm[n - 1][r];
@@ -214,6 +244,6 @@ extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
         }
     }
     QC_CHECK(cudaMemcpyToSymbol(c_rys, &t, sizeof(t)));
-    g_rys_ready = true;
+    g_rys_ready[dev] = true;
     return 0;
 }

@@ -95,6 +95,150 @@ sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, co
     }
 }
 
+// ---- fused K4a: vb = w (v phi + 2 g . grad phi) cut straight into the B-operand planes ----
+// The slicer needs the column maxima of vb per superblock BEFORE it can cut, which is why round 1 wrote vb to HBM in
+// fp64 (4.4 GB at C60) and read it back twice.  Any upper bound of the maximum works as the block exponent -- a bound
+// that is 2^k too large costs k of the 7 S mantissa bits -- and a cheap one follows from the triangle inequality:
+//     max_g |vb_g,nu|  <=  max_g |w v| * max_g |phi_nu|  +  sum_d max_g |2 w g_d| * max_g |d_d phi_nu|
+// with the column maxima of phi / grad phi per superblock precomputed once (sb_colmax_kernel) and the four coefficient
+// maxima formed here from the 512 rows of the superblock.  One pass: reads the fp64 AO values once, writes int8.
+
+// colmax[(idx_off + col) * NCOMP + c] = max over the superblock's rows of |ao_c[row][col]|
+template <int NCOMP>
+__global__ void __launch_bounds__(256)
+sb_colmax_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp, double *__restrict__ colmax) {
+    const SBDesc d = sbd[blockIdx.y];
+    const int c0 = blockIdx.x * 64;
+    if (c0 >= d.nsp) return;
+    const int col = c0 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+    const int64_t ld = d.nsp;
+    __shared__ double smax[4][64];
+#pragma unroll
+    for (int c = 0; c < NCOMP; c++) {
+        const double *X = ao + d.ao_off + (int64_t)c * sbp * ld;
+        double m = 0.0;
+        for (int r = rg; r < sbp; r += 4) m = fmax(m, fabs(X[(int64_t)r * ld + col]));
+        smax[rg][threadIdx.x & 63] = m;
+        __syncthreads();
+        if (rg == 0)
+            colmax[(int64_t)(d.idx_off + col) * NCOMP + c] =
+                fmax(fmax(smax[0][col - c0], smax[1][col - c0]), fmax(smax[2][col - c0], smax[3][col - c0]));
+        __syncthreads();
+    }
+}
+
+// planes: the B operand of vxc_i8_gemm_kernel, same tiled order as sb_slice_kernel<S, W> writes:
+// [tile = col / W][k tile = row / 32][slice][(row % 32) / 8][(col % W) / 16][row % 8][col % 16]
+template <int S, int W, int NCOMP>
+__global__ void __launch_bounds__(256)
+vxc_vbslice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp, int64_t ngrid_ld,
+                   const double *__restrict__ w, const double *__restrict__ vrho, const double *__restrict__ vgrad,
+                   const double *__restrict__ colmax, const int64_t *__restrict__ p_off, signed char *__restrict__ planes,
+                   double *__restrict__ scales) {
+    extern __shared__ double vbs_smem[];          // coef[NCOMP][sbp]
+    __shared__ double wmax[8][NCOMP], sinv[64];
+    const int sb = blockIdx.y;
+    const SBDesc d = sbd[sb];
+    const int c0 = blockIdx.x * 64;
+    if (c0 >= d.nsp) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *coef = vbs_smem;
+    // 1. the row coefficients of this superblock and their maxima
+    double m[NCOMP];
+#pragma unroll
+    for (int c = 0; c < NCOMP; c++) m[c] = 0.0;
+    for (int r = tid; r < sbp; r += 256) {
+        const int64_t g = (int64_t)sb * sbp + r;
+        const double wg = w[g];
+        double cf = wg * vrho[g];
+        coef[r] = cf;
+        m[0] = fmax(m[0], fabs(cf));
+        if (NCOMP == 4) {
+#pragma unroll
+            for (int dd = 0; dd < 3; dd++) {
+                cf = 2.0 * wg * vgrad[(int64_t)dd * ngrid_ld + g];
+                coef[(dd + 1) * sbp + r] = cf;
+                m[dd + 1] = fmax(m[dd + 1], fabs(cf));
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCOMP; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[c] = fmax(m[c], __shfl_xor_sync(0xffffffffu, m[c], o));
+        if (lane == 0) wmax[warp][c] = m[c];
+    }
+    __syncthreads();
+    // 2. bound of the column maxima -> block exponents of the 64 columns of this CTA
+    if (tid < 64) {
+        const int col = c0 + tid;
+        double b = 0.0;
+#pragma unroll
+        for (int c = 0; c < NCOMP; c++) {
+            double a = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) a = fmax(a, wmax[q][c]);
+            b += a * colmax[(int64_t)(d.idx_off + col) * NCOMP + c];
+        }
+        int e = 0;
+        if (b > 0.0) frexp(b, &e);              // b = f 2^e, f in [0.5, 1)  =>  |vb| / 2^e < 1
+        sinv[tid] = ldexp(64.0, -e);
+        scales[d.idx_off + col] = ldexp(1.0, e);
+    }
+    __syncthreads();
+    // 3. a thread owns 16 consecutive columns of one row: 128 contiguous bytes per component in, one 16-byte store
+    //    per slice out
+    constexpr int PLANE = I8_KT * W;
+    const int nk = sbp / I8_KT;
+    const int64_t ld = d.nsp, cs = (int64_t)sbp * ld;
+    const int cg = tid & 3;
+    const int cq = c0 + cg * 16;
+    const int tile = cq / W, wc = cq % W;
+    signed char *P = planes + p_off[sb] + (int64_t)tile * nk * S * PLANE + (wc >> 4) * 128;
+    for (int r = tid >> 2; r < sbp; r += 64) {
+        double acc[16];
+        {
+            const double cf = coef[r];
+            const double *src = ao + d.ao_off + (int64_t)r * ld + cq;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(src + j);
+                acc[j] = cf * v.x;
+                acc[j + 1] = cf * v.y;
+            }
+        }
+        if (NCOMP == 4) {
+#pragma unroll
+            for (int c = 1; c < 4; c++) {
+                const double cf = coef[c * sbp + r];
+                const double *src = ao + d.ao_off + c * cs + (int64_t)r * ld + cq;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(src + j);
+                    acc[j] += cf * v.x;
+                    acc[j + 1] += cf * v.y;
+                }
+            }
+        }
+        unsigned int q4[S][4];
+#pragma unroll
+        for (int s = 0; s < S; s++) q4[s][0] = q4[s][1] = q4[s][2] = q4[s][3] = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            double y = acc[j] * sinv[cg * 16 + j];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const double q = rint(y);
+                q4[s][j >> 2] |= ((unsigned int)(int)q & 0xffu) << (8 * (j & 3));
+                y = (y - q) * 128.0;
+            }
+        }
+        signed char *Q = P + (int64_t)(r >> 5) * S * PLANE + ((r & 31) >> 3) * (W / 16) * 128 + (r & 7) * 16;
+#pragma unroll
+        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * PLANE) = make_uint4(q4[s][0], q4[s][1], q4[s][2], q4[s][3]);
+    }
+}
+
 // ---- tcgen05 plumbing (PTX spellings as in the CUTLASS sm100 headers) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -457,13 +601,20 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
 // Slices the (static) AO values of every superblock once into the tiled A-operand order.
 // aplanes: sum_sb ceil(nsp / 128) * 128 * sbp * nslice bytes, ZERO-FILLED by the caller (partial last M tile);
 // a_off[sb]: byte offset of the SB's block; ascale: sum_sb nsp doubles.
-extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const double *ao,
-                                     const int64_t *a_off, signed char *aplanes, double *ascale, void *stream) {
+extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, int ncomp,
+                                     const double *ao, const int64_t *a_off, signed char *aplanes, double *ascale,
+                                     double *colmax, void *stream) {
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
     QC_REQUIRE(sbp % I8_KT == 0, "superblock size must be a multiple of 32");
+    QC_REQUIRE(ncomp == 1 || ncomp == 4, "ncomp must be 1 or 4");
     if (nsb == 0) return 0;
     dim3 grid((unsigned)(max_nsp / 64), (unsigned)nsb);
     const SBDesc *sbd = (const SBDesc *)sbdesc;
+    if (colmax != nullptr) {    // static column maxima of phi (and grad phi) per superblock: the fused vb slicer's bound
+        if (ncomp == 4) sb_colmax_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, colmax);
+        else sb_colmax_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, colmax);
+        QC_LAUNCHED(1);
+    }
     if (nslice == 5)
         sb_slice_kernel<5, I8_BM><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, nullptr, 1, sbp, a_off, aplanes, ascale);
     else
@@ -475,27 +626,38 @@ extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int m
 template <int S, int BN>
 static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
                       const double *weights, const double *vrho, const double *vgrad, double *vb,
-                      const int64_t *vb_off, const signed char *aplanes, const int64_t *a_off, const double *ascale,
+                      const int64_t *vb_off, const double *colmax, const signed char *aplanes, const int64_t *a_off,
+                      const double *ascale,
                       signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
                       const int *ptile_off, int nptiles, int nao, double *mat, cudaStream_t st) {
-    // K4a: vb = w (v phi + 2 g . grad phi) in fp64 (one streaming pass at the HBM roofline), then the slicer.
-    // (A fused single-pass variant that staged a 32-column slab of vb in shared memory was slower: one
-    // 128 KB CTA per SM cannot keep enough loads in flight.)
     const int64_t ngl = (int64_t)nsb * sbp;
-    const int wpb = 8;
-    const unsigned nb1 = (unsigned)((ngl + wpb - 1) / wpb);
-    prof_begin(PROF_VXC_VB, st);
-    if (vgrad)
-        vxc_vb_sb_kernel<4><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
-    else
-        vxc_vb_sb_kernel<1><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
-    prof_end(st);
-    QC_LAUNCHED(1);
     dim3 gs((unsigned)(max_nsp / 64), (unsigned)nsb);
-    prof_begin(PROF_I8_SLICE, st);
-    sb_slice_kernel<S, BN><<<gs, 256, 0, st>>>(sbd, vb, vb_off, 0, sbp, b_off, bplanes, bscale);
-    prof_end(st);
-    QC_LAUNCHED(1);
+    if (colmax != nullptr) {
+        // K4a fused: vb is cut into the int8 planes as it is formed (block exponents from the column-maximum bound)
+        const size_t sm1 = sizeof(double) * (vgrad ? 4 : 1) * sbp;
+        prof_begin(PROF_VXC_VB, st);
+        if (vgrad)
+            vxc_vbslice_kernel<S, BN, 4><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale);
+        else
+            vxc_vbslice_kernel<S, BN, 1><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale);
+        prof_end(st);
+        QC_LAUNCHED(1);
+    } else {
+        // K4a unfused (exact column maxima): vb in fp64 (one streaming pass at the HBM roofline), then the slicer
+        const int wpb = 8;
+        const unsigned nb1 = (unsigned)((ngl + wpb - 1) / wpb);
+        prof_begin(PROF_VXC_VB, st);
+        if (vgrad)
+            vxc_vb_sb_kernel<4><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
+        else
+            vxc_vb_sb_kernel<1><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb);
+        prof_end(st);
+        QC_LAUNCHED(1);
+        prof_begin(PROF_I8_SLICE, st);
+        sb_slice_kernel<S, BN><<<gs, 256, 0, st>>>(sbd, vb, vb_off, 0, sbp, b_off, bplanes, bscale);
+        prof_end(st);
+        QC_LAUNCHED(1);
+    }
     constexpr int NSTAGE = (BN == 96) ? 3 : I8_STAGES;
     const size_t smem = (size_t)NSTAGE * S * (I8_A_PLANE + I8_KT * BN) + sizeof(double) * I8_BM * (BN + 1);
     prof_begin(PROF_VXC_GEMM, st);
@@ -516,30 +678,33 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
     return 0;
 }
 
-// Same contract as b200qc_vxc_sb, with the GEMM on tcgen05 int8 slices.  aplanes / a_off / ascale come from
-// b200qc_vxc_i8_prepare; bplanes (nslice * sum_sb sbp * ceil(nsp / bn) * bn bytes at b_off[sb], ZERO-FILLED once by the
+// Same contract as b200qc_vxc_sb, with the GEMM on tcgen05 int8 slices.  aplanes / a_off / ascale / colmax come from
+// b200qc_vxc_i8_prepare; colmax != NULL selects the fused vb slicer (vb / vb_off are then unused and may be NULL),
+// colmax == NULL the two-pass form with exact column maxima (vb: scratch of sum_sb sbp * nsp doubles); bplanes (nslice * sum_sb sbp * ceil(nsp / bn) * bn bytes at b_off[sb], ZERO-FILLED once by the
 // caller: the columns past nsp of a last N tile are never written) and bscale (sum_sb nsp) are scratch;
 // tile_off[sb] = exclusive prefix of ceil(nsp / 128) * ceil(nsp / bn) (device int32), ntiles = its total.
 extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
                                 const double *ao, const double *weights, const double *vrho, const double *vgrad,
-                                int nao, const int64_t *vb_off, double *vb, const signed char *aplanes,
-                                const int64_t *a_off, const double *ascale, signed char *bplanes,
+                                int nao, const int64_t *vb_off, double *vb, const double *colmax,
+                                const signed char *aplanes, const int64_t *a_off, const double *ascale, signed char *bplanes,
                                 const int64_t *b_off, double *bscale, int bn, const int *tile_off, int ntiles,
                                 const int *ptile_off, int nptiles, double *mat, void *stream) {
     QC_REQUIRE(sbp % I8_KT == 0 && sbp % I8_BM == 0, "superblock size must be a multiple of 128");
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
     QC_REQUIRE(bn == 64 || (bn == 96 && nslice == 5), "N tile: 64, or 96 with 5 slices");
     QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
+    QC_REQUIRE(colmax != nullptr || (vb != nullptr && vb_off != nullptr), "either colmax or the vb scratch is needed");
+    QC_REQUIRE(colmax == nullptr || sbp <= 1536, "fused vb slicer: superblock too long for its shared-memory table");
     cudaStream_t st = as_stream(stream);
     QC_CHECK(cudaMemsetAsync(mat, 0, sizeof(double) * nao * nao, st));
     if (nsb == 0) return 0;
     const SBDesc *sbd = (const SBDesc *)sbdesc;
     if (nslice == 5 && bn == 96)
-        return vxc_i8_run<5, 96>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+        return vxc_i8_run<5, 96>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, aplanes, a_off, ascale,
                                  bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
     if (nslice == 5)
-        return vxc_i8_run<5, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+        return vxc_i8_run<5, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, aplanes, a_off, ascale,
                                  bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
-    return vxc_i8_run<6, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, aplanes, a_off, ascale,
+    return vxc_i8_run<6, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, aplanes, a_off, ascale,
                              bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
 }

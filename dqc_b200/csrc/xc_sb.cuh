@@ -58,6 +58,7 @@ ao_screen_kernel(const ShellRec *__restrict__ shells, const double *__restrict__
 
 extern "C" int b200qc_ao_screen(const b200qc_basis *basis, int sh0, int sh1, const double *coords, int64_t ngrid,
                                 int sbp, double eps, int deriv, unsigned char *flags, void *stream) {
+    if (qc_require_basis_device(basis)) return 2;
     QC_REQUIRE(basis && 0 <= sh0 && sh0 < sh1 && sh1 <= basis->nbas, "bad shell range");
     QC_REQUIRE(sbp > 0 && sbp % GM_BM == 0, "superblock size must be a multiple of 128");
     if (ngrid == 0) return 0;
@@ -132,6 +133,7 @@ ao_eval_sb_kernel(const ShellRec *__restrict__ shells, const double *__restrict_
 extern "C" int b200qc_eval_gto_sb(const b200qc_basis *basis, int deriv, const double *coords, int64_t ngrid, int sbp,
                                   int nsb, const void *sbdesc, const int *shell_ids, const int *shell_col, double *ao,
                                   void *stream) {
+    if (qc_require_basis_device(basis)) return 2;
     QC_REQUIRE(basis && (deriv == 0 || deriv == 1), "bad arguments");
     QC_REQUIRE(sbp % AO_PTS == 0, "superblock size must be a multiple of 32");
     if (ngrid == 0 || nsb == 0) return 0;

@@ -22,6 +22,7 @@ one packed all-reduce in ``get_fock_2e`` (or one per call of the individual ``ge
 There is no CPU fallback: constructing this class without a CUDA device raises.
 """
 from typing import List, Optional, Tuple, Union
+import warnings
 import numpy as np
 import torch
 from dqc_b200 import _lib
@@ -65,6 +66,13 @@ class HamiltonCGTO(BaseHamilton):
             raise RuntimeError("Unknown ao parameterizer: %s. Available options are: ['qr', 'matexp']" % aoparamzer)
         self.atombases = atombases
         self.spherical = spherical
+        for ab in atombases:
+            if ab.pos.requires_grad or any(b.alphas.requires_grad or b.coeffs.requires_grad for b in ab.bases):
+                warnings.warn("atom positions / basis parameters with requires_grad=True: the B200 Fock-build kernels "
+                              "differentiate only through `dqc_b200.hamilton.intor` autograd functions (positions of "
+                              "S, T, V and the AO values); everything else in this Hamiltonian is forward-only and "
+                              "returns tensors without grad_fn", stacklevel=2)
+                break
         self.libcint_wrapper = LibcintWrapper(atombases, spherical)
         self.dtype = self.libcint_wrapper.dtype
         dev = device if device is not None else self.libcint_wrapper.device

@@ -10,27 +10,47 @@ the two solvers below (device-resident, no host round trip except the convergenc
 fixed point -- hence the energy -- is the same; only the path differs."""
 from abc import abstractmethod
 from typing import Any, Dict, Optional, Union
+import warnings
 import torch
 from dqc_b200.utils.config import config
 from dqc_b200.utils.datastruct import SpinParam
 from dqc_b200.utils.linop import EditableModule
 
-__all__ = ["SCF_QCCalc", "BaseSCFEngine", "equilibrium"]
+__all__ = ["SCF_QCCalc", "BaseSCFEngine", "equilibrium", "ConvergenceWarning"]
+
+
+class ConvergenceWarning(UserWarning):
+    """The fixed-point iteration stopped at ``maxiter`` with max|fcn(y) - y| >= f_tol (xitorch warns likewise)."""
+
+
+def _not_converged(method: str, maxiter: int, err: float, f_tol: float, info: Optional[dict]):
+    if info is not None:
+        info.update(converged=False, niter=maxiter, residual=err)
+    warnings.warn("equilibrium(method=%r) did not converge in %d iterations: max|f(y) - y| = %.3e >= f_tol = %.1e; "
+                  "the last iterate is returned" % (method, maxiter, err, f_tol), ConvergenceWarning, stacklevel=3)
 
 
 def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, f_tol: float = 1e-9,
-                alpha: float = -0.5, history: int = 8, verbose: bool = False, **unused) -> torch.Tensor:
+                alpha: float = -0.5, history: int = 8, verbose: bool = False, info: Optional[dict] = None,
+                **unused) -> torch.Tensor:
     """Solve y = fcn(y).  method "diis": Anderson/Pulay mixing of the last `history` iterates on the
     residual fcn(y) - y; "broyden1": Broyden's good method with J0 = alpha^-1 I like the reference's
-    default; "simple": y <- fcn(y).  Stops when max|fcn(y) - y| < f_tol."""
+    default; "simple": y <- fcn(y).  Stops when max|fcn(y) - y| < f_tol; when ``maxiter`` is exhausted first a
+    ``ConvergenceWarning`` is emitted and the last iterate returned.  ``info`` (a dict, optional) receives
+    ``converged``, ``niter`` and the last ``residual``."""
     y = y0
     shape = y0.shape
+    err = float("inf")
     if method == "simple":
-        for _ in range(maxiter):
+        for it in range(maxiter):
             fy = fcn(y)
-            if float((fy - y).abs().max()) < f_tol:
+            err = float((fy - y).abs().max())
+            if err < f_tol:
+                if info is not None:
+                    info.update(converged=True, niter=it + 1, residual=err)
                 return fy
             y = fy
+        _not_converged(method, maxiter, err, f_tol, info)
         return y
     if method == "broyden1":
         x = y0.reshape(-1)
@@ -48,8 +68,13 @@ def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, 
             for u, w in zip(us, vs):
                 out = out + w * torch.dot(u, v)
             return out
-        for it in range(maxiter):
-            if float(f.abs().max()) < f_tol:
+        for it in range(maxiter + 1):
+            err = float(f.abs().max())
+            if err < f_tol:
+                if info is not None:
+                    info.update(converged=True, niter=it, residual=err)
+                return x.reshape(shape)
+            if it == maxiter:
                 break
             dx = -binv(f)
             xn = x + dx
@@ -62,6 +87,7 @@ def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, 
             x, f = xn, fn
             if verbose:
                 print("broyden1 iter %3d  max|f| = %.3e" % (it, float(f.abs().max())))
+        _not_converged(method, maxiter, err, f_tol, info)
         return x.reshape(shape)
     if method != "diis":
         raise RuntimeError("Unknown equilibrium method: %s (available: diis, broyden1, simple)" % method)
@@ -73,6 +99,8 @@ def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, 
         if verbose:
             print("diis iter %3d  max|f| = %.3e" % (it, err))
         if err < f_tol:
+            if info is not None:
+                info.update(converged=True, niter=it + 1, residual=err)
             return fy
         ys.append(fy.reshape(-1))
         rs.append(r)
@@ -89,11 +117,12 @@ def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, 
         rhs[n] = -1.0
         try:
             c = torch.linalg.solve(B, rhs)[:n]
-        except Exception:
+        except torch.linalg.LinAlgError:      # singular DIIS matrix (linearly dependent residuals): restart the history
             ys, rs = ys[-1:], rs[-1:]
             y = fy
             continue
         y = (c.unsqueeze(-1) * torch.stack(ys)).sum(0).reshape(shape)
+    _not_converged(method, maxiter, err, f_tol, info)
     return y
 
 
@@ -157,10 +186,17 @@ class SCF_QCCalc(object):
         elif isinstance(dm, SpinParam) and not self._polarized:
             dm = dm.u + dm.d
         scp0 = self._engine.dm2scp(dm)
-        scp = equilibrium(self._engine.scp2scp, scp0, **fwd)
+        self.scf_info: Dict[str, Any] = {}
+        scp = equilibrium(self._engine.scp2scp, scp0, info=self.scf_info, **fwd)
         self._dm = self._engine.scp2dm(scp)
         self._has_run = True
         return self
+
+    @property
+    def converged(self) -> bool:
+        """False when the last ``run`` stopped at ``maxiter`` (a ConvergenceWarning was emitted then)."""
+        assert self._has_run, "run() must be called first"
+        return bool(self.scf_info.get("converged", False))
 
     def energy(self) -> torch.Tensor:
         assert self._has_run, "run() must be called first"

@@ -86,7 +86,15 @@ class Mol(BaseSystem):
         if method is None:
             method = "coulomb"
         if auxbasis is None:
-            auxbasis = "cc-pvtz-jkfit"   # the reference's default (mol.py:190-192); must be embedded to be used
+            # the reference's default is "cc-pvtz-jkfit" (mol.py:190-192), fetched from basis_set_exchange; it is not
+            # embedded here (no network), so the default falls back to the shipped even-tempered set -- loudly,
+            # because density-fitted numbers then differ from the reference's defaults at the 1e-4 Ha level
+            from dqc_b200.api.loadbasis import has_basis
+            auxbasis = "cc-pvtz-jkfit"
+            if not all(has_basis(int(z), auxbasis) for z in self._atomzs_int):
+                warnings.warn("auxbasis 'cc-pvtz-jkfit' (the reference's default) is not embedded; using the shipped "
+                              "even-tempered 'etb-jfit' set instead -- pass auxbasis explicitly to silence this")
+                auxbasis = "etb-jfit"
         auxbasis_lst = _parse_basis(self._atomzs_int, auxbasis)
         atomaux = [AtomCGTOBasis(atomz=ab.atomz, bases=bas, pos=ab.pos)
                    for (ab, bas) in zip(self._atombases, auxbasis_lst)]

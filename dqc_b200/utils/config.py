@@ -21,8 +21,13 @@ class _Config:
     VXC_I8_BN: int = int(os.environ.get("B200QC_VXC_I8_BN", "96"))
     # density GEMM (K2) on tcgen05 the same way: 0 = off (fp64 DMMA), 5 or 6 slices
     RHO_I8_SLICES: int = int(os.environ.get("B200QC_RHO_I8", "5"))
-    # N tile of that GEMM: 64, or 96 (only with 5 slices)
-    RHO_I8_BN: int = int(os.environ.get("B200QC_RHO_I8_BN", "64"))
+    # form of that GEMM: 128 = point-stationary kernel (rows of the sliced density on the TMEM lanes, 64 grid points
+    # per tile whose phi planes stay in shared memory); 64, or 96 (only with 5 slices) = the round-1 kernel with the
+    # 128-row phi tile streamed once per N tile
+    RHO_I8_BN: int = int(os.environ.get("B200QC_RHO_I8_BN", "128"))
+    # K4 operand preparation: 1 = vb = w (v phi + 2 g . grad phi) is cut into the int8 planes in the pass that forms
+    # it, block exponents from a column-maximum bound; 0 = fp64 vb written to HBM, exact maxima, second slicing pass
+    VXC_FUSED_VB: bool = os.environ.get("B200QC_VXC_FUSED_VB", "1") != "0"
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
     # experimental scheduling of the tcgen05 XC kernels (bit mask, default 0; all measured slower or equal, DESIGN.md
     # section 7): 1 = L2 evict_last hint on the K2 A planes, 2 = K4 in 2-CTA clusters with multicast A stages

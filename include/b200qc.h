@@ -37,6 +37,10 @@ int b200qc_profile_read(double *h_ms_total, int64_t *h_counts);
 /* measured fp64 tensor-pipe (DMMA m8n8k4) peak of this device in TFLOP/s: the roofline
  * denominator of K2 / K4 (MEASURED_PEAKS.json has no fp64 entry).  scratch: >= 1 double (device) */
 int b200qc_peak_fp64_dmma(int iters, double *scratch, double *h_tflops, void *stream);
+/* measured tcgen05.mma.kind::i8 issue-rate peak of this device in TOP/s (2 ops per multiply-add; one CTA per SM,
+ * M = 128, N = 256, K = 32 MMAs on resident shared-memory operands): the denominator of the int8 (sliced fp64)
+ * tensor rooflines -- bench.py measures it in-process instead of assuming 2 x the bf16 figure. */
+int b200qc_peak_i8_mma(int iters, double *h_tops, void *stream);
 
 /* ---- basis / tables ------------------------------------------------------------------ */
 /* Replaces the (atm, bas, env) argument pack every dqclibs call receives
@@ -127,14 +131,19 @@ int b200qc_vxc_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *
  * ceil(nsp / 128) * ceil(nsp / bn) output tiles per superblock, ntiles their total (the GEMM is one persistent
  * CTA per SM walking that list).  bn = N tile: 64, or 96 with nslice = 5 (tcgen05.mma re-reads both operands from
  * shared memory per instruction: the wider tile with one slice less moves 42 % fewer bytes per unit of work);
- * bplanes then holds nslice * sbp * ceil(nsp / bn) * bn bytes per superblock, zero-filled once by the caller. */
-int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const double *ao,
-                          const int64_t *a_off, signed char *aplanes, double *ascale, void *stream);
+ * bplanes then holds nslice * sbp * ceil(nsp / bn) * bn bytes per superblock, zero-filled once by the caller.
+ * colmax (sum_sb nsp * ncomp doubles, ncomp = 1 or 4 components of `ao`; optional) receives max_g |ao_c[g][col]| per
+ * superblock column; passing it to b200qc_vxc_sb_i8 selects the FUSED operand preparation: vb = w (v phi + 2 g . grad
+ * phi) is cut into the int8 planes in the pass that forms it, with block exponents from the bound
+ * max|w v| colmax_0 + sum_d max|2 w g_d| colmax_d instead of the exact column maxima (vb never goes to HBM in fp64;
+ * vb / vb_off may then be NULL).  colmax = NULL: two passes with exact maxima through the fp64 scratch vb. */
+int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, int ncomp, const double *ao,
+                          const int64_t *a_off, signed char *aplanes, double *ascale, double *colmax, void *stream);
 int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx, const double *ao,
                      const double *weights, const double *vrho, const double *vgrad, int nao, const int64_t *vb_off,
-                     double *vb, const signed char *aplanes, const int64_t *a_off, const double *ascale,
-                     signed char *bplanes, const int64_t *b_off, double *bscale, int bn, const int *tile_off, int ntiles,
-                     const int *ptile_off, int nptiles, double *mat, void *stream);
+                     double *vb, const double *colmax, const signed char *aplanes, const int64_t *a_off,
+                     const double *ascale, signed char *bplanes, const int64_t *b_off, double *bscale, int bn,
+                     const int *tile_off, int ntiles, const int *ptile_off, int nptiles, double *mat, void *stream);
 /* Scheduling switches of the tcgen05 kernels (bit mask; default 0): 1 = L2 evict_last hint on the re-used A planes
  * of K2; 2 = K4 in 2-CTA thread-block clusters, every A stage fetched half by each CTA and multicast to both (the
  * pair works on two N tiles of one M tile; needs ptile_off / nptiles = exclusive prefix and total of
@@ -152,9 +161,13 @@ int b200qc_i8_debug_variant(int v);
  * epilogue.  prepare slices the static AO values row-wise once: aplanes = sum_sb nslice * sbp * nsp bytes at
  * a_off[sb], rscale = nsb * sbp doubles.  bplanes (sum_sb nslice * nsp * ceil(nsp / bn) * bn bytes at b_off[sb],
  * zero-filled once by the caller) and cscale (sum_sb nsp doubles) are per-call scratch for the gathered, sliced
- * density.  bn = N tile: 64, or 96 with nslice = 5 (the A tile of a unit is streamed once per N tile). */
-int b200qc_rho_i8_prepare(const void *sbdesc, int nsb, int sbp, int nslice, const double *ao, const int64_t *a_off,
-                          signed char *aplanes, double *rscale, void *stream);
+ * density.  bn = row tile of the sliced density.  bn = 128 (default): point-stationary kernel -- M = 128 density rows,
+ * N = 64 grid points whose phi planes (prepare with row_tile = 64) stay in shared memory for the whole unit, so every
+ * plane is read from HBM once; the fp64 AO values of the epilogue are read coalesced and the row sums are formed by a
+ * fixed-order warp reduce-scatter (bitwise reproducible).  bn = 64, or 96 with nslice = 5: the round-1 kernel (prepare
+ * with row_tile = 128; the 128-row phi tile is streamed once per N tile). */
+int b200qc_rho_i8_prepare(const void *sbdesc, int nsb, int sbp, int nslice, int row_tile, const double *ao,
+                          const int64_t *a_off, signed char *aplanes, double *rscale, void *stream);
 int b200qc_rho_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx, const double *ao,
                      const double *dm, int nao, const signed char *aplanes, const int64_t *a_off,
                      const double *rscale, signed char *bplanes, const int64_t *b_off, double *cscale, int bn,

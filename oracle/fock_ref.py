@@ -35,9 +35,8 @@ class RefHamilton:
         self.shl = (s0, s1)
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64)
         sl2 = (s0, s1, s0, s1)
+        self._t, self._sl2 = t, sl2
         self.S = t(cint.int1e("ovlp", atm, bas, env, sl2))
-        self.T = t(cint.int1e("kin", atm, bas, env, sl2))
-        self.V = t(cint.int1e("nuc", atm, bas, env, sl2))
         ev, evec = torch.linalg.eigh(self.S)
         if orthozer:
             keep = ev > 1e-6
@@ -47,10 +46,29 @@ class RefHamilton:
         self.orthozer = orthozer
         self.nao = self.X.shape[1]
         self.olp_mat = self.S if not orthozer else self.conv2(self.S)
-        self.kinnucl_mat = self.conv2(self.T + self.V)
+        self._kinnucl = None
         self.el_mat = None
         self.j3c = None
         self.aux = auxwrapper
+
+    # T and V are built on first use: the grid-only checks at the C60 / taxol sizes never need them
+    @property
+    def T(self):
+        if not hasattr(self, "_T"):
+            self._T = self._t(cint.int1e("kin", self.atm, self.bas, self.env, self._sl2))
+        return self._T
+
+    @property
+    def V(self):
+        if not hasattr(self, "_V"):
+            self._V = self._t(cint.int1e("nuc", self.atm, self.bas, self.env, self._sl2))
+        return self._V
+
+    @property
+    def kinnucl_mat(self):
+        if self._kinnucl is None:
+            self._kinnucl = self.conv2(self.T + self.V)
+        return self._kinnucl
 
     # ---- build ----
     def build_eri(self):
