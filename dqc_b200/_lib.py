@@ -73,7 +73,7 @@ _SIGS = {
     "b200qc_vxc_sb_i8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_i8_debug_variant": (ctypes.c_int, [ctypes.c_int]),
@@ -724,8 +724,11 @@ class GridBlocks(object):
             self.ascale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
             self.bscale = torch.empty(int(nsp.sum()), dtype=torch.float64, device=dev)
             # fused operand preparation (vb cut into int8 planes as it is formed): static column maxima per superblock
-            self.colmax = torch.empty(int(nsp.sum()) * self.ncomp, dtype=torch.float64, device=dev) \
+            self.colmax = torch.empty(int(nsp.sum()) * (self.sbp // 32) * self.ncomp, dtype=torch.float32, device=dev) \
                 if (_cfg.VXC_FUSED_VB and self.sbp <= 1536) else None
+            # ... and the per-call flags of the 64-column blocks whose bound came out loose (cut again with exact exponents)
+            self.fixflag = torch.zeros(self.nsb * (self.max_nsp // 64), dtype=torch.int32, device=dev) \
+                if self.colmax is not None else None
             _check(lib.b200qc_vxc_i8_prepare(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, S, self.ncomp,
                                              _ptr(self.ao), _ptr(self.d_a_off), _ptr(self.aplanes), _ptr(self.ascale),
                                              _ptr(self.colmax), _stream()),
@@ -790,7 +793,8 @@ class GridBlocks(object):
             _check(lib.b200qc_vxc_sb_i8(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, self.i8_slices,
                                         _ptr(self.d_idx), _ptr(self.ao), _ptr(self.w), _ptr(vrho.contiguous()),
                                         _ptr(vgrad), self.nao, _ptr(self.d_vb_off), _ptr(None if fused else self.vb),
-                                        _ptr(self.colmax if fused else None), _ptr(self.aplanes),
+                                        _ptr(self.colmax if fused else None), _ptr(self.fixflag if fused else None),
+                                        _ptr(self.aplanes),
                                         _ptr(self.d_a_off), _ptr(self.ascale), _ptr(self.bplanes), _ptr(self.d_b_off),
                                         _ptr(self.bscale), self.i8_bn, _ptr(self.d_tile_off), self.ntiles, _ptr(self.d_ptile_off),
                                         self.nptiles, _ptr(mat), _stream()),

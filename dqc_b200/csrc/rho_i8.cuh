@@ -18,8 +18,11 @@
 #define RI8_STAGES 5      // no staging tile here: 5-stage ring (3..5 measure the same; 7 starves L1)
 
 // ---- phi rows -> S int8 planes, K-major tiles of RT grid rows; scale per grid row ----
-// RT = 128: the A operand (M tile) of rho_i8_kernel; RT = 64: the stationary B operand (N tile) of rho_i8_ps_kernel
-// out (per SB, bytes): [row tile = g / RT][k tile = mu / 32][slice][(mu % 32) / 16][(g % RT) / 8][g % 8][mu % 16]
+// RT = 128: the A operand (M tile) of rho_i8_kernel
+//   out (per SB, bytes): [row tile = g / 128][k tile = mu / 32][slice][(mu % 32) / 16][(g % 128) / 8][g % 8][mu % 16]
+// RT = 64: the stationary B operand (N tile) of rho_i8_ps_kernel, slices INSIDE the K chunk so that consecutive slices
+// of the 64 rows form one K-major operand of 64 n rows (rho_i8_ps.cuh, "concatenated B slices")
+//   out (per SB, bytes): [row tile = g / 64][k tile = mu / 32][(mu % 32) / 16][slice][(g % 64) / 8][g % 8][mu % 16]
 template <int S, int RT>
 __global__ void __launch_bounds__(256)
 sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp,
@@ -44,11 +47,13 @@ sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ 
     signed char *P = planes + p_off[sb] + (int64_t)(g / RT) * nkt * S * PLANE + ((g % RT) >> 3) * 128 + (g & 7) * 16;
     for (int c = lane; c < d.nsp; c += 32) {
         double y = X[c] * inv;
-        signed char *Q = P + (int64_t)(c >> 5) * S * PLANE + ((c & 31) >> 4) * (RT * 16) + (c & 15);
+        // byte strides of the K chunk and of the slice inside a K tile
+        constexpr int KC = (RT == 64) ? S * RT * 16 : RT * 16, SL = (RT == 64) ? RT * 16 : PLANE;
+        signed char *Q = P + (int64_t)(c >> 5) * S * PLANE + ((c & 31) >> 4) * KC + (c & 15);
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const double q = rint(y);
-            Q[s * PLANE] = (signed char)(int)q;
+            Q[s * SL] = (signed char)(int)q;
             y = (y - q) * 128.0;
         }
     }

@@ -35,8 +35,19 @@
 #define I8_B_PLANE (I8_KT * I8_BN)   // 2048 bytes: [4 K groups][4 MN chunks][8 rows][16 bytes]
 
 // ---- slicing: X [rows][ld] fp64 per superblock -> S int8 planes in the TILED operand order + per-column scale
-// out (per SB, bytes): [tile = col / W][k tile = row / 32][slice][(row % 32) / 8][(col % W) / 16][row % 8][col % 16]
-// with W = 128 (A operand, M tiles, zero-padded to a whole tile by the caller's memset) or 64 (B operand).
+// W = 128 (A operand, M tiles, zero-padded to a whole tile by the caller's memset), out (per SB, bytes):
+//     [tile = col / 128][k tile = row / 32][slice][(row % 32) / 8][(col % 128) / 16][row % 8][col % 16]
+// W = 96 / 64 (B operand, N tiles): the slices sit INSIDE the 8-row K group,
+//     [tile = col / W][k tile = row / 32][(row % 32) / 8][slice][(col % W) / 16][row % 8][col % 16]
+// so that the slices t0 .. t0 + n - 1 of a tile form ONE MN-major operand of n W columns: tcgen05.mma re-reads both
+// operands from shared memory for every instruction, and one MMA of N = n W (<= 256) against A slice s that updates
+// the n adjacent accumulators s + t0 .. replaces n MMAs that would each re-read the A plane.
+template <int S, int W>
+struct BPlaneLayout {
+    static constexpr int PLANE = I8_KT * W;
+    static constexpr int KG = (W == I8_BM) ? (W / 16) * 128 : S * (W / 16) * 128;   // stride of an 8-row K group
+    static constexpr int SL = (W == I8_BM) ? PLANE : (W / 16) * 128;                // stride of a slice
+};
 template <int S, int W>
 __global__ void __launch_bounds__(256)
 sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, const int64_t *__restrict__ x_off,
@@ -89,154 +100,213 @@ sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, co
                 }
             }
         }
-        signed char *Q = P + (int64_t)(r >> 5) * S * PLANE + ((r & 31) >> 3) * (W / 16) * 128 + (r & 7) * 16;
+        using L = BPlaneLayout<S, W>;
+        signed char *Q = P + (int64_t)(r >> 5) * S * PLANE + ((r & 31) >> 3) * L::KG + (r & 7) * 16;
 #pragma unroll
-        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * PLANE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * L::SL) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
     }
 }
 
 // ---- fused K4a: vb = w (v phi + 2 g . grad phi) cut straight into the B-operand planes ----
 // The slicer needs the column maxima of vb per superblock BEFORE it can cut, which is why round 1 wrote vb to HBM in
-// fp64 (4.4 GB at C60) and read it back twice.  Any upper bound of the maximum works as the block exponent -- a bound
-// that is 2^k too large costs k of the 7 S mantissa bits -- and a cheap one follows from the triangle inequality:
-//     max_g |vb_g,nu|  <=  max_g |w v| * max_g |phi_nu|  +  sum_d max_g |2 w g_d| * max_g |d_d phi_nu|
-// with the column maxima of phi / grad phi per superblock precomputed once (sb_colmax_kernel) and the four coefficient
-// maxima formed here from the 512 rows of the superblock.  One pass: reads the fp64 AO values once, writes int8.
+// fp64 (4.4 GB at C60) and read it back twice.  Here: bound, cut, verify, repair.
+//  1. Any upper bound of the maximum works as the block exponent -- a bound that is 2^k too large costs k of the 7 S
+//     mantissa bits -- and a cheap one follows from the triangle inequality, taken per group of 32 consecutive rows:
+//         max_g |vb_g,nu| <= max_groups [ max_g |w v| * max_g |phi_nu| + sum_d max_g |2 w g_d| * max_g |d_d phi_nu| ]
+//     with the per-group column maxima of phi / grad phi precomputed once (sb_colmax_kernel, fp32 rounded up: 1/64 of
+//     the AO storage) and the coefficient maxima formed here.
+//  2. One pass over the fp64 AO values forms vb and cuts it (vb never goes to HBM).  While cutting, the kernel records
+//     the LARGEST scaled value it saw per column: that is the exact column maximum, for free.
+//  3. A column whose bound turned out more than 2^VBS_LOOSE_BITS too large gets its exact exponent written to `scales`
+//     and its 64-column block flagged; vxc_vbslice_kernel<.., FIX = true> then re-cuts the flagged blocks only (for a
+//     smooth potential on a molecular grid: none or a handful; for a potential that is uncorrelated from point to
+//     point -- tests/test_gpu_xcpath.py -- many).  The planes therefore never lose more than VBS_LOOSE_BITS bits
+//     against the two-pass form with exact maxima, whatever the potential.
+// Memory access: a warp reads 8 consecutive rows, lane = 2 adjacent columns -> every load instruction is one contiguous
+// 512-byte row segment (the round-2 first version, thread = 16 columns of a row, ran at 93 % L1 throughput with half
+// of every sector wasted per instruction: 4.65 ms); the int8 bytes are staged in shared memory and leave as 16-byte
+// pieces of whole 128-byte core matrices.
+#define VBS_GROUP 32
+#define VBS_LOOSE_BITS 4
+#define VBS_PHASE 64            // rows per staging phase (two K tiles)
+#define VBS_ROWB 80             // staged row: 64 bytes + 16 of padding (16-byte reads of 8 consecutive rows: no conflicts)
 
-// colmax[(idx_off + col) * NCOMP + c] = max over the superblock's rows of |ao_c[row][col]|
+// colmax[((idx_off + col) * ngroups + group) * NCOMP + c] >= max over the group's rows of |ao_c[row][col]|
 template <int NCOMP>
-__global__ void __launch_bounds__(256)
-sb_colmax_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp, double *__restrict__ colmax) {
+__global__ void __launch_bounds__(64 * NCOMP)
+sb_colmax_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp, float *__restrict__ colmax) {
     const SBDesc d = sbd[blockIdx.y];
     const int c0 = blockIdx.x * 64;
     if (c0 >= d.nsp) return;
-    const int col = c0 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+    const int col = c0 + (threadIdx.x & 63), c = threadIdx.x >> 6;
     const int64_t ld = d.nsp;
-    __shared__ double smax[4][64];
-#pragma unroll
-    for (int c = 0; c < NCOMP; c++) {
-        const double *X = ao + d.ao_off + (int64_t)c * sbp * ld;
+    const int ngroups = sbp / VBS_GROUP;
+    const double *X = ao + d.ao_off + (int64_t)c * sbp * ld + col;
+    for (int grp = 0; grp < ngroups; grp++) {
         double m = 0.0;
-        for (int r = rg; r < sbp; r += 4) m = fmax(m, fabs(X[(int64_t)r * ld + col]));
-        smax[rg][threadIdx.x & 63] = m;
-        __syncthreads();
-        if (rg == 0)
-            colmax[(int64_t)(d.idx_off + col) * NCOMP + c] =
-                fmax(fmax(smax[0][col - c0], smax[1][col - c0]), fmax(smax[2][col - c0], smax[3][col - c0]));
-        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < VBS_GROUP; r++) m = fmax(m, fabs(X[(int64_t)(grp * VBS_GROUP + r) * ld]));
+        colmax[((int64_t)(d.idx_off + col) * ngroups + grp) * NCOMP + c] = __double2float_ru(m);
     }
 }
 
-// planes: the B operand of vxc_i8_gemm_kernel, same tiled order as sb_slice_kernel<S, W> writes:
-// [tile = col / W][k tile = row / 32][slice][(row % 32) / 8][(col % W) / 16][row % 8][col % 16]
-template <int S, int W, int NCOMP>
-__global__ void __launch_bounds__(256)
+// planes: the B operand of vxc_i8_gemm_kernel in the order sb_slice_kernel<S, W> writes (BPlaneLayout<S, W>).
+// fixflag[sb * gridDim.x + column block]: written by the FIX = false pass (1 = re-cut this block), read by FIX = true.
+template <int S, int W, int NCOMP, bool FIX>
+__global__ void __launch_bounds__(256, 2)
 vxc_vbslice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp, int64_t ngrid_ld,
                    const double *__restrict__ w, const double *__restrict__ vrho, const double *__restrict__ vgrad,
-                   const double *__restrict__ colmax, const int64_t *__restrict__ p_off, signed char *__restrict__ planes,
-                   double *__restrict__ scales) {
-    extern __shared__ double vbs_smem[];          // coef[NCOMP][sbp]
-    __shared__ double wmax[8][NCOMP], sinv[64];
+                   const float *__restrict__ colmax, const int64_t *__restrict__ p_off, signed char *__restrict__ planes,
+                   double *__restrict__ scales, int *__restrict__ fixflag) {
+    extern __shared__ __align__(16) unsigned char vbs_raw[];
+    // coef[NCOMP][sbp], wmax[ngroups][NCOMP] (doubles), then the staging tile [S][VBS_PHASE][VBS_ROWB] bytes
+    __shared__ double sinv[64], bpart[4][64];
+    __shared__ float obs[8][64];
+    __shared__ int anyfix;
     const int sb = blockIdx.y;
     const SBDesc d = sbd[sb];
     const int c0 = blockIdx.x * 64;
     if (c0 >= d.nsp) return;
+    if (FIX && fixflag[sb * gridDim.x + blockIdx.x] == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *coef = vbs_smem;
-    // 1. the row coefficients of this superblock and their maxima
-    double m[NCOMP];
-#pragma unroll
-    for (int c = 0; c < NCOMP; c++) m[c] = 0.0;
-    for (int r = tid; r < sbp; r += 256) {
+    const int ngroups = sbp / VBS_GROUP;
+    double *coef = reinterpret_cast<double *>(vbs_raw), *wmax = coef + NCOMP * sbp;
+    unsigned char *stage = reinterpret_cast<unsigned char *>(wmax + NCOMP * ngroups);
+    // 1. the row coefficients of this superblock; a warp handles whole 32-row groups and leaves their maxima
+    for (int grp = warp; grp < ngroups; grp += 8) {
+        const int r = grp * VBS_GROUP + lane;
         const int64_t g = (int64_t)sb * sbp + r;
         const double wg = w[g];
+        double m[NCOMP];
         double cf = wg * vrho[g];
         coef[r] = cf;
-        m[0] = fmax(m[0], fabs(cf));
+        m[0] = fabs(cf);
         if (NCOMP == 4) {
 #pragma unroll
             for (int dd = 0; dd < 3; dd++) {
                 cf = 2.0 * wg * vgrad[(int64_t)dd * ngrid_ld + g];
                 coef[(dd + 1) * sbp + r] = cf;
-                m[dd + 1] = fmax(m[dd + 1], fabs(cf));
+                m[dd + 1] = fabs(cf);
+            }
+        }
+        if (!FIX) {
+#pragma unroll
+            for (int c = 0; c < NCOMP; c++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m[c] = fmax(m[c], __shfl_xor_sync(0xffffffffu, m[c], o));
+                if (lane == 0) wmax[grp * NCOMP + c] = m[c];
             }
         }
     }
-#pragma unroll
-    for (int c = 0; c < NCOMP; c++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m[c] = fmax(m[c], __shfl_xor_sync(0xffffffffu, m[c], o));
-        if (lane == 0) wmax[warp][c] = m[c];
-    }
+    if (tid == 0) anyfix = 0;
     __syncthreads();
-    // 2. bound of the column maxima -> block exponents of the 64 columns of this CTA
-    if (tid < 64) {
-        const int col = c0 + tid;
+    if (FIX) {
+        // the exponents are final: exact for the columns the first pass found loose, the (tight) bound for the others
+        if (tid < 64) sinv[tid] = 64.0 / scales[d.idx_off + c0 + tid];
+    } else {
+        // 2. bound of the column maxima -> block exponents of the 64 columns of this CTA (4 threads per column, each a
+        //    quarter of the row groups)
+        const int col = c0 + (tid & 63), part = tid >> 6;
+        const float *cm = colmax + (int64_t)(d.idx_off + col) * ngroups * NCOMP;
         double b = 0.0;
+        for (int grp = part; grp < ngroups; grp += 4) {
+            double t = 0.0;
 #pragma unroll
-        for (int c = 0; c < NCOMP; c++) {
-            double a = 0.0;
-#pragma unroll
-            for (int q = 0; q < 8; q++) a = fmax(a, wmax[q][c]);
-            b += a * colmax[(int64_t)(d.idx_off + col) * NCOMP + c];
+            for (int c = 0; c < NCOMP; c++) t += wmax[grp * NCOMP + c] * (double)cm[grp * NCOMP + c];
+            b = fmax(b, t);
         }
-        int e = 0;
-        if (b > 0.0) frexp(b, &e);              // b = f 2^e, f in [0.5, 1)  =>  |vb| / 2^e < 1
-        sinv[tid] = ldexp(64.0, -e);
-        scales[d.idx_off + col] = ldexp(1.0, e);
+        bpart[part][tid & 63] = b;
+        __syncthreads();
+        if (tid < 64) {
+            const double bb = fmax(fmax(bpart[0][tid], bpart[1][tid]), fmax(bpart[2][tid], bpart[3][tid])) * (1.0 + 1e-12);
+            int e = 0;
+            if (bb > 0.0) frexp(bb, &e);            // bb = f 2^e, f in [0.5, 1)  =>  |vb| / 2^e < 1
+            sinv[tid] = ldexp(64.0, -e);
+        }
     }
     __syncthreads();
-    // 3. a thread owns 16 consecutive columns of one row: 128 contiguous bytes per component in, one 16-byte store
-    //    per slice out
-    constexpr int PLANE = I8_KT * W;
+    // 3. cut.  Warp = 8 consecutive rows (one K row group) of a 64-row phase, lane = columns c0 + 2 lane, + 1.
+    using L = BPlaneLayout<S, W>;
+    constexpr int PLANE = L::PLANE;
     const int nk = sbp / I8_KT;
     const int64_t ld = d.nsp, cs = (int64_t)sbp * ld;
-    const int cg = tid & 3;
-    const int cq = c0 + cg * 16;
-    const int tile = cq / W, wc = cq % W;
-    signed char *P = planes + p_off[sb] + (int64_t)tile * nk * S * PLANE + (wc >> 4) * 128;
-    for (int r = tid >> 2; r < sbp; r += 64) {
-        double acc[16];
-        {
-            const double cf = coef[r];
-            const double *src = ao + d.ao_off + (int64_t)r * ld + cq;
+    const double si0 = sinv[2 * lane], si1 = sinv[2 * lane + 1];
+    const double *src0 = ao + d.ao_off + c0 + 2 * lane;
+    float mo0 = 0.f, mo1 = 0.f;                     // largest |scaled value| seen: the exact column maxima
+    for (int r0 = 0; r0 < sbp; r0 += VBS_PHASE) {
+        // (two half-groups of 4 rows: 16 independent 16-byte loads in flight per thread at 128 registers)
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                const double2 v = *reinterpret_cast<const double2 *>(src + j);
-                acc[j] = cf * v.x;
-                acc[j + 1] = cf * v.y;
-            }
-        }
-        if (NCOMP == 4) {
+        for (int hf = 0; hf < 2; hf++) {
+            const int rw = r0 + warp * 8 + hf * 4;
+            double2 v[NCOMP][4];
 #pragma unroll
-            for (int c = 1; c < 4; c++) {
-                const double cf = coef[c * sbp + r];
-                const double *src = ao + d.ao_off + c * cs + (int64_t)r * ld + cq;
+            for (int c = 0; c < NCOMP; c++)
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(src + j);
-                    acc[j] += cf * v.x;
-                    acc[j + 1] += cf * v.y;
+                for (int j = 0; j < 4; j++)
+                    v[c][j] = *reinterpret_cast<const double2 *>(src0 + c * cs + (int64_t)(rw + j) * ld);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double y0 = coef[rw + j] * v[0][j].x, y1 = coef[rw + j] * v[0][j].y;
+                if (NCOMP == 4) {
+#pragma unroll
+                    for (int c = 1; c < 4; c++) {
+                        const double cf = coef[c * sbp + rw + j];
+                        y0 += cf * v[c][j].x;
+                        y1 += cf * v[c][j].y;
+                    }
+                }
+                y0 *= si0;
+                y1 *= si1;
+                if (!FIX) {
+                    mo0 = fmaxf(mo0, __double2float_ru(fabs(y0)));
+                    mo1 = fmaxf(mo1, __double2float_ru(fabs(y1)));
+                }
+                unsigned char *q = stage + (warp * 8 + hf * 4 + j) * VBS_ROWB + 2 * lane;
+#pragma unroll
+                for (int sl = 0; sl < S; sl++) {
+                    const double q0 = rint(y0), q1 = rint(y1);
+                    *reinterpret_cast<unsigned short *>(q + sl * (VBS_PHASE * VBS_ROWB)) =
+                        (unsigned short)(((unsigned int)(int)q0 & 0xffu) | (((unsigned int)(int)q1 & 0xffu) << 8));
+                    y0 = (y0 - q0) * 128.0;
+                    y1 = (y1 - q1) * 128.0;
                 }
             }
         }
-        unsigned int q4[S][4];
-#pragma unroll
-        for (int s = 0; s < S; s++) q4[s][0] = q4[s][1] = q4[s][2] = q4[s][3] = 0u;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            double y = acc[j] * sinv[cg * 16 + j];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const double q = rint(y);
-                q4[s][j >> 2] |= ((unsigned int)(int)q & 0xffu) << (8 * (j & 3));
-                y = (y - q) * 128.0;
-            }
+        __syncthreads();
+        // the phase leaves as 16-byte pieces; 8 consecutive threads write one 128-byte core matrix
+        // piece = (((k tile of the phase * 4 + K row group) * S + slice) * 4 + 16-column chunk) * 8 + row % 8
+        for (int pc = tid; pc < (VBS_PHASE / 8) * S * 4 * 8; pc += 256) {
+            const int r8 = pc & 7, ch = (pc >> 3) & 3, t = pc >> 5;
+            const int sl = t % S, kg = t / S;                        // kg = 8-row group inside the phase (0..7)
+            const uint4 val = *reinterpret_cast<const uint4 *>(stage + sl * (VBS_PHASE * VBS_ROWB) + (kg * 8 + r8) * VBS_ROWB + ch * 16);
+            const int cq = c0 + ch * 16, tile = cq / W, wc = cq % W;
+            const int r = r0 + kg * 8 + r8;
+            signed char *Q = planes + p_off[sb] + (int64_t)tile * nk * S * PLANE + (int64_t)(r >> 5) * S * PLANE +
+                             ((r & 31) >> 3) * L::KG + sl * L::SL + (wc >> 4) * 128 + r8 * 16;
+            *reinterpret_cast<uint4 *>(Q) = val;
         }
-        signed char *Q = P + (int64_t)(r >> 5) * S * PLANE + ((r & 31) >> 3) * (W / 16) * 128 + (r & 7) * 16;
-#pragma unroll
-        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * PLANE) = make_uint4(q4[s][0], q4[s][1], q4[s][2], q4[s][3]);
+        __syncthreads();
     }
+    if (FIX) return;
+    // 4. verify the bound against the maxima actually seen; exact exponents for the loose columns
+    obs[warp][2 * lane] = mo0;
+    obs[warp][2 * lane + 1] = mo1;
+    __syncthreads();
+    if (tid < 64) {
+        float mo = obs[0][tid];
+#pragma unroll
+        for (int q = 1; q < 8; q++) mo = fmaxf(mo, obs[q][tid]);
+        double sc = 64.0 / sinv[tid];                                // 2^e of the bound
+        if (mo > 0.f && (mo < ldexpf(64.f, -VBS_LOOSE_BITS) || mo >= 64.f)) {
+            int e = 0;
+            frexp((double)mo * (1.0 + 1e-6) / sinv[tid], &e);        // (mo is rounded up already; margin for the fp32 step)
+            sc = ldexp(1.0, e);
+            anyfix = 1;
+        }
+        scales[d.idx_off + c0 + tid] = sc;
+    }
+    __syncthreads();
+    if (tid == 0) fixflag[sb * gridDim.x + blockIdx.x] = anyfix;
 }
 
 // ---- tcgen05 plumbing (PTX spellings as in the CUTLASS sm100 headers) ----
@@ -417,10 +487,11 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
     static_assert(S * BN <= 512, "accumulators exceed the tensor memory");
     constexpr int B_PLANE = I8_KT * BN, NSTAGE = (BN == 96) ? 3 : I8_STAGES, EPI_LD = BN + 1;
     constexpr int A_STAGE = S * I8_A_PLANE, B_STAGE = S * B_PLANE, STAGE = A_STAGE + B_STAGE;
-    constexpr uint32_t LBO_A = (I8_BM / 16) * 128, LBO_B = (BN / 16) * 128;   // stride between 8-row K groups
-    // instruction descriptor: D = S32, A = B = signed int8, both MN-major, N = BN, M = 128 (dense)
-    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(I8_BM >> 4) << 24);
+    constexpr uint32_t LBO_A = (I8_BM / 16) * 128, LBO_B = BPlaneLayout<S, BN>::KG;   // stride between 8-row K groups
+    constexpr int B_SL = BPlaneLayout<S, BN>::SL;                             // stride between the slices of a K group
+    constexpr int NCAT = 256 / BN;                                            // B slices one MMA can take (N <= 256)
+    // instruction descriptor without N: D = S32, A = B = signed int8, both MN-major, M = 128 (dense)
+    constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(I8_BM >> 4) << 24);
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -519,12 +590,17 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
                     if (variant != 2 && active) {      // (variant 2: timing experiment without the MMAs)
+                    // A slice s2 against the B slices t0 .. t0 + n - 1 (one operand of n BN columns) -> the adjacent
+                    // accumulators s2 + t0 .. s2 + t0 + n - 1
 #pragma unroll
-                    for (int dd = 0; dd < S; dd++)
+                    for (int s2 = 0; s2 < S; s2++)
 #pragma unroll
-                        for (int s2 = 0; s2 <= dd; s2++)
-                            umma_i8(tmem + dd * BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
-                                    db + (uint64_t)(((dd - s2) * B_PLANE) >> 4), IDESC, (kt > 0 || s2 > 0) ? 1u : 0u);
+                        for (int t0 = 0; t0 < S - s2; t0 += NCAT) {
+                            const int n = (S - s2 - t0) < NCAT ? (S - s2 - t0) : NCAT;
+                            umma_i8(tmem + (s2 + t0) * BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                    db + (uint64_t)((t0 * B_SL) >> 4), IDESC0 | ((uint32_t)((n * BN) >> 3) << 17),
+                                    (kt > 0 || s2 > 0) ? 1u : 0u);
+                        }
                     }
                     // frees the stage (in both CTAs of a pair) when the MMAs above retire
                     if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3); else umma_commit(&empty_bar[slot]);
@@ -603,16 +679,16 @@ vxc_i8_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ tile_
 // a_off[sb]: byte offset of the SB's block; ascale: sum_sb nsp doubles.
 extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, int ncomp,
                                      const double *ao, const int64_t *a_off, signed char *aplanes, double *ascale,
-                                     double *colmax, void *stream) {
+                                     float *colmax, void *stream) {
     QC_REQUIRE(nslice == 5 || nslice == 6, "nslice must be 5 or 6");
     QC_REQUIRE(sbp % I8_KT == 0, "superblock size must be a multiple of 32");
     QC_REQUIRE(ncomp == 1 || ncomp == 4, "ncomp must be 1 or 4");
     if (nsb == 0) return 0;
     dim3 grid((unsigned)(max_nsp / 64), (unsigned)nsb);
     const SBDesc *sbd = (const SBDesc *)sbdesc;
-    if (colmax != nullptr) {    // static column maxima of phi (and grad phi) per superblock: the fused vb slicer's bound
+    if (colmax != nullptr) {    // static column maxima of phi (and grad phi) per 32-row group: the fused vb slicer's bound
         if (ncomp == 4) sb_colmax_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, colmax);
-        else sb_colmax_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(sbd, ao, sbp, colmax);
+        else sb_colmax_kernel<1><<<grid, 64, 0, as_stream(stream)>>>(sbd, ao, sbp, colmax);
         QC_LAUNCHED(1);
     }
     if (nslice == 5)
@@ -626,22 +702,32 @@ extern "C" int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int m
 template <int S, int BN>
 static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
                       const double *weights, const double *vrho, const double *vgrad, double *vb,
-                      const int64_t *vb_off, const double *colmax, const signed char *aplanes, const int64_t *a_off,
-                      const double *ascale,
+                      const int64_t *vb_off, const float *colmax, int *fixflag, const signed char *aplanes,
+                      const int64_t *a_off, const double *ascale,
                       signed char *bplanes, const int64_t *b_off, double *bscale, const int *tile_off, int ntiles,
                       const int *ptile_off, int nptiles, int nao, double *mat, cudaStream_t st) {
     const int64_t ngl = (int64_t)nsb * sbp;
     dim3 gs((unsigned)(max_nsp / 64), (unsigned)nsb);
     if (colmax != nullptr) {
-        // K4a fused: vb is cut into the int8 planes as it is formed (block exponents from the column-maximum bound)
-        const size_t sm1 = sizeof(double) * (vgrad ? 4 : 1) * sbp;
+        // K4a fused: vb is cut into the int8 planes as it is formed (block exponents from the column-maximum bound),
+        // then the blocks whose bound was loose are cut again with their exact exponents
+        const size_t sm1 = sizeof(double) * (vgrad ? 4 : 1) * (sbp + sbp / VBS_GROUP) + (size_t)S * VBS_PHASE * VBS_ROWB;
+        if (sm1 > 40 * 1024) {       // (the kernel also has ~5 KB of static shared memory)
+            QC_CHECK(cudaFuncSetAttribute(vxc_vbslice_kernel<S, BN, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+            QC_CHECK(cudaFuncSetAttribute(vxc_vbslice_kernel<S, BN, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+            QC_CHECK(cudaFuncSetAttribute(vxc_vbslice_kernel<S, BN, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+            QC_CHECK(cudaFuncSetAttribute(vxc_vbslice_kernel<S, BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+        }
         prof_begin(PROF_VXC_VB, st);
-        if (vgrad)
-            vxc_vbslice_kernel<S, BN, 4><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale);
-        else
-            vxc_vbslice_kernel<S, BN, 1><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale);
+        if (vgrad) {
+            vxc_vbslice_kernel<S, BN, 4, false><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
+            vxc_vbslice_kernel<S, BN, 4, true><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
+        } else {
+            vxc_vbslice_kernel<S, BN, 1, false><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
+            vxc_vbslice_kernel<S, BN, 1, true><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
+        }
         prof_end(st);
-        QC_LAUNCHED(1);
+        QC_LAUNCHED(2);
     } else {
         // K4a unfused (exact column maxima): vb in fp64 (one streaming pass at the HBM roofline), then the slicer
         const int wpb = 8;
@@ -685,7 +771,7 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
 // tile_off[sb] = exclusive prefix of ceil(nsp / 128) * ceil(nsp / bn) (device int32), ntiles = its total.
 extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx,
                                 const double *ao, const double *weights, const double *vrho, const double *vgrad,
-                                int nao, const int64_t *vb_off, double *vb, const double *colmax,
+                                int nao, const int64_t *vb_off, double *vb, const float *colmax, int *fixflag,
                                 const signed char *aplanes, const int64_t *a_off, const double *ascale, signed char *bplanes,
                                 const int64_t *b_off, double *bscale, int bn, const int *tile_off, int ntiles,
                                 const int *ptile_off, int nptiles, double *mat, void *stream) {
@@ -695,16 +781,17 @@ extern "C" int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_ns
     QC_REQUIRE((int64_t)sbp * 6 * 4096 < (1LL << 31), "superblock too long for exact int32 accumulation");
     QC_REQUIRE(colmax != nullptr || (vb != nullptr && vb_off != nullptr), "either colmax or the vb scratch is needed");
     QC_REQUIRE(colmax == nullptr || sbp <= 1536, "fused vb slicer: superblock too long for its shared-memory table");
+    QC_REQUIRE(colmax == nullptr || (fixflag != nullptr && sbp % VBS_PHASE == 0), "fused vb slicer: fixflag scratch missing");
     cudaStream_t st = as_stream(stream);
     QC_CHECK(cudaMemsetAsync(mat, 0, sizeof(double) * nao * nao, st));
     if (nsb == 0) return 0;
     const SBDesc *sbd = (const SBDesc *)sbdesc;
     if (nslice == 5 && bn == 96)
-        return vxc_i8_run<5, 96>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, aplanes, a_off, ascale,
+        return vxc_i8_run<5, 96>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, fixflag, aplanes, a_off, ascale,
                                  bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
     if (nslice == 5)
-        return vxc_i8_run<5, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, aplanes, a_off, ascale,
+        return vxc_i8_run<5, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, fixflag, aplanes, a_off, ascale,
                                  bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
-    return vxc_i8_run<6, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, aplanes, a_off, ascale,
+    return vxc_i8_run<6, 64>(sbd, nsb, sbp, max_nsp, idx, ao, weights, vrho, vgrad, vb, vb_off, colmax, fixflag, aplanes, a_off, ascale,
                              bplanes, b_off, bscale, tile_off, ntiles, ptile_off, nptiles, nao, mat, st);
 }

@@ -26,13 +26,16 @@ class _Config:
     # 128-row phi tile streamed once per N tile
     RHO_I8_BN: int = int(os.environ.get("B200QC_RHO_I8_BN", "128"))
     # K4 operand preparation: 1 = vb = w (v phi + 2 g . grad phi) is cut into the int8 planes in the pass that forms
-    # it, block exponents from a column-maximum bound; 0 = fp64 vb written to HBM, exact maxima, second slicing pass
+    # it, block exponents from a column-maximum bound that is verified while cutting (loose blocks are cut again);
+    # 0 = fp64 vb written to HBM, exact maxima, second slicing pass
     VXC_FUSED_VB: bool = os.environ.get("B200QC_VXC_FUSED_VB", "1") != "0"
     I8_VARIANT: int = int(os.environ.get("B200QC_I8_VARIANT", "0"))
     # experimental scheduling of the tcgen05 XC kernels (bit mask, default 0; all measured slower or equal, DESIGN.md
     # section 7): 1 = L2 evict_last hint on the K2 A planes, 2 = K4 in 2-CTA clusters with multicast A stages
-    # (64-wide tiles only), 4 = the same for K2, 16 = K2 with the first K steps of the A tile cached in shared
-    # memory, bits 8..11 = depth of the K2 operand ring (2..8 stages, 0 = the default 5)
+    # (64-wide tiles only), 4 = the same for the round-1 K2, 16 = round-1 K2 with the first K steps of the A tile cached
+    # in shared memory, bits 8..11 = depth of the round-1 K2 operand ring (2..8 stages, 0 = the default 5);
+    # point-stationary K2: bits 12..16 = B cache slots, bits 17..18 = cluster size of the multicast D_sb stream
+    # (0 = default, 1 = no clusters, 2, 3 = clusters of four)
     I8_MODE: int = int(os.environ.get("B200QC_I8_MODE", "0"))
     # density-fitted exact exchange (two batched GEMMs on tcgen05): 5 or 6 int8 slices
     DFK_I8_SLICES: int = int(os.environ.get("B200QC_DFK_I8", "6"))

@@ -132,16 +132,20 @@ int b200qc_vxc_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *
  * CTA per SM walking that list).  bn = N tile: 64, or 96 with nslice = 5 (tcgen05.mma re-reads both operands from
  * shared memory per instruction: the wider tile with one slice less moves 42 % fewer bytes per unit of work);
  * bplanes then holds nslice * sbp * ceil(nsp / bn) * bn bytes per superblock, zero-filled once by the caller.
- * colmax (sum_sb nsp * ncomp doubles, ncomp = 1 or 4 components of `ao`; optional) receives max_g |ao_c[g][col]| per
- * superblock column; passing it to b200qc_vxc_sb_i8 selects the FUSED operand preparation: vb = w (v phi + 2 g . grad
- * phi) is cut into the int8 planes in the pass that forms it, with block exponents from the bound
- * max|w v| colmax_0 + sum_d max|2 w g_d| colmax_d instead of the exact column maxima (vb never goes to HBM in fp64;
- * vb / vb_off may then be NULL).  colmax = NULL: two passes with exact maxima through the fp64 scratch vb. */
+ * colmax (sum_sb nsp * (sbp / 32) * ncomp floats, ncomp = 1 or 4 components of `ao`; optional) receives, per superblock
+ * column and per group of 32 grid rows, an upper bound of max_g |ao_c[g][col]|; passing it to b200qc_vxc_sb_i8 selects
+ * the FUSED operand preparation: vb = w (v phi + 2 g . grad phi) is cut into the int8 planes in the pass that forms it,
+ * with block exponents from the bound max_groups [max|w v| colmax_0 + sum_d max|2 w g_d| colmax_d] instead of the exact
+ * column maxima (vb never goes to HBM in fp64; vb / vb_off may then be NULL; every factor 2 the bound is loose costs one
+ * of the 7 * nslice mantissa bits -- the slicer records the exact column maxima while it cuts, and 64-column blocks
+ * whose bound came out more than 2^4 too large are flagged in fixflag (nsb * (max_nsp / 64) ints of scratch, needed with
+ * colmax) and cut a second time with their exact exponents, so the planes never lose more than 4 bits against the
+ * two-pass form).  colmax = NULL: two passes with exact maxima through the fp64 scratch vb. */
 int b200qc_vxc_i8_prepare(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, int ncomp, const double *ao,
-                          const int64_t *a_off, signed char *aplanes, double *ascale, double *colmax, void *stream);
+                          const int64_t *a_off, signed char *aplanes, double *ascale, float *colmax, void *stream);
 int b200qc_vxc_sb_i8(const void *sbdesc, int nsb, int sbp, int max_nsp, int nslice, const int *idx, const double *ao,
                      const double *weights, const double *vrho, const double *vgrad, int nao, const int64_t *vb_off,
-                     double *vb, const double *colmax, const signed char *aplanes, const int64_t *a_off,
+                     double *vb, const float *colmax, int *fixflag, const signed char *aplanes, const int64_t *a_off,
                      const double *ascale, signed char *bplanes, const int64_t *b_off, double *bscale, int bn,
                      const int *tile_off, int ntiles, const int *ptile_off, int nptiles, double *mat, void *stream);
 /* Scheduling switches of the tcgen05 kernels (bit mask; default 0): 1 = L2 evict_last hint on the re-used A planes

@@ -259,12 +259,21 @@ def test_superblock_path_matches_dense_kernels(cuda, eps, sbp, gga):
 
 @pytest.mark.parametrize("nslice,tol", [(6, 5e-11), (5, 5e-9)])
 @pytest.mark.parametrize("gga", [False, True])
-def test_vxc_tcgen05_int8_matches_fp64_path(cuda, nslice, tol, gga):
+@pytest.mark.parametrize("fused", [False, True])
+def test_vxc_tcgen05_int8_matches_fp64_path(cuda, nslice, tol, gga, fused, monkeypatch):
     """K4 on tcgen05 (error-free sliced int8 GEMM, int32 TMEM accumulators) against the fp64 DMMA form of
-    the same contraction on a real molecular grid: the slicing error bound is ~1e-12 (6 slices) / ~1e-10 (5)."""
+    the same contraction on a real molecular grid: the slicing error bound is ~1e-12 (6 slices) / ~1e-10 (5).
+    fused = the one-pass operand preparation (vb cut into int8 planes as it is formed, exponents from a bound that
+    is verified while cutting; blocks whose bound came out more than 2^4 too large are cut again): at most 4 bits
+    (a factor 16) behind the two-pass form with exact column maxima -- on a potential that is uncorrelated from
+    point to point, the worst case for the bound."""
     from dqc_b200 import _lib
     from dqc_b200.utils import systems
+    from dqc_b200.utils.config import config as cfg
     from dqc_b200.grid.factory import get_predefined_grid
+    monkeypatch.setattr(cfg, "VXC_FUSED_VB", fused)
+    if fused:
+        tol = tol * 16
     zs, pos = systems.benzene()
     w, _ = util.make_wrapper(zs, pos.tolist(), "def2-svp")
     nb = len(w)
@@ -283,5 +292,10 @@ def test_vxc_tcgen05_int8_matches_fp64_path(cuda, nslice, tol, gga):
     m = gb.vxc_mat(vr, vg)
     scale = float(m_ref.abs().max())
     assert float((m - m_ref).abs().max()) < tol * max(scale, 1.0)
+    assert (gb.colmax is not None) == fused
     m2 = gb.vxc_mat(vr, vg)                       # repeatable (atomics order noise only)
     assert float((m - m2).abs().max()) < 1e-13 * max(scale, 1.0)
+    if fused:
+        # the repair pass did run on this potential, and only on part of the blocks
+        nfix = int(gb.fixflag.sum())
+        assert 0 < nfix < gb.fixflag.numel()
