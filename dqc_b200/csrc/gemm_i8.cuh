@@ -52,9 +52,7 @@ __device__ __forceinline__ void i8_quantise16(const double (&x)[16], double inv,
         double y = x[j] * inv;
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const double q = rint(y);
-            w[s][j >> 2] |= ((unsigned int)(int)q & 0xffu) << (8 * (j & 3));
-            y = (y - q) * 128.0;
+            w[s][j >> 2] |= ((unsigned int)slice_digit(y) & 0xffu) << (8 * (j & 3));
         }
     }
 #pragma unroll
@@ -201,9 +199,7 @@ i8_slice_dual_kernel(I8Slice2Args a) {
                 unsigned int w = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const double q = rint(y[j]);
-                    w |= ((unsigned int)(int)q & 0xffu) << (8 * j);
-                    y[j] = (y[j] - q) * 128.0;
+                    w |= ((unsigned int)slice_digit(y[j]) & 0xffu) << (8 * j);
                 }
                 *reinterpret_cast<unsigned int *>(&sm[warp][s][t * 128 + 4 * lane]) = w;
             }

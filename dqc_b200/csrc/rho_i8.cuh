@@ -52,9 +52,7 @@ sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ 
         signed char *Q = P + (int64_t)(c >> 5) * S * PLANE + ((c & 31) >> 4) * KC + (c & 15);
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const double q = rint(y);
-            Q[s * SL] = (signed char)(int)q;
-            y = (y - q) * 128.0;
+            Q[s * SL] = (signed char)slice_digit(y);
         }
     }
 }
@@ -89,16 +87,18 @@ sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict_
     if (lane == 0) cscale[d.idx_off + nu] = ldexp(1.0, e);
     const int nkt = d.nsp / I8_KT;
     constexpr int B_PLANE = I8_KT * BN;      // N tiles of BN rows (the last one zero-padded by the caller's memset)
-    signed char *P = planes + p_off[sb] + (int64_t)(nu / BN) * nkt * S * B_PLANE + ((nu % BN) >> 3) * 128 + (nu & 7) * 16;
+    // BN = 128 (the A operand of rho_i8_ps_kernel): row nu = 32 lg + 4 q + r of a tile sits at position (TMEM lane)
+    // 32 lg + q + 8 r, so that the four lanes q, q + 8, q + 16, q + 24 a thread of the epilogue drains with
+    // tcgen05.ld.16x256b are four consecutive AO columns (one 256-bit load of the fp64 AO values)
+    const int pos = (BN == I8_BM) ? ((nu % BN) & ~31) + (((nu & 31) >> 2) + 8 * (nu & 3)) : nu % BN;
+    signed char *P = planes + p_off[sb] + (int64_t)(nu / BN) * nkt * S * B_PLANE + (pos >> 3) * 128 + (pos & 7) * 16;
     for (int c = lane; c < d.nsp; c += 32) {
         const int b = ix[c];
         double y = (a < nao && b < nao) ? row[b] * inv : 0.0;
         signed char *Q = P + (int64_t)(c >> 5) * S * B_PLANE + ((c & 31) >> 4) * (BN * 16) + (c & 15);
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const double q = rint(y);
-            Q[s * B_PLANE] = (signed char)(int)q;
-            y = (y - q) * 128.0;
+            Q[s * B_PLANE] = (signed char)slice_digit(y);
         }
     }
 }

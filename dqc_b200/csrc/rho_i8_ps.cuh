@@ -15,40 +15,45 @@
 // Superblocks with more than NBC * 32 kept AOs keep the first NBC - 3 K steps of B stationary and stream the rest
 // through the last three cache slots once per M tile (from L2: the tile was just read).
 //
-// Epilogue (8 warps; TMEM lane = AO nu, warp = lane quarter x column half): the accumulators are drained to fp64
-// registers (TMEM is released to the next M tile at once), multiplied with the fp64 AO values phi_c[g][nu] -- read
-// COALESCED across the lanes (consecutive nu), unlike the row-per-thread reads of rho_i8_kernel -- and reduced over
-// nu by a butterfly reduce-scatter across the warp (fixed order, no atomics); partial sums live in registers across
-// the M tiles and meet in shared memory once per unit.
+// Epilogue (8 warps = lane quarter x column half): the accumulators are drained with tcgen05.ld.16x256b, whose
+// fragment layout gives a thread 4 AO rows x 8 points (instead of the 1 row x 32 points of .32x32b), merged exactly and
+// multiplied with the fp64 AO values phi_c[g][nu] straight into 8 x NCOMP per-thread accumulators that live across the
+// M tiles of the unit: no cross-lane traffic per M tile at all (the first version reduced 32 x 32 values over the warp
+// for every M tile -- 868 of its 2 600 instructions per thread and tile, and the kernel was bound by exactly that
+// epilogue), one butterfly reduce-scatter (fixed order, no atomics) per unit.  TMEM is released to the next M tile as
+// soon as it is in registers.
+//
+// Two things keep the tensor pipe fed (round 2):
+//  * CL-CTA clusters (CL = 1, 2, 4): the CL CTAs of a cluster work on CL consecutive point tiles of the SAME superblock,
+//    so they need the same D_sb stream; each CTA fetches 1 / CL of every A stage and multicasts it to the whole
+//    cluster (cp.async.bulk ... .multicast::cluster), the stage is released cluster-wide by a multicast
+//    tcgen05.commit.  L2 -> SM traffic of the A stream (25 GB of the 48 GB the kernel pulls at C60) divides by CL.
+//  * concatenated B slices: tcgen05.mma re-reads both operands from shared memory for every instruction.  The S
+//    planes of a B slot are laid out [K chunk][slice][row], so the slices t0 .. t0 + n - 1 of the 64 points form ONE
+//    K-major operand of N = 64 n rows and one MMA (A slice s, N = 64 n <= 256) updates the n accumulators
+//    s + t0 .. s + t0 + n - 1, which are adjacent TMEM columns: 6 MMAs per K step instead of 15 at S = 5, the same
+//    tensor time, 40 % fewer shared-memory operand bytes (54 KB instead of 90 KB per K step).
 #pragma once
 #include "rho_i8.cuh"
 
 #define RPS_BN 64          // grid points per tile (MMA N)
-#define RPS_NST 3          // A-operand (D_sb) ring depth
+#define RPS_MAXST 8        // A-operand (D_sb) ring: up to 8 stages (run-time depth: what the B cache leaves)
 #define RPS_MAXSLOT 16     // B cache slots (one K step of the 64-point tile each)
 #define RPS_STREAM 3       // slots that turn into a ring when the tile does not fit
 #define RPS_CLUSTER 2      // default cluster size of the multicast A stream
+#define RPS_DEFAULT_SLOTS 16  // default B-cache slots
 
-__device__ __forceinline__ double ldcs_f64(const double *p) {
-    double v;
-    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
+// exact int32 -> fp64 on the ALU + fp64 pipes (I2F.F64 is an XU instruction): 2^52 + 2^31 + v has v + 2^31 in its
+// low mantissa word
+__device__ __forceinline__ double i32_to_f64(int v) {
+    return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
 }
-
-// Sum of v[i] over the 32 lanes for every i in [0, 32): lane l returns the total of element l.
-// Five exchange rounds (16, 8, 4, 2, 1 elements), 31 shuffles of 64 bits; the order of the additions is fixed.
-__device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; i++) {
-            const double send = upper ? v[i] : v[i + off];
-            const double keep = upper ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
+// 16 TMEM lanes x 16 columns as two m16n8 fragments: regs 4 j + {0, 1}: (lane q, columns 8 j + 2 p + {0, 1}),
+// regs 4 j + {2, 3}: (lane q + 8, same columns), q = laneid / 4, p = laneid % 4
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
@@ -61,17 +66,17 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
                  const signed char *__restrict__ pplanes, const int64_t *__restrict__ p_off,
                  const signed char *__restrict__ dplanes, const int64_t *__restrict__ d_off,
                  const double *__restrict__ rscale, const double *__restrict__ cscale, int64_t ngrid_ld,
-                 double *__restrict__ rho, double *__restrict__ grad, int nbc, int variant) {
+                 double *__restrict__ rho, double *__restrict__ grad, int nbc, int nst, int variant) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     constexpr int A_STAGE = S * I8_A_PLANE, A_PART = A_STAGE / CL, B_ROWS = RPS_BN * 16, B_SLOT = S * I8_KT * RPS_BN;
     static_assert(A_STAGE % (16 * CL) == 0, "the A stage splits into 16-byte aligned parts");
     // instruction descriptor without N: D = S32, A = B = signed int8, both K-major, M = 128
     constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BM >> 4) << 24);
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
-    constexpr int NCH = (NCOMP == 4) ? 4 : 1;     // reduce-scatter rounds per M tile: 4 x (8 points x 4 components) or 1 x 32 points
-    __shared__ uint64_t afull[RPS_NST], aempty[RPS_NST], bfull[RPS_MAXSLOT], bempty[RPS_MAXSLOT], accum_full, accum_empty;
+    constexpr int NV = 8 * NCOMP, NVL = NV / 8;   // per-thread accumulators (8 points x components); values left per lane
+    __shared__ uint64_t afull[RPS_MAXST], aempty[RPS_MAXST], bfull[RPS_MAXSLOT], bempty[RPS_MAXSLOT], accum_full, accum_empty;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ double comb[3][2][NCH][32];        // partial sums of lane quarters 1..3, handed to quarter 0
+    __shared__ double comb[3][2][NVL][32];        // partial sums of lane quarters 1..3, handed to quarter 0
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ptiles = sbp / RPS_BN;
     // a cluster walks groups of CL consecutive point tiles of one superblock; CTA r of the cluster owns tile r of the group
@@ -80,7 +85,7 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
     const int g0 = (int)blockIdx.x / CL, gstep = (int)gridDim.x / CL;
 
     if (tid == 0) {
-        for (int i = 0; i < RPS_NST; i++) {
+        for (int i = 0; i < RPS_MAXST; i++) {
             mbar_init(&afull[i], 1);
             mbar_init(&aempty[i], CL);            // every CTA of the cluster releases a stage
         }
@@ -89,7 +94,7 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
             mbar_init(&bempty[i], 1);
         }
         mbar_init(&accum_full, 1);
-        mbar_init(&accum_empty, 1);
+        mbar_init(&accum_empty, 8);               // every epilogue warp releases TMEM on its own
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -102,7 +107,7 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_smem;
     const uint32_t abase = smem_u32(i8_smem);                 // A ring
-    const uint32_t bbase = abase + RPS_NST * A_STAGE;         // B cache: nbc slots
+    const uint32_t bbase = abase + nst * A_STAGE;             // B cache: nbc slots
     // K steps of a unit whose B slot stays for the whole unit (the rest cycle through the last RPS_STREAM slots)
     auto ncached = [&](int nkt) { return nkt <= nbc ? nkt : nbc - RPS_STREAM; };
 
@@ -137,8 +142,8 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
                             mbar_expect_tx(&bfull[bs], B_SLOT);
                             bulk_g2s(bbase + bs * B_SLOT, B + (int64_t)kt * B_SLOT, B_SLOT, &bfull[bs]);
                         }
-                        const int slot = ait % RPS_NST;
-                        mbar_wait(&aempty[slot], ((ait / RPS_NST) & 1) ^ 1);
+                        const int slot = ait % nst;
+                        mbar_wait(&aempty[slot], ((ait / nst) & 1) ^ 1);
                         mbar_expect_tx(&afull[slot], A_STAGE);
                         const signed char *src = A + ((int64_t)mt * nkt + kt) * A_STAGE + crank * A_PART;
                         if (CL > 1) bulk_g2s_mc(abase + slot * A_STAGE + crank * A_PART, src, A_PART, &afull[slot], CMASK);
@@ -179,8 +184,8 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
                             mbar_wait(&bfull[bs], (cph >> bs) & 1u);
                             cph ^= 1u << bs;
                         }
-                        const int slot = ait % RPS_NST;
-                        mbar_wait(&afull[slot], (ait / RPS_NST) & 1);
+                        const int slot = ait % nst;
+                        mbar_wait(&afull[slot], (ait / nst) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t da = da0 + (uint64_t)((slot * A_STAGE) >> 4), db = db0 + (uint64_t)((bs * B_SLOT) >> 4);
                         if (variant != 2) {
@@ -206,27 +211,37 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        // ===== epilogue: TMEM lane quarter lg = warp % 4 (AO rows), column half = 32 of the 64 grid points =====
+        // ===== epilogue: TMEM lane quarter lg = warp % 4 (32 AO rows), column half = 32 of the 64 grid points =====
+        // Fragment layout of tcgen05.ld.16x256b (measured: tools/tmem_layout.cu), q = lane / 4, p = lane % 4:
+        //   TMEM lanes L = 32 lg + q + 8 r,          r = 0..3   (r = 0, 1: the load at lane base 0; 2, 3: lane base 16)
+        //   points     g = 32 half + 8 k + 2 p + c,  k = 0..3, c = 0, 1
+        // sb_gather_slice_dm_kernel stores row nu = 32 lg + 4 q + r of a D_sb tile at lane L (RPS_ROW_PERM), so the four
+        // rows of a thread are four CONSECUTIVE AO columns: one 256-bit load per (component, point) instead of four
+        // 64-bit ones (the LSU request queue, not bandwidth, was what the epilogue waited on: stall_lg 18 %, long
+        // scoreboard 30 % in profiles/r02_k2_ps_v2_ncu.txt)
         const int lg = warp & 3, half = (warp - 4) >> 2;
+        const int q = lane >> 2, p = lane & 3;
         const int et = tid - 128;                                    // 0..255: (component, point row) of the L2 prefetch
+        const uint32_t tq = tmem + ((uint32_t)(lg * 32) << 16) + half * 32;
         int nt = 0;
         for (int ug = g0; ug < ngroups; ug += gstep) {
             const int sb = ug / gps, pt = (ug - sb * gps) * CL + crank;
             const SBDesc d = sbd[sb];
             const int ntm = (d.nsp + I8_BM - 1) / I8_BM;
             const int64_t ld = d.nsp, cstride = (int64_t)sbp * ld;
-            const int grow0 = pt * RPS_BN + half * 32;               // first grid row (inside the superblock) of this warp
-            double acc[NCH];
+            // acc[c4 * 8 + k * 2 + c]: this thread's part (its 4 AO rows per M tile) of component c4 at point (k, c)
+            double acc[NV];
 #pragma unroll
-            for (int ch = 0; ch < NCH; ch++) acc[ch] = 0.0;
+            for (int i = 0; i < NV; i++) acc[i] = 0.0;
+            // first AO row / point of this thread (component 0)
+            const double *a0 = ao + d.ao_off + (int64_t)(pt * RPS_BN + half * 32 + 2 * p) * ld + lg * 32 + 4 * q;
             for (int mt = 0; mt < ntm; mt++, nt++) {
-                const int nu = mt * I8_BM + lg * 32 + lane;          // AO row of D_sb == AO column of phi
-                const bool live = nu < d.nsp;
-                const double cs = live ? cscale[d.idx_off + nu] : 0.0;
-                const double *col = ao + d.ao_off + (int64_t)grow0 * ld + (live ? nu : 0);
-                // the fp64 AO values of the NEXT M tile (or of the first M tile of the next unit) start their way from
-                // HBM into L2 now, one 1 KB row segment per thread, a whole MMA phase before they are read
-                if (variant != 1 && variant != 3 && et < 64 * NCOMP) {
+                const bool live = mt * I8_BM + lg * 32 < d.nsp;      // (nsp is a multiple of 64: a warp's 32 rows all exist or none)
+                // optional: the fp64 AO values of the NEXT M tile (or of the first M tile of the next unit) start their way
+                // from HBM into L2 now, one 1 KB row segment per thread, a whole MMA phase before they are read
+                // (measured: off is faster -- 6.1 against 7.1 ms at C60 -- and the prefetched lines were often evicted again
+                // before their use, 34 GB of DRAM reads instead of 24; kept as timing variant 5)
+                if (variant == 5 && et < 64 * NCOMP) {
                     const int prow = et & 63, pc = et >> 6;
                     if (mt + 1 < ntm) {
                         const int w = min(I8_BM, d.nsp - (mt + 1) * I8_BM);
@@ -238,78 +253,105 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
                                          min(I8_BM, d2.nsp) * 8);
                     }
                 }
+                // row scales of D_sb times the weight 2^(-12 - 7 (S - 1)) of the last anti-diagonal
+                double cs[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    cs[r] = live ? ldexp(cscale[d.idx_off + mt * I8_BM + lg * 32 + 4 * q + r], -12 - 7 * (S - 1)) : 0.0;
                 mbar_wait(&accum_full, nt & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                double x[32];
+                double x[32];                                        // x[(k * 4 + r) * 2 + c]
                 if (variant == 3) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) x[j] = 1.0;
                 } else {
 #pragma unroll
-                    for (int ch = 0; ch < 4; ch++) {
-                        double t8[8];
-                        i8_recombine8<S>(tmem + ((uint32_t)(lg * 32) << 16), RPS_BN, half * 32 + ch * 8, t8);
+                    for (int kp = 0; kp < 2; kp++) {                 // 16 columns (two column groups k) at a time
+                        uint32_t v[S][2][8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) x[ch * 8 + j] = t8[j] * cs;
+                        for (int dd = 0; dd < S; dd++)
+#pragma unroll
+                            for (int bb = 0; bb < 2; bb++)
+                                tmem_ld_16x256b_x2(tq + ((uint32_t)(bb * 16) << 16) + dd * RPS_BN + kp * 16, v[dd][bb]);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int bb = 0; bb < 2; bb++)
+#pragma unroll
+                            for (int rg = 0; rg < 8; rg++) {
+                                const int k = kp * 2 + (rg >> 2), r = bb * 2 + ((rg >> 1) & 1), c = rg & 1;
+                                // exact merge of the S anti-diagonal sums, Horner in fp64 (every partial result is an
+                                // integer below 2^53 for the K limits the host enforces)
+                                double t = i32_to_f64((int)v[0][bb][rg]);
+#pragma unroll
+                                for (int dd = 1; dd < S; dd++) t = fma(t, 128.0, i32_to_f64((int)v[dd][bb][rg]));
+                                x[(k * 4 + r) * 2 + c] = t * cs[r];
+                            }
                     }
                 }
+                // this warp's part of TMEM is in registers: no CTA-wide barrier here, the eight epilogue warps run out of
+                // phase with each other (one drains while another waits on its AO loads)
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("bar.sync 1, 256;" ::: "memory");      // all epilogue warps have drained TMEM
-                if (warp == 4 && lane == 0)
+                __syncwarp();
+                if (lane == 0)
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
                 if (variant == 1 || variant == 3) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) acc[0] += x[j];
                     continue;
                 }
-                if (NCOMP == 4) {
-                    // chunk ch = 8 points x 4 components; the loads of chunk ch + 1 are issued before chunk ch is reduced
-                    double v[2][32];
-                    auto load_chunk = [&](double (&t)[32], int ch) {
+                if (!live) continue;
+                // row dots: 4 AO rows x 8 points x NCOMP components, straight FMAs into the per-thread accumulators
+                // (lanes of equal p read 8 consecutive AO values = two full sectors of one grid row)
+                const double *am = a0 + mt * I8_BM;
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
+                for (int c4 = 0; c4 < NCOMP; c4++) {
+                    double a[32];
 #pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                t[c * 8 + j] = live ? ldcs_f64(col + c * cstride + (int64_t)(ch * 8 + j) * ld) : 0.0;
-                    };
-                    load_chunk(v[0], 0);
+                    for (int k = 0; k < 4; k++)
 #pragma unroll
-                    for (int ch = 0; ch < 4; ch++) {
-                        if (ch + 1 < 4) load_chunk(v[(ch + 1) & 1], ch + 1);
+                        for (int c = 0; c < 2; c++)
+                            ldcs_f64x4(am + c4 * cstride + (int64_t)(8 * k + c) * ld, a[(k * 4 + 0) * 2 + c], a[(k * 4 + 1) * 2 + c],
+                                       a[(k * 4 + 2) * 2 + c], a[(k * 4 + 3) * 2 + c]);
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
+                    for (int k = 0; k < 4; k++)
 #pragma unroll
-                            for (int j = 0; j < 8; j++) v[ch & 1][c * 8 + j] *= x[ch * 8 + j];
-                        acc[ch] += warp_reduce_scatter32(v[ch & 1], lane);    // lane l: component l / 8, point ch * 8 + l % 8
-                    }
-                } else {
-                    double v[32];
+                        for (int c = 0; c < 2; c++)
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = live ? ldcs_f64(col + (int64_t)j * ld) : 0.0;
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] *= x[j];
-                    acc[0] += warp_reduce_scatter32(v, lane);         // lane l: point l
+                            for (int r = 0; r < 4; r++)
+                                acc[c4 * 8 + k * 2 + c] = fma(x[(k * 4 + r) * 2 + c], a[(k * 4 + r) * 2 + c], acc[c4 * 8 + k * 2 + c]);
                 }
             }
-            // the four lane quarters of a column half meet in shared memory (the next write of `comb` is ordered
-            // behind these reads by the bar.sync 1 of the next unit's first M tile)
+            // one reduction per unit: over the 8 lanes of equal p (butterfly reduce-scatter over lane bits 4, 3, 2; fixed
+            // order, no atomics), then over the four lane quarters through shared memory
+#pragma unroll
+            for (int rd = 0; rd < 3; rd++) {
+                const int lm = 16 >> rd, hv = NV >> (rd + 1);
+                const bool upper = (lane & lm) != 0;
+#pragma unroll
+                for (int i = 0; i < hv; i++) {
+                    const double send = upper ? acc[i] : acc[i + hv];
+                    const double keep = upper ? acc[i + hv] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, lm);
+                }
+            }
+            // this lane now holds the values i = q * NVL + j, j < NVL
             if (lg > 0) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) comb[lg - 1][half][ch][lane] = acc[ch];
+                for (int j = 0; j < NVL; j++) comb[lg - 1][half][j][lane] = acc[j];
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");
             if (lg == 0) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) {
-                    const double t = ((acc[ch] + comb[0][half][ch][lane]) + comb[1][half][ch][lane]) + comb[2][half][ch][lane];
-                    const int c = (NCOMP == 4) ? (lane >> 3) : 0;
-                    const int grow = grow0 + ((NCOMP == 4) ? (ch * 8 + (lane & 7)) : lane);
-                    const int64_t g = (int64_t)sb * sbp + grow;
+                for (int j = 0; j < NVL; j++) {
+                    const double t = ((acc[j] + comb[0][half][j][lane]) + comb[1][half][j][lane]) + comb[2][half][j][lane];
+                    const int i = q * NVL + j, c4 = i >> 3, k = (i & 7) >> 1, c = i & 1;
+                    const int64_t g = (int64_t)sb * sbp + pt * RPS_BN + half * 32 + 8 * k + 2 * p + c;
                     const double sa_ = rscale[g];
-                    if (c == 0) rho[g] = sa_ * t;
-                    else grad[(int64_t)(c - 1) * ngrid_ld + g] = 2.0 * sa_ * t;
+                    if (c4 == 0) rho[g] = sa_ * t;
+                    else grad[(int64_t)(c4 - 1) * ngrid_ld + g] = 2.0 * sa_ * t;
                 }
             }
+            asm volatile("bar.sync 3, 256;" ::: "memory");          // `comb` is free for the next unit
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -318,12 +360,17 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// B-cache slots that fit beside the A ring in the 227 KB of shared memory (static barriers / comb: < 7 KB)
+// shared memory: 227 KB minus the static part (barriers, comb: < 7 KB) = A ring + B cache
 template <int S>
-static constexpr int rps_slots() {
-    return (227 * 1024 - 7 * 1024 - RPS_NST * S * I8_A_PLANE) / (S * I8_KT * RPS_BN) < RPS_MAXSLOT
-               ? (227 * 1024 - 7 * 1024 - RPS_NST * S * I8_A_PLANE) / (S * I8_KT * RPS_BN)
+static constexpr int rps_slots() {      // most B-cache slots beside a 3-stage ring
+    return (227 * 1024 - 7 * 1024 - 3 * S * I8_A_PLANE) / (S * I8_KT * RPS_BN) < RPS_MAXSLOT
+               ? (227 * 1024 - 7 * 1024 - 3 * S * I8_A_PLANE) / (S * I8_KT * RPS_BN)
                : RPS_MAXSLOT;
+}
+template <int S>
+static int rps_stages(int nbc) {        // ring stages beside nbc B-cache slots
+    const int n = (227 * 1024 - 7 * 1024 - nbc * S * I8_KT * RPS_BN) / (S * I8_A_PLANE);
+    return n < RPS_MAXST ? n : RPS_MAXST;
 }
 
 template <typename K, typename... Args>
@@ -374,9 +421,14 @@ static int rho_i8_ps_launch(const SBDesc *sbd, int nsb, int sbp, const double *a
     // the cache takes what the static shared memory (barriers, comb) leaves of the 227 KB: shrink it by a slot if
     // the driver does not accept the launch configuration
     size_t smem = 0;
+    int nst = 0;
     for (;; nbc--) {
         QC_REQUIRE(nbc > RPS_STREAM, "rho_i8_ps_kernel does not fit in shared memory");
-        smem = (size_t)RPS_NST * S * I8_A_PLANE + (size_t)nbc * S * I8_KT * RPS_BN;
+        // the A ring takes what the B cache leaves (the MMA issuer waits on the latency of the D_sb stream, not on its
+        // bandwidth: bytes in flight are what counts)
+        nst = rps_stages<S>(nbc);
+        if (nst < 2) continue;
+        smem = (size_t)nst * S * I8_A_PLANE + (size_t)nbc * S * I8_KT * RPS_BN;
         int nblk = 0;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, 384, smem) == cudaSuccess && nblk >= 1)
@@ -395,10 +447,10 @@ static int rho_i8_ps_launch(const SBDesc *sbd, int nsb, int sbp, const double *a
     prof_begin(PROF_RHO, st);
     if (CL > 1)
         QC_CHECK(launch_cluster(kern, CL, grid, 384, smem, st, sbd, nsb, sbp, ao, pplanes, p_off, dplanes, d_off, rscale, cscale,
-                                ngl, rho, grad, nbc, g_i8_variant));
+                                ngl, rho, grad, nbc, nst, g_i8_variant));
     else
         kern<<<grid, 384, smem, st>>>(sbd, nsb, sbp, ao, pplanes, p_off, dplanes, d_off, rscale, cscale, ngl, rho, grad, nbc,
-                                      g_i8_variant);
+                                      nst, g_i8_variant);
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;
@@ -417,7 +469,7 @@ static int rho_i8_ps_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const
     // B200QC_I8_MODE bits 12..16: number of B cache slots (experiments: what the cache does not take stays L1);
     // bits 17..18: cluster size of the multicast A stream (0 = default, 1 = no clusters, 2, 3 = clusters of 4)
     int nbc = (g_i8_mode >> 12) & 31;
-    if (nbc < RPS_STREAM + 1 || nbc > rps_slots<S>()) nbc = rps_slots<S>();
+    if (nbc < RPS_STREAM + 1 || nbc > rps_slots<S>()) nbc = RPS_DEFAULT_SLOTS < rps_slots<S>() ? RPS_DEFAULT_SLOTS : rps_slots<S>();
     int cl = (g_i8_mode >> 17) & 3;
     cl = cl == 0 ? RPS_CLUSTER : (cl == 3 ? 4 : cl);
     while (cl > 1 && (sbp / RPS_BN) % cl != 0) cl >>= 1;

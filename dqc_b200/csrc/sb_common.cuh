@@ -3,6 +3,18 @@
 #pragma once
 #include "common.cuh"
 
+// One digit of the sliced representation: q = round-to-nearest-even(y) as an int in [-64, 64], y <- (y - q) * 128.
+// rint() / (int) compile to FRND.F64 + F2I.F64, two instructions of the 16-lane XU pipe per digit -- at C60 the slicers
+// cut 2.8e9 digits per Fock build and were bound by exactly that.  The classic magic-number form stays on the fp64
+// pipe: y + 1.5 * 2^52 has the rounded integer (two's complement) in its low mantissa word, valid for |y| < 2^31.
+__device__ __forceinline__ int slice_digit(double &y) {
+    const double magic = 6755399441055744.0;      // 1.5 * 2^52
+    const double t = y + magic;
+    const double q = t - magic;
+    y = (y - q) * 128.0;
+    return __double2loint(t);
+}
+
 struct SBDesc {
     int64_t ao_off;   // doubles: start of this SB's [ncomp][SBP][nsp] block
     int64_t d_off;    // doubles: start of this SB's gathered D (nsp x nsp) in the scratch

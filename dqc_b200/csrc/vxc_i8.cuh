@@ -94,9 +94,7 @@ sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, co
                 double y = (h ? v.y : v.x) * sinv[cg * 16 + j + h];
 #pragma unroll
                 for (int s = 0; s < S; s++) {
-                    const double q = rint(y);
-                    w[s][(j + h) >> 2] |= ((unsigned int)(int)q & 0xffu) << (8 * ((j + h) & 3));
-                    y = (y - q) * 128.0;
+                    w[s][(j + h) >> 2] |= ((unsigned int)slice_digit(y) & 0xffu) << (8 * ((j + h) & 3));
                 }
             }
         }
@@ -117,17 +115,21 @@ sb_slice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ x, co
 //     the AO storage) and the coefficient maxima formed here.
 //  2. One pass over the fp64 AO values forms vb and cuts it (vb never goes to HBM).  While cutting, the kernel records
 //     the LARGEST scaled value it saw per column: that is the exact column maximum, for free.
-//  3. A column whose bound turned out more than 2^VBS_LOOSE_BITS too large gets its exact exponent written to `scales`
-//     and its 64-column block flagged; vxc_vbslice_kernel<.., FIX = true> then re-cuts the flagged blocks only (for a
-//     smooth potential on a molecular grid: none or a handful; for a potential that is uncorrelated from point to
-//     point -- tests/test_gpu_xcpath.py -- many).  The planes therefore never lose more than VBS_LOOSE_BITS bits
-//     against the two-pass form with exact maxima, whatever the potential.
+//  3. A column whose bound turned out more than 2^VBS_LOOSE_BITS too large AND whose last digit would weigh more than
+//     2^VBS_ABS_EXP gets its exact exponent written to `scales` and its 64-column block flagged;
+//     vxc_vbslice_kernel<.., FIX = true> then re-cuts the flagged blocks only.  The bound has a long loose tail on a
+//     molecular grid (tools/check_vb_bound.py, C60 / PBE: 38 % of the columns exact, 78 % within 4 bits, 10 % more than
+//     20 bits off -- the core functions of the neighbouring atoms, large exactly where the Becke weight of this atom's
+//     points vanishes), but almost all of those columns are tiny in absolute terms: 4.5 % of the blocks are re-cut,
+//     Vxc agrees with the two-pass form to 5e-11 (2.6e-10 without any repair; the parity bar is 1e-6).  For a
+//     potential that is uncorrelated from point to point (tests/test_gpu_xcpath.py) most blocks are re-cut.
 // Memory access: a warp reads 8 consecutive rows, lane = 2 adjacent columns -> every load instruction is one contiguous
 // 512-byte row segment (the round-2 first version, thread = 16 columns of a row, ran at 93 % L1 throughput with half
 // of every sector wasted per instruction: 4.65 ms); the int8 bytes are staged in shared memory and leave as 16-byte
 // pieces of whole 128-byte core matrices.
 #define VBS_GROUP 32
 #define VBS_LOOSE_BITS 4
+#define VBS_ABS_EXP (-40)       // 2^-40 = 9e-13 (at -49: 27 % of the C60 blocks are re-cut)
 #define VBS_PHASE 64            // rows per staging phase (two K tiles)
 #define VBS_ROWB 80             // staged row: 64 bytes + 16 of padding (16-byte reads of 8 consecutive rows: no conflicts)
 
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256, 2)
 vxc_vbslice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp, int64_t ngrid_ld,
                    const double *__restrict__ w, const double *__restrict__ vrho, const double *__restrict__ vgrad,
                    const float *__restrict__ colmax, const int64_t *__restrict__ p_off, signed char *__restrict__ planes,
-                   double *__restrict__ scales, int *__restrict__ fixflag) {
+                   double *__restrict__ scales, int *__restrict__ fixflag, int loose_bits) {
     extern __shared__ __align__(16) unsigned char vbs_raw[];
     // coef[NCOMP][sbp], wmax[ngroups][NCOMP] (doubles), then the staging tile [S][VBS_PHASE][VBS_ROWB] bytes
     __shared__ double sinv[64], bpart[4][64];
@@ -264,11 +266,8 @@ vxc_vbslice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao
                 unsigned char *q = stage + (warp * 8 + hf * 4 + j) * VBS_ROWB + 2 * lane;
 #pragma unroll
                 for (int sl = 0; sl < S; sl++) {
-                    const double q0 = rint(y0), q1 = rint(y1);
-                    *reinterpret_cast<unsigned short *>(q + sl * (VBS_PHASE * VBS_ROWB)) =
-                        (unsigned short)(((unsigned int)(int)q0 & 0xffu) | (((unsigned int)(int)q1 & 0xffu) << 8));
-                    y0 = (y0 - q0) * 128.0;
-                    y1 = (y1 - q1) * 128.0;
+                    const unsigned int q0 = (unsigned int)slice_digit(y0) & 0xffu, q1 = (unsigned int)slice_digit(y1) & 0xffu;
+                    *reinterpret_cast<unsigned short *>(q + sl * (VBS_PHASE * VBS_ROWB)) = (unsigned short)(q0 | (q1 << 8));
                 }
             }
         }
@@ -297,7 +296,10 @@ vxc_vbslice_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao
 #pragma unroll
         for (int q = 1; q < 8; q++) mo = fmaxf(mo, obs[q][tid]);
         double sc = 64.0 / sinv[tid];                                // 2^e of the bound
-        if (mo > 0.f && (mo < ldexpf(64.f, -VBS_LOOSE_BITS) || mo >= 64.f)) {
+        // loose AND coarse in absolute terms: the last digit of a column cut with exponent e weighs 2^(e - 7 S); columns
+        // whose bound is loose because the grid weights vanish exactly where the AO is large (the core functions of
+        // the neighbouring atoms: thousands of them at C60, true maximum 2^-20 of the bound and below) stay as they are
+        if (mo > 0.f && ((mo < ldexpf(64.f, -loose_bits) && sc > ldexp(1.0, VBS_ABS_EXP + 7 * S)) || mo >= 64.f)) {
             int e = 0;
             frexp((double)mo * (1.0 + 1e-6) / sinv[tid], &e);        // (mo is rounded up already; margin for the fp32 step)
             sc = ldexp(1.0, e);
@@ -718,13 +720,16 @@ static int vxc_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
             QC_CHECK(cudaFuncSetAttribute(vxc_vbslice_kernel<S, BN, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
             QC_CHECK(cudaFuncSetAttribute(vxc_vbslice_kernel<S, BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
         }
+        // (B200QC_I8_MODE bits 20..22: looseness threshold of the repair pass, experiments; 0 = VBS_LOOSE_BITS)
+        // (bit 23: never repair -- diagnostics of the bound, tools/check_vb_bound.py)
+        const int loose = (g_i8_mode & (1 << 23)) ? 1000 : ((g_i8_mode >> 20) & 7) ? ((g_i8_mode >> 20) & 7) : VBS_LOOSE_BITS;
         prof_begin(PROF_VXC_VB, st);
         if (vgrad) {
-            vxc_vbslice_kernel<S, BN, 4, false><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
-            vxc_vbslice_kernel<S, BN, 4, true><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
+            vxc_vbslice_kernel<S, BN, 4, false><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag, loose);
+            vxc_vbslice_kernel<S, BN, 4, true><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag, loose);
         } else {
-            vxc_vbslice_kernel<S, BN, 1, false><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
-            vxc_vbslice_kernel<S, BN, 1, true><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag);
+            vxc_vbslice_kernel<S, BN, 1, false><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag, loose);
+            vxc_vbslice_kernel<S, BN, 1, true><<<gs, 256, sm1, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, colmax, b_off, bplanes, bscale, fixflag, loose);
         }
         prof_end(st);
         QC_LAUNCHED(2);

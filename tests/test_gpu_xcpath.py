@@ -299,3 +299,41 @@ def test_vxc_tcgen05_int8_matches_fp64_path(cuda, nslice, tol, gga, fused, monke
         # the repair pass did run on this potential, and only on part of the blocks
         nfix = int(gb.fixflag.sum())
         assert 0 < nfix < gb.fixflag.numel()
+
+
+@pytest.mark.parametrize("nslice,tol", [(6, 2e-10), (5, 2e-8)])
+@pytest.mark.parametrize("gga", [False, True])
+@pytest.mark.parametrize("mode", [1 << 17, 2 << 17, 3 << 17, (5 << 12) | (2 << 17)])
+def test_rho_tcgen05_int8_matches_fp64_path(cuda, nslice, tol, gga, mode):
+    """K2 on tcgen05 (point-stationary sliced int8 GEMM, fragment-layout epilogue) against the fp64 DMMA form of the
+    same contraction, on a grid with several M tiles per superblock (benzene / cc-pVDZ: up to 128 kept AOs; the
+    carbon cluster below: several hundred), without clusters and with the D_sb stream multicast over clusters of 2
+    and 4 CTAs, and with a B cache too small for the tile (streaming slots)."""
+    from dqc_b200 import _lib
+    from dqc_b200.utils import systems
+    from dqc_b200.grid.factory import get_predefined_grid
+    zs, pos = systems.carbon_cluster(27)
+    w, _ = util.make_wrapper(zs, pos.tolist(), "def2-svp")
+    nb = len(w)
+    grid = get_predefined_grid(3, zs, torch.tensor(pos, device=cuda), device=cuda)
+    xyz, wts = grid.get_rgrid(), grid.get_dvolume()
+    db = w.device_basis(cuda)
+    deriv = 1 if gga else 0
+    ref = _lib.GridBlocks(db, 0, nb, xyz, wts, deriv, sbp=512, eps=1e-12)
+    gb = _lib.GridBlocks(db, 0, nb, xyz, wts, deriv, sbp=512, eps=1e-12, rho_i8_slices=nslice)
+    assert gb.rho_bn == 128 and int(gb.nsp.max()) > 256
+    dm = util.seeded_dm(w.nao(), int(sum(zs)) // 2, seed=1).to(cuda)
+    r_ref, g_ref = ref.rho(dm, gga)
+    lib = _lib.load()
+    lib.b200qc_i8_mode(mode)
+    try:
+        r, g = gb.rho(dm, gga)
+        r2, g2 = gb.rho(dm, gga)
+    finally:
+        lib.b200qc_i8_mode(0)
+    scale = float(r_ref.abs().max())
+    assert float((r - r_ref).abs().max()) < tol * scale
+    assert torch.equal(r, r2)                        # fixed-order reductions, no atomics: bitwise repeatable
+    if gga:
+        assert float((g - g_ref).abs().max()) < tol * float(g_ref.abs().max())
+        assert torch.equal(g, g2)
