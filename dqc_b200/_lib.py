@@ -20,8 +20,8 @@ GRID_ALIGN = 128  # leading dimension of the grid axis (K2/K4 CTA tile)
 AO_ALIGN = 64     # leading dimension of the AO axis
 
 FUNC_IDS = {"lda_x": 1, "lda_c_pw": 2, "lda_c_pw_mod": 3, "lda_c_vwn": 4, "lda_c_vwn_rpa": 5,
-            "gga_x_pbe": 101, "gga_c_pbe": 102, "gga_x_b88": 103, "gga_c_lyp": 104}
-FUNC_FAMILY = {name: (2 if fid >= 100 else 1) for name, fid in FUNC_IDS.items()}
+            "gga_x_pbe": 101, "gga_c_pbe": 102, "gga_x_b88": 103, "gga_c_lyp": 104, "mgga_x_scan": 201}
+FUNC_FAMILY = {name: (4 if fid >= 200 else 2 if fid >= 100 else 1) for name, fid in FUNC_IDS.items()}
 
 _SIGS = {
     # name: (restype, argtypes)
@@ -49,6 +49,18 @@ _SIGS = {
     "b200qc_xc_unpol": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_xc_mgga_unpol": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_rho_sb_mgga": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]),
+    "b200qc_vxc_sb_mgga": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_xc_pol": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -282,7 +294,7 @@ def eval_gto(basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, deriv
     nao = basis.nao(sh0, sh1)
     ngrid_ld = round_up(max(ngrid, 1), GRID_ALIGN) if ngrid_ld is None else ngrid_ld
     ao_ld = round_up(nao, AO_ALIGN) if ao_ld is None else ao_ld
-    ncomp = 4 if deriv else 1
+    ncomp = {0: 1, 1: 4, 2: 5}[int(deriv)]
     ao = torch.zeros((ncomp, ngrid_ld, ao_ld), dtype=torch.float64, device=coords.device)
     coords = coords.contiguous()
     _check(lib.b200qc_eval_gto(basis.handle, sh0, sh1, deriv, _ptr(coords), ngrid, _ptr(ao), ngrid_ld, ao_ld,
@@ -328,6 +340,21 @@ def xc_unpol(terms, rho_t, grad_t, want_e=True, want_v=True):
     _check(lib.b200qc_xc_unpol(len(ids), _np(ids), _np(coefs), n, n, _ptr(rho_t), _ptr(grad_t), _ptr(e), _ptr(vr),
                                _ptr(vg), _stream()), "xc_unpol")
     return e, vr, vg
+
+
+def xc_mgga_unpol(terms, rho_t, grad_t, lapl_t, kin_t, want_e=True, want_v=True):
+    """Meta-GGA sums: rho (n,), grad (3, n), lapl (n,), kin (n,) -> edens, vrho, vgrad (3, n), vlapl, vkin."""
+    lib = load()
+    ids, coefs = _terms(terms)
+    n = rho_t.shape[-1]
+    e = torch.empty_like(rho_t) if want_e else None
+    vr = torch.empty_like(rho_t) if want_v else None
+    vg = torch.empty_like(grad_t) if want_v else None
+    vl = torch.empty_like(rho_t) if want_v else None
+    vk = torch.empty_like(rho_t) if want_v else None
+    _check(lib.b200qc_xc_mgga_unpol(len(ids), _np(ids), _np(coefs), n, n, _ptr(rho_t), _ptr(grad_t), _ptr(lapl_t),
+                                    _ptr(kin_t), _ptr(e), _ptr(vr), _ptr(vg), _ptr(vl), _ptr(vk), _stream()), "xc_mgga_unpol")
+    return e, vr, vg, vl, vk
 
 
 def xc_pol(terms, rho_t, grad_t, want_e=True, want_v=True):
@@ -652,7 +679,9 @@ class GridBlocks(object):
         self.basis, self.sh0, self.sh1 = basis, sh0, sh1
         self.ngrid = int(coords.shape[0])
         self.sbp, self.deriv, self.eps = int(sbp), int(deriv), float(eps)
-        self.ncomp = 4 if deriv else 1
+        self.ncomp = {0: 1, 1: 4, 2: 5}[self.deriv]      # deriv 2: phi, grad phi, lapl phi (meta-GGA)
+        if self.deriv == 2:
+            i8_slices = rho_i8_slices = 0                 # the meta-GGA contractions run on the fp64 DMMA engine
         self.nsb = (self.ngrid + self.sbp - 1) // self.sbp
         self.ngl = self.nsb * self.sbp
         self.nao = basis.nao(sh0, sh1)
@@ -780,6 +809,28 @@ class GridBlocks(object):
         _check(lib.b200qc_rho_sb(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
                                  _ptr(dm.contiguous()), self.nao, _ptr(self.dsb), _ptr(r), _ptr(g), _stream()), "rho_sb")
         return r, g
+
+    def rho_mgga(self, dm: torch.Tensor):
+        """dm (nao, nao) -> rho (ngl,), grad (3, ngl), lapl rho (ngl,), tau (ngl,)   (hcgto.py:399-438)."""
+        assert self.deriv == 2 and dm.shape == (self.nao, self.nao)
+        dev = dm.device
+        r, lp, kn = (torch.empty(self.ngl, dtype=torch.float64, device=dev) for _ in range(3))
+        g = torch.empty((3, self.ngl), dtype=torch.float64, device=dev)
+        if self.nsb:
+            _check(load().b200qc_rho_sb_mgga(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx),
+                                             _ptr(self.ao), _ptr(dm.contiguous()), self.nao, _ptr(self.dsb), _ptr(r), _ptr(g),
+                                             _ptr(lp), _ptr(kn), _stream()), "rho_sb_mgga")
+        return r, g, lp, kn
+
+    def vxc_mat_mgga(self, vrho, vgrad, vlapl, vkin) -> torch.Tensor:
+        """(nao, nao) = sum_g w [phi^T (vrho phi + 2 vgrad . grad phi + 2 vlapl lapl phi) + sum_d dphi_d^T (2 vlapl + vkin / 2) dphi_d]."""
+        assert self.deriv == 2 and vrho.shape[0] == self.ngl
+        mat = torch.empty((self.nao, self.nao), dtype=torch.float64, device=vrho.device)
+        _check(load().b200qc_vxc_sb_mgga(_ptr(self.d_desc), self.nsb, self.sbp, self.max_nsp, _ptr(self.d_idx), _ptr(self.ao),
+                                         _ptr(self.w), _ptr(vrho.contiguous()), _ptr(vgrad.contiguous()),
+                                         _ptr(vlapl.contiguous()), _ptr(vkin.contiguous()), self.nao, _ptr(self.d_vb_off),
+                                         _ptr(self.vb), _ptr(mat), _stream()), "vxc_sb_mgga")
+        return mat
 
     def vxc_mat(self, vrho: torch.Tensor, vgrad: Optional[torch.Tensor]) -> torch.Tensor:
         """vrho (ngl,), vgrad (3, ngl) | None -> (nao, nao) = sum_g w phi^T (vrho phi + 2 vgrad . grad phi)."""

@@ -1,6 +1,7 @@
-// K1 -- AO values (and gradients) on grid points.
-// Replaces GTOval_sph / GTOval_ip_sph as called from dqc/hamilton/intor/gtoeval.py:196-239
-// (to_transpose=True layout: [comp][grid][ao], ao contiguous).
+// K1 -- AO values (gradients, Laplacians) on grid points.
+// Replaces GTOval_sph / GTOval_ip_sph / the GTOval_sph_deriv2 sum of eval_laplgto as called from
+// dqc/hamilton/intor/gtoeval.py:196-260 (to_transpose=True layout: [comp][grid][ao], ao contiguous).
+// DERIV = 0: phi; 1: phi, d/dx, d/dy, d/dz; 2: those four and the Laplacian (the meta-GGA branch, hcgto.py:183-186).
 //
 // HBM-write-bound: ncomp * ngrid * nao * 8 bytes written, 24 bytes/point read.  Layout of the work:
 // one CTA owns 32 grid points (lane = point, so shell data are warp-uniform broadcasts and there is
@@ -13,19 +14,22 @@
 #define AO_PTS 32
 #define AO_WIN 64
 #define AO_THREADS 256
+#define AO_NCOMP(DERIV) ((DERIV) == 0 ? 1 : ((DERIV) == 1 ? 4 : 5))
 
-template <int L, bool DERIV>
+template <int L, int DERIV>
 __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const double *__restrict__ env,
                                                  double x, double y, double z, int col0, int lane,
                                                  double *tile /* [ncomp][AO_WIN][33] */) {
     constexpr int NC = NCART(L), NS = 2 * L + 1;
     const double r2 = x * x + y * y + z * z;
-    double rad = 0.0, drad = 0.0;
+    // rad = sum c e^(-a r^2);  grad rad = r drad, drad = sum -2 a c e^(-a r^2);  lapl rad = d2rad = sum (4 a^2 r^2 - 6 a) c e^(-a r^2)
+    double rad = 0.0, drad = 0.0, d2rad = 0.0;
     for (int p = 0; p < sh.nprim; p++) {
         const double a = env[sh.ptr_exp + p];
         const double e = env[sh.ptr_coef + p] * exp(-a * r2);
         rad += e;
         if (DERIV) drad -= 2.0 * a * e;
+        if (DERIV == 2) d2rad += (4.0 * a * a * r2 - 6.0 * a) * e;
     }
     double px[L + 2], py[L + 2], pz[L + 2];
     px[0] = py[0] = pz[0] = 1.0;
@@ -35,7 +39,7 @@ __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const doubl
         py[k] = py[k - 1] * y;
         pz[k] = pz[k - 1] * z;
     }
-    double cv[DERIV ? 4 : 1][NC];
+    double cv[AO_NCOMP(DERIV)][NC];
     {
         int c = 0;
 #pragma unroll
@@ -53,6 +57,13 @@ __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const doubl
                     cv[2][c] = dmy * rad + mono * y * drad;
                     cv[3][c] = dmz * rad + mono * z * drad;
                 }
+                if (DERIV == 2) {
+                    // lapl (m R) = (lapl m) R + 2 grad m . grad R + m lapl R,  grad m . r = L m
+                    const double lm = (a > 1 ? a * (a - 1) * px[a > 1 ? a - 2 : 0] : 0.0) * py[b] * pz[g] +
+                                      px[a] * (b > 1 ? b * (b - 1) * py[b > 1 ? b - 2 : 0] : 0.0) * pz[g] +
+                                      px[a] * py[b] * (g > 1 ? g * (g - 1) * pz[g > 1 ? g - 2 : 0] : 0.0);
+                    cv[4][c] = lm * rad + mono * (2.0 * L * drad + d2rad);
+                }
                 c++;
             }
     }
@@ -62,7 +73,7 @@ __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const doubl
         const int col = col0 + m;
         if (col < 0 || col >= AO_WIN) continue;
 #pragma unroll
-        for (int comp = 0; comp < (DERIV ? 4 : 1); comp++) {
+        for (int comp = 0; comp < AO_NCOMP(DERIV); comp++) {
             double s = 0.0;
 #pragma unroll
             for (int c = 0; c < NC; c++) s += M[m * NC + c] * cv[comp][c];
@@ -71,13 +82,13 @@ __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const doubl
     }
 }
 
-template <bool DERIV>
+template <int DERIV>
 __global__ void __launch_bounds__(AO_THREADS)
 ao_eval_kernel(const ShellRec *__restrict__ shells, const double *__restrict__ env,
                const int *__restrict__ ao_loc, int sh0, int sh1, const double *__restrict__ coords,
                int64_t ngrid, double *__restrict__ ao, int64_t ngrid_ld, int64_t ao_ld) {
     extern __shared__ double tile[];
-    constexpr int NCOMP = DERIV ? 4 : 1;
+    constexpr int NCOMP = AO_NCOMP(DERIV);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * AO_PTS + lane;
     const bool live = g < ngrid;
@@ -134,18 +145,22 @@ extern "C" int b200qc_eval_gto(const b200qc_basis *basis, int sh0, int sh1, int 
     if (qc_require_basis_device(basis)) return 2;
     QC_REQUIRE(basis != nullptr, "null basis");
     QC_REQUIRE(0 <= sh0 && sh0 < sh1 && sh1 <= basis->nbas, "bad shell range");
-    QC_REQUIRE(deriv == 0 || deriv == 1, "deriv must be 0 or 1");
+    QC_REQUIRE(deriv >= 0 && deriv <= 2, "deriv must be 0, 1 or 2");
     QC_REQUIRE(ngrid_ld >= ngrid && ao_ld >= basis->h_ao_loc[sh1] - basis->h_ao_loc[sh0], "leading dims too small");
     if (ngrid == 0) return 0;
     const int nblk = (int)((ngrid + AO_PTS - 1) / AO_PTS);
-    const size_t smem = sizeof(double) * (deriv ? 4 : 1) * AO_WIN * 33;
+    const size_t smem = sizeof(double) * AO_NCOMP(deriv) * AO_WIN * 33;
     prof_begin(PROF_AO_EVAL, as_stream(stream));
-    if (deriv) {
-        QC_CHECK(cudaFuncSetAttribute(ao_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ao_eval_kernel<true><<<nblk, AO_THREADS, smem, as_stream(stream)>>>(
+    if (deriv == 2) {
+        QC_CHECK(cudaFuncSetAttribute(ao_eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ao_eval_kernel<2><<<nblk, AO_THREADS, smem, as_stream(stream)>>>(
+            basis->d_shells, basis->d_env, basis->d_ao_loc, sh0, sh1, coords, ngrid, ao, ngrid_ld, ao_ld);
+    } else if (deriv == 1) {
+        QC_CHECK(cudaFuncSetAttribute(ao_eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ao_eval_kernel<1><<<nblk, AO_THREADS, smem, as_stream(stream)>>>(
             basis->d_shells, basis->d_env, basis->d_ao_loc, sh0, sh1, coords, ngrid, ao, ngrid_ld, ao_ld);
     } else {
-        ao_eval_kernel<false><<<nblk, AO_THREADS, smem, as_stream(stream)>>>(
+        ao_eval_kernel<0><<<nblk, AO_THREADS, smem, as_stream(stream)>>>(
             basis->d_shells, basis->d_env, basis->d_ao_loc, sh0, sh1, coords, ngrid, ao, ngrid_ld, ao_ld);
     }
     prof_end(as_stream(stream));

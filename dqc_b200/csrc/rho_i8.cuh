@@ -59,8 +59,10 @@ sb_slice_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ 
 
 // ---- B operand: D_sb[nu][mu] = D[idx_nu][idx_mu] gathered and sliced, K-major tiles; scale per row nu ----
 // out (per SB, bytes): [n tile = nu / 64][k tile = mu / 32][slice][(mu % 32) / 16][(nu % 64) / 8][nu % 8][mu % 16]
-// (Variants that staged the bytes in shared memory for 16-byte stores, or kept the gathered row in registers between
-// the two passes, measured 2.5 - 3.9 ms against the 2.2 ms of this plain form at C60: the gathers dominate.)
+// (Measured alternatives at C60, all slower than this plain two-pass, lane-per-column form at 1.9 ms: 16-byte stores
+// staged through shared memory and a gathered row kept in registers between the passes (round 1: 2.5 - 3.9 ms); four
+// columns per lane with 4-byte stores (2.2 ms); the whole row in registers with every gather in flight at once (2.4 ms).
+// The kernel moves 3 GB of planes out and ~10 GB of L2-resident D in; neither LSU instructions nor latency bound it.)
 template <int S, int BN>
 __global__ void __launch_bounds__(256)
 sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const double *__restrict__ dm,
@@ -97,10 +99,15 @@ sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict_
         double y = (a < nao && b < nao) ? row[b] * inv : 0.0;
         signed char *Q = P + (int64_t)(c >> 5) * S * B_PLANE + ((c & 31) >> 4) * (BN * 16) + (c & 15);
 #pragma unroll
-        for (int s = 0; s < S; s++) {
-            Q[s * B_PLANE] = (signed char)slice_digit(y);
-        }
+        for (int s = 0; s < S; s++) Q[s * B_PLANE] = (signed char)slice_digit(y);
     }
+}
+
+template <int S, int BN>
+static void sb_gather_slice_dm_launch(const SBDesc *sbd, int nsb, int max_nsp, const int *idx, const double *dm, int nao,
+                                      const int64_t *p_off, signed char *planes, double *cscale, cudaStream_t st) {
+    dim3 gg((unsigned)(max_nsp / 8), (unsigned)nsb);
+    sb_gather_slice_dm_kernel<S, BN><<<gg, 256, 0, st>>>(sbd, idx, dm, nao, p_off, planes, cscale);
 }
 
 // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
@@ -407,9 +414,8 @@ static int rho_i8_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const in
                       const double *dm, int nao, const signed char *aplanes, const int64_t *a_off,
                       const double *rscale, signed char *bplanes, const int64_t *b_off, double *cscale, double *rho,
                       double *grad, cudaStream_t st) {
-    dim3 gg((unsigned)(max_nsp / 8), (unsigned)nsb);
     prof_begin(PROF_SB_GATHER, st);
-    sb_gather_slice_dm_kernel<S, BN><<<gg, 256, 0, st>>>(sbd, idx, dm, nao, b_off, bplanes, cscale);
+    sb_gather_slice_dm_launch<S, BN>(sbd, nsb, max_nsp, idx, dm, nao, b_off, bplanes, cscale, st);
     prof_end(st);
     QC_LAUNCHED(1);
     // mode bit 16: A cache (4-stage ring + 5 (S = 5) or 3 (S = 6) cached K steps of the A tile), 128 x 64 tiles only

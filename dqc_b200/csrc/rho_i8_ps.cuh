@@ -461,9 +461,8 @@ static int rho_i8_ps_run(const SBDesc *sbd, int nsb, int sbp, int max_nsp, const
                          const double *dm, int nao, const signed char *pplanes, const int64_t *p_off,
                          const double *rscale, signed char *dplanes, const int64_t *d_off, double *cscale, double *rho,
                          double *grad, cudaStream_t st) {
-    dim3 gg((unsigned)(max_nsp / 8), (unsigned)nsb);
     prof_begin(PROF_SB_GATHER, st);
-    sb_gather_slice_dm_kernel<S, I8_BM><<<gg, 256, 0, st>>>(sbd, idx, dm, nao, d_off, dplanes, cscale);
+    sb_gather_slice_dm_launch<S, I8_BM>(sbd, nsb, max_nsp, idx, dm, nao, d_off, dplanes, cscale, st);
     prof_end(st);
     QC_LAUNCHED(1);
     // B200QC_I8_MODE bits 12..16: number of B cache slots (experiments: what the cache does not take stays L1);

@@ -28,7 +28,8 @@ template <int NCOMP>
 __global__ void vxc_vb_sb_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp,
                                  int64_t ngrid_ld, const double *__restrict__ w, const double *__restrict__ vrho,
                                  const double *__restrict__ vgrad, const int64_t *__restrict__ vb_off,
-                                 double *__restrict__ vb) {
+                                 double *__restrict__ vb, const double *__restrict__ vlapl = nullptr) {
+    // NCOMP = 5 (meta-GGA): + 2 w vlapl lapl phi (hcgto.py:477)
     // one warp per grid row
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= ngrid_ld) return;
@@ -37,8 +38,9 @@ __global__ void vxc_vb_sb_kernel(const SBDesc *__restrict__ sbd, const double *_
     const int lane = threadIdx.x & 31;
     const double wg = w[g];
     const double c0 = wg * vrho[g];
-    double c1 = 0, c2 = 0, c3 = 0;
-    if (NCOMP == 4) {
+    double c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    if (NCOMP == 5) c4 = 2.0 * wg * vlapl[g];
+    if (NCOMP >= 4) {
         c1 = 2.0 * wg * vgrad[g];
         c2 = 2.0 * wg * vgrad[ngrid_ld + g];
         c3 = 2.0 * wg * vgrad[2 * ngrid_ld + g];
@@ -48,14 +50,18 @@ __global__ void vxc_vb_sb_kernel(const SBDesc *__restrict__ sbd, const double *_
     const double2 *p1 = reinterpret_cast<const double2 *>(ao + d.ao_off + cs + (int64_t)r * ld);
     const double2 *p2 = reinterpret_cast<const double2 *>(ao + d.ao_off + 2 * cs + (int64_t)r * ld);
     const double2 *p3 = reinterpret_cast<const double2 *>(ao + d.ao_off + 3 * cs + (int64_t)r * ld);
+    const double2 *p4 = reinterpret_cast<const double2 *>(ao + d.ao_off + 4 * cs + (int64_t)r * ld);
     double2 *out = reinterpret_cast<double2 *>(vb + vb_off[sb] + (int64_t)r * ld);
     for (int c = lane; c < ld / 2; c += 32) {
         double2 v = p0[c];
         double2 o = make_double2(c0 * v.x, c0 * v.y);
-        if (NCOMP == 4) {
+        if (NCOMP >= 4) {
             v = p1[c]; o.x += c1 * v.x; o.y += c1 * v.y;
             v = p2[c]; o.x += c2 * v.x; o.y += c2 * v.y;
             v = p3[c]; o.x += c3 * v.x; o.y += c3 * v.y;
+        }
+        if (NCOMP == 5) {
+            v = p4[c]; o.x += c4 * v.x; o.y += c4 * v.y;
         }
         out[c] = o;
     }

@@ -17,6 +17,7 @@
 #define XC_LDA_C_VWN_RPA 5   // VWN-RPA (libxc lda_c_vwn_rpa, the LDA part of libxc's B3LYP)
 #define XC_GGA_X_B88 103
 #define XC_GGA_C_LYP 104
+#define XC_MGGA_X_SCAN 201  // SCAN exchange (libxc mgga_x_scan); needs tau, through b200qc_xc_mgga_unpol only
 #define XC_MAX_TERMS 8
 #define XC_RHO_CUT 1e-15   // densities at or below this contribute exactly zero (libxc-style threshold)
 
@@ -288,6 +289,34 @@ __device__ __forceinline__ void gga_c_pbe_core(double rho, double zeta, double s
     vd = common - dz * (1.0 + zeta) / rho;
     vs = rho * H_y * ct / (phi * phi * r73);
 }
+// SCAN exchange, unpolarised (Sun, Ruzsinszky, Perdew, PRL 115, 036402 (2015); the closed form the reference's own
+// test checks libxc against, dqc/test/test_xc.py:427-455): e = e_x^LDA(rho) F_x(s, alpha),
+//   s = |grad rho| / (2 rho kF), alpha = (tau - tau_W) / tau_unif, tau_W = sigma / (8 rho), tau_unif = 0.3 kF^2 rho.
+// Derivatives by forward-mode duals in (rho, sigma, tau); the functional does not depend on lapl rho.
+__device__ __forceinline__ void mgga_x_scan_unpol(double rho, double sigma, double tau, double &e, double &vr,
+                                                  double &vs, double &vt) {
+    typedef Dual<3> T;
+    const T r = dvar<3>(rho, 0), sg = dvar<3>(sigma, 1), t = dvar<3>(tau, 2);
+    const double a1 = 4.9479, c1x = 0.667, c2x = 0.8, dx = 1.24, mu_ak = 10.0 / 81.0, b3 = 0.5, k1 = 0.065, h0 = 1.174;
+    const double b2 = sqrt(5913.0 / 405000.0), b1 = 511.0 / 13500.0 / (2.0 * b2);
+    const double b4 = mu_ak * mu_ak / k1 - 1606.0 / 18225.0 - b1 * b1;
+    const T kf = dcbrt(r * (3.0 * 9.869604401089358)), kf2 = kf * kf;
+    const T s2 = sg / (4.0 * r * r * kf2);
+    const T alpha = (t - sg / (8.0 * r)) / (0.3 * kf2 * r);
+    const T oma = 1.0 - alpha;
+    const T w1 = b1 * s2 + b2 * oma * dexp(-b3 * (oma * oma));
+    const T x = mu_ak * s2 * (1.0 + (b4 / mu_ak) * s2 * dexp(s2 * (-fabs(b4) / mu_ak))) + w1 * w1;
+    const T h1 = (1.0 + k1) - k1 / (1.0 + x / k1);
+    T gs = dconst<3>(1.0);                           // 1 - exp(-a1 / sqrt(s)) -> 1 (all derivatives 0) as s -> 0
+    if (s2.v > 1e-40) gs = 1.0 - dexp(-a1 / dsqrt(dsqrt(s2)));
+    T fa = dconst<3>(0.0);                           // both branches and all their derivatives vanish at alpha = 1
+    if (oma.v > 1e-12) fa = dexp(-c1x * alpha / oma);
+    else if (oma.v < -1e-12) fa = -dx * dexp(c2x / oma);
+    const T fx = (h1 + fa * (h0 - h1)) * gs;
+    const T r13 = dcbrt(r);
+    const T res = (-0.7385587663820224 * r * r13) * fx;     // -(3/4) (3/pi)^(1/3) rho^(4/3)
+    e = res.v; vr = res.d[0]; vs = res.d[1]; vt = res.d[2];
+}
 }  // namespace xc
 
 // rho (n), grad (3, ld) -> edens (n), vrho (n), vgrad (3, ld)
@@ -412,7 +441,52 @@ __global__ void xc_pol_kernel(XCTerms terms, int64_t n, int64_t ld, const double
     }
 }
 
-static int xc_pack_terms(int nterm, const int *ids, const double *coefs, XCTerms &t, bool &gga) {
+// meta-GGA: rho (n), grad (3, ld), tau (n) -> edens, vrho, vgrad = 2 (de/dsigma) grad rho, vlapl (= 0: no functional here
+// depends on lapl rho), vtau = de/dtau.  LDA / GGA terms of the sum take the same formulas as xc_unpol_kernel.
+__global__ void xc_mgga_unpol_kernel(XCTerms terms, int64_t n, int64_t ld, const double *__restrict__ rho,
+                                     const double *__restrict__ grad, const double *__restrict__ tau,
+                                     double *__restrict__ edens, double *__restrict__ vrho, double *__restrict__ vgrad,
+                                     double *__restrict__ vlapl, double *__restrict__ vtau) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double r = rho[i], tk = tau[i];
+    const double gx = grad[i], gy = grad[ld + i], gz = grad[2 * ld + i];
+    const double sigma = gx * gx + gy * gy + gz * gz;
+    double e = 0, vr = 0, vs = 0, vt = 0;
+    if (r > XC_RHO_CUT) {
+        for (int k = 0; k < terms.n; k++) {
+            double ek = 0, vrk = 0, vsk = 0, vtk = 0;
+            switch (terms.id[k]) {
+                case XC_LDA_X: xc::lda_x_unpol(r, ek, vrk); break;
+                case XC_LDA_C_PW: xc::lda_c_pw_unpol(false, r, ek, vrk); break;
+                case XC_LDA_C_PW_MOD: xc::lda_c_pw_unpol(true, r, ek, vrk); break;
+                case XC_GGA_X_PBE: xc::gga_x_pbe_unpol(r, sigma, ek, vrk, vsk); break;
+                case XC_GGA_C_PBE: {
+                    double vd;
+                    xc::gga_c_pbe_core(r, 0.0, sigma, ek, vrk, vd, vsk);
+                    break;
+                }
+                case XC_MGGA_X_SCAN: xc::mgga_x_scan_unpol(r, sigma, tk, ek, vrk, vsk, vtk); break;
+                default: xc::dual_unpol(terms.id[k], r, sigma, ek, vrk, vsk); break;
+            }
+            e += terms.coef[k] * ek;
+            vr += terms.coef[k] * vrk;
+            vs += terms.coef[k] * vsk;
+            vt += terms.coef[k] * vtk;
+        }
+    }
+    if (edens) edens[i] = e;
+    if (vrho) vrho[i] = vr;
+    if (vgrad) {
+        vgrad[i] = 2.0 * vs * gx;
+        vgrad[ld + i] = 2.0 * vs * gy;
+        vgrad[2 * ld + i] = 2.0 * vs * gz;
+    }
+    if (vlapl) vlapl[i] = 0.0;
+    if (vtau) vtau[i] = vt;
+}
+
+static int xc_pack_terms(int nterm, const int *ids, const double *coefs, XCTerms &t, bool &gga, bool allow_mgga = false) {
     QC_REQUIRE(nterm >= 1 && nterm <= XC_MAX_TERMS, "1..8 functional terms supported");
     t.n = nterm;
     gga = false;
@@ -420,7 +494,7 @@ static int xc_pack_terms(int nterm, const int *ids, const double *coefs, XCTerms
         const int id = ids[k];
         QC_REQUIRE(id == XC_LDA_X || id == XC_LDA_C_PW || id == XC_LDA_C_PW_MOD || id == XC_GGA_X_PBE ||
                        id == XC_GGA_C_PBE || id == XC_LDA_C_VWN || id == XC_LDA_C_VWN_RPA || id == XC_GGA_X_B88 ||
-                       id == XC_GGA_C_LYP, "unknown functional id");
+                       id == XC_GGA_C_LYP || (allow_mgga && id == XC_MGGA_X_SCAN), "unknown functional id");
         gga = gga || id >= 100;
         t.id[k] = id;
         t.coef[k] = coefs[k];
@@ -459,5 +533,25 @@ extern "C" int b200qc_xc_pol(int nterm, const int *h_func_ids, const double *h_c
     prof_end(as_stream(stream));
     QC_LAUNCHED(1);
     if (!gga && vgrad) QC_CHECK(cudaMemsetAsync(vgrad, 0, sizeof(double) * 6 * ld, as_stream(stream)));
+    return 0;
+}
+
+// Meta-GGA functionals (family 4), unpolarised; the spin-polarised exchange follows from the spin-scaling relation on the
+// host side (dqc_b200/xc/b200xc.py).  lapl is accepted for interface symmetry with libxc and not read.
+extern "C" int b200qc_xc_mgga_unpol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n, int64_t ld,
+                                    const double *rho, const double *grad, const double *lapl, const double *tau,
+                                    double *edens, double *vrho, double *vgrad, double *vlapl, double *vtau,
+                                    void *stream) {
+    (void)lapl;
+    XCTerms t;
+    bool gga;
+    if (int rc = xc_pack_terms(nterm, h_func_ids, h_coefs, t, gga, true)) return rc;
+    QC_REQUIRE(rho && grad && tau, "meta-GGA functionals need rho, grad rho and tau");
+    if (n == 0) return 0;
+    prof_begin(PROF_XC, as_stream(stream));
+    xc_mgga_unpol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(t, n, ld, rho, grad, tau, edens, vrho,
+                                                                                    vgrad, vlapl, vtau);
+    prof_end(as_stream(stream));
+    QC_LAUNCHED(1);
     return 0;
 }

@@ -38,16 +38,18 @@ ao_screen_kernel(const ShellRec *__restrict__ shells, const double *__restrict__
             const double r2 = x * x + y * y + z * z, r = sqrt(r2);
             double rl = 1.0;
             for (int k = 0; k < sh.l; k++) rl *= r;
-            double v = 0.0, dv = 0.0;
+            double v = 0.0, dv = 0.0, lv = 0.0;
             for (int q = 0; q < sh.nprim; q++) {
                 const double a = env[sh.ptr_exp + q];
                 const double e = fabs(env[sh.ptr_coef + q]) * exp(-a * r2);
                 v += e;
                 dv += e * (2.0 * a * r * rl + (sh.l > 0 ? sh.l * rl / fmax(r, 1e-300) : 0.0));
+                lv += e * (4.0 * a * a * r2 + 2.0 * a * (2 * sh.l + 3));   // |lapl (r^l Y_lm e^(-a r^2))| / (r^l |Y_lm|)
             }
             v *= rl * ang;
             dv *= ang * 2.0 * (sh.l + 1);   // generous bound on |grad (r^l Y_lm)| / r^(l-1)
-            if (v > eps || (deriv && dv > eps)) mine = true;
+            lv *= rl * ang;
+            if (v > eps || (deriv && dv > eps) || (deriv == 2 && lv > eps)) mine = true;
         }
         if (mine) hit = 1;
         __syncthreads();
@@ -70,13 +72,13 @@ extern "C" int b200qc_ao_screen(const b200qc_basis *basis, int sh0, int sh1, con
 }
 
 // ---- compact AO evaluation: same per-shell arithmetic as ao_eval.cuh, columns = kept shells of the SB ----
-template <bool DERIV>
+template <int DERIV>
 __global__ void __launch_bounds__(AO_THREADS)
 ao_eval_sb_kernel(const ShellRec *__restrict__ shells, const double *__restrict__ env, const SBDesc *__restrict__ sbd,
                   const int *__restrict__ shell_ids, const int *__restrict__ shell_col,
                   const double *__restrict__ coords, int64_t ngrid, int sbp, double *__restrict__ ao) {
     extern __shared__ double tile[];
-    constexpr int NCOMP = DERIV ? 4 : 1;
+    constexpr int NCOMP = AO_NCOMP(DERIV);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = sbp / AO_PTS;
     const int sb = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
@@ -134,20 +136,24 @@ extern "C" int b200qc_eval_gto_sb(const b200qc_basis *basis, int deriv, const do
                                   int nsb, const void *sbdesc, const int *shell_ids, const int *shell_col, double *ao,
                                   void *stream) {
     if (qc_require_basis_device(basis)) return 2;
-    QC_REQUIRE(basis && (deriv == 0 || deriv == 1), "bad arguments");
+    QC_REQUIRE(basis && deriv >= 0 && deriv <= 2, "bad arguments");
     QC_REQUIRE(sbp % AO_PTS == 0, "superblock size must be a multiple of 32");
     if (ngrid == 0 || nsb == 0) return 0;
-    const size_t smem = sizeof(double) * (deriv ? 4 : 1) * AO_WIN * 33;
+    const size_t smem = sizeof(double) * AO_NCOMP(deriv) * AO_WIN * 33;
     const unsigned nblk = (unsigned)nsb * (unsigned)(sbp / AO_PTS);
     cudaStream_t st = as_stream(stream);
     prof_begin(PROF_AO_EVAL, st);
-    if (deriv) {
-        QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ao_eval_sb_kernel<true><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
-                                                               shell_ids, shell_col, coords, ngrid, sbp, ao);
+    if (deriv == 2) {
+        QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ao_eval_sb_kernel<2><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
+                                                            shell_ids, shell_col, coords, ngrid, sbp, ao);
+    } else if (deriv == 1) {
+        QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ao_eval_sb_kernel<1><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
+                                                            shell_ids, shell_col, coords, ngrid, sbp, ao);
     } else {
-        ao_eval_sb_kernel<false><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
-                                                                shell_ids, shell_col, coords, ngrid, sbp, ao);
+        ao_eval_sb_kernel<0><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
+                                                            shell_ids, shell_col, coords, ngrid, sbp, ao);
     }
     prof_end(st);
     QC_LAUNCHED(1);
@@ -171,7 +177,8 @@ __global__ void sb_gather_dm_kernel(const SBDesc *__restrict__ sbd, const int *_
 template <int NCOMP>
 __global__ void __launch_bounds__(GM_THREADS, 2)
 rho_sb_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, const double *__restrict__ dsb, int sbp,
-              int64_t ngrid_ld, double *__restrict__ rho, double *__restrict__ grad) {
+              int64_t ngrid_ld, double *__restrict__ rho, double *__restrict__ grad, double *__restrict__ lapl) {
+    // NCOMP = 5 (meta-GGA storage): component 4 is the AO Laplacian, lapl[g] = sum_nu X_g,nu lapl phi_g,nu
     extern __shared__ __align__(16) double gm_smem[];
     __shared__ double red[2][GM_BM][NCOMP];
     const int tiles = sbp / GM_BM;
@@ -224,10 +231,62 @@ rho_sb_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, con
         const int r = threadIdx.x;
         const int64_t g = (int64_t)sb * sbp + (int64_t)tile * GM_BM + r;
         rho[g] = red[0][r][0] + red[1][r][0];
-        if (NCOMP == 4) {
+        if (NCOMP >= 4) {
 #pragma unroll
             for (int dd = 0; dd < 3; dd++) grad[(int64_t)dd * ngrid_ld + g] = 2.0 * (red[0][r][dd + 1] + red[1][r][dd + 1]);
         }
+        if (NCOMP == 5) lapl[g] = red[0][r][NCOMP - 1] + red[1][r][NCOMP - 1];
+    }
+}
+
+// gg[g] = sum_d sum_mu,nu d_d phi_g,mu D_mu,nu d_d phi_g,nu (hcgto.py:427-429): three GEMMs X_d = (d_d phi) D_sb with the
+// row dots against the same component, accumulated over d.  lapl rho = 2 (lapl part + gg), tau = gg / 2.
+__global__ void __launch_bounds__(GM_THREADS, 2)
+rho_sb_gg_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, const double *__restrict__ dsb, int sbp,
+                 double *__restrict__ gg) {
+    extern __shared__ __align__(16) double gm_smem[];
+    __shared__ double red[2][GM_BM];
+    const int tiles = sbp / GM_BM;
+    const int sb = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+    const SBDesc d = sbd[sb];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int64_t ld = d.nsp;
+    const double *D = dsb + d.d_off;
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+    const int ntile = d.nsp / GM_BN, ktiles = d.nsp / GM_BK;
+    for (int dd = 1; dd <= 3; dd++) {
+        const double *base = ao + d.ao_off + ((int64_t)dd * sbp + (int64_t)tile * GM_BM) * ld;   // component dd, this tile's rows
+        for (int nt = 0; nt < ntile; nt++) {
+            const int n0 = nt * GM_BN;
+            double acc[4][4][2];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            gemm_tile_128x64<true>(base, ld, GM_BM, D + n0, ld, ktiles, acc, gm_smem);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double *row = base + n0 + (int64_t)(wm + i * 8 + (lane >> 2)) * ld + wn + 2 * (lane & 3);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double2 v = *reinterpret_cast<const double2 *>(row + j * 8);
+                    part[i] += acc[i][j][0] * v.x + acc[i][j][1] * v.y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double v = part[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if ((lane & 3) == 0) red[warp & 1][wm + i * 8 + (lane >> 2)] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < GM_BM) {
+        const int r = threadIdx.x;
+        gg[(int64_t)sb * sbp + (int64_t)tile * GM_BM + r] = red[0][r] + red[1][r];
     }
 }
 
@@ -250,13 +309,50 @@ extern "C" int b200qc_rho_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, 
     prof_begin(PROF_RHO, st);
     if (grad) {
         QC_CHECK(cudaFuncSetAttribute(rho_sb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
-        rho_sb_kernel<4><<<nblk, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, ao, dsb, sbp, ngl, rho, grad);
+        rho_sb_kernel<4><<<nblk, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, ao, dsb, sbp, ngl, rho, grad, nullptr);
     } else {
         QC_CHECK(cudaFuncSetAttribute(rho_sb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
-        rho_sb_kernel<1><<<nblk, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, ao, dsb, sbp, ngl, rho, grad);
+        rho_sb_kernel<1><<<nblk, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, ao, dsb, sbp, ngl, rho, grad, nullptr);
     }
     prof_end(st);
     QC_LAUNCHED(1);
+    return 0;
+}
+
+// Meta-GGA densities (hcgto.py:399-438) on the 5-component superblock storage [phi, dx, dy, dz, lapl]:
+// rho, grad (3, ngrid_ld), lapl = lapl rho = 2 (sum X lapl phi + gg), kin = tau = gg / 2.  fp64 DMMA engine.
+__global__ void mgga_finish_kernel(int64_t n, double *__restrict__ lapl, double *__restrict__ kin) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double gg = kin[i];
+    lapl[i] = 2.0 * (lapl[i] + gg);
+    kin[i] = 0.5 * gg;
+}
+
+extern "C" int b200qc_rho_sb_mgga(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                                  const double *dm, int nao, double *dsb, double *rho, double *grad, double *lapl,
+                                  double *kin, void *stream) {
+    QC_REQUIRE(sbp % GM_BM == 0, "superblock size must be a multiple of 128");
+    QC_REQUIRE(rho && grad && lapl && kin, "all four outputs are needed");
+    if (nsb == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    const SBDesc *sbd = (const SBDesc *)sbdesc;
+    const int64_t ngl = (int64_t)nsb * sbp;
+    prof_begin(PROF_SB_GATHER, st);
+    dim3 gg((unsigned)(((int64_t)max_nsp * max_nsp + 1023) / 1024 > 64 ? 64 : ((int64_t)max_nsp * max_nsp + 1023) / 1024),
+            (unsigned)nsb);
+    sb_gather_dm_kernel<<<gg, 256, 0, st>>>(sbd, idx, dm, nao, dsb);
+    prof_end(st);
+    QC_LAUNCHED(1);
+    const unsigned nblk = (unsigned)nsb * (unsigned)(sbp / GM_BM);
+    prof_begin(PROF_RHO, st);
+    QC_CHECK(cudaFuncSetAttribute(rho_sb_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
+    rho_sb_kernel<5><<<nblk, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, ao, dsb, sbp, ngl, rho, grad, lapl);
+    QC_CHECK(cudaFuncSetAttribute(rho_sb_gg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
+    rho_sb_gg_kernel<<<nblk, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, ao, dsb, sbp, kin);
+    mgga_finish_kernel<<<(unsigned)((ngl + 255) / 256), 256, 0, st>>>(ngl, lapl, kin);
+    prof_end(st);
+    QC_LAUNCHED(3);
     return 0;
 }
 
@@ -265,7 +361,8 @@ extern "C" int b200qc_rho_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, 
 __global__ void __launch_bounds__(GM_THREADS, 2)
 vxc_sb_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, const double *__restrict__ ao,
                    const double *__restrict__ vb, const int64_t *__restrict__ vb_off, int sbp, int nao,
-                   double *__restrict__ mat) {
+                   double *__restrict__ mat, int acomp) {
+    // acomp: component of the AO storage on the left (0 = phi; 1..3 = d_d phi for the meta-GGA tau term)
     extern __shared__ __align__(16) double gm_smem[];
     const SBDesc d = sbd[blockIdx.y];
     const int ntn = d.nsp / GM_BN, ntm = (d.nsp + GM_BM - 1) / GM_BM;
@@ -278,7 +375,7 @@ vxc_sb_gemm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict__ idx, 
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    gemm_tile_128x64<false>(ao + d.ao_off + m0, ld, min(GM_BM, d.nsp - m0), vb + vb_off[blockIdx.y] + n0, ld,
+    gemm_tile_128x64<false>(ao + d.ao_off + (int64_t)acomp * sbp * ld + m0, ld, min(GM_BM, d.nsp - m0), vb + vb_off[blockIdx.y] + n0, ld,
                             sbp / GM_BK, acc, gm_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
@@ -323,8 +420,65 @@ extern "C" int b200qc_vxc_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, 
     dim3 grid((unsigned)maxtiles, (unsigned)nsb);
     QC_CHECK(cudaFuncSetAttribute(vxc_sb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
     prof_begin(PROF_VXC_GEMM, st);
-    vxc_sb_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, idx, ao, vb, vb_off, sbp, nao, mat);
+    vxc_sb_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, idx, ao, vb, vb_off, sbp, nao, mat, 0);
     prof_end(st);
     QC_LAUNCHED(1);
+    return 0;
+}
+
+// Meta-GGA Vxc (hcgto.py:463-489) on the 5-component storage:
+//   mat = sum_g w phi^T (vrho phi + 2 vgrad . grad phi + 2 vlapl lapl phi) + sum_d (d_d phi)^T w (2 vlapl + vkin / 2) (d_d phi)
+// (the caller symmetrises, like the reference).  vlapl / vkin are de/d(lapl rho) and de/dtau.  fp64 DMMA engine.
+__global__ void sb_scale_rows_kernel(const SBDesc *__restrict__ sbd, const double *__restrict__ ao, int sbp, int64_t ngrid_ld,
+                                     int comp, const double *__restrict__ w, const double *__restrict__ vlapl,
+                                     const double *__restrict__ vkin, const int64_t *__restrict__ vb_off,
+                                     double *__restrict__ vb) {
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per grid row
+    if (g >= ngrid_ld) return;
+    const int sb = (int)(g / sbp), r = (int)(g - (int64_t)sb * sbp);
+    const SBDesc d = sbd[sb];
+    const int lane = threadIdx.x & 31;
+    const double cf = w[g] * (2.0 * vlapl[g] + 0.5 * vkin[g]);
+    const int64_t ld = d.nsp;
+    const double2 *p = reinterpret_cast<const double2 *>(ao + d.ao_off + ((int64_t)comp * sbp + r) * ld);
+    double2 *out = reinterpret_cast<double2 *>(vb + vb_off[sb] + (int64_t)r * ld);
+    for (int c = lane; c < ld / 2; c += 32) {
+        const double2 v = p[c];
+        out[c] = make_double2(cf * v.x, cf * v.y);
+    }
+}
+
+extern "C" int b200qc_vxc_sb_mgga(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                                  const double *weights, const double *vrho, const double *vgrad, const double *vlapl,
+                                  const double *vkin, int nao, const int64_t *vb_off, double *vb, double *mat,
+                                  void *stream) {
+    QC_REQUIRE(sbp % GM_BM == 0, "superblock size must be a multiple of 128");
+    QC_REQUIRE(vrho && vgrad && vlapl && vkin, "all four potentials are needed");
+    cudaStream_t st = as_stream(stream);
+    QC_CHECK(cudaMemsetAsync(mat, 0, sizeof(double) * nao * nao, st));
+    if (nsb == 0) return 0;
+    const SBDesc *sbd = (const SBDesc *)sbdesc;
+    const int64_t ngl = (int64_t)nsb * sbp;
+    const int wpb = 8;
+    const unsigned nb1 = (unsigned)((ngl + wpb - 1) / wpb);
+    const int maxtiles = (max_nsp / GM_BN) * ((max_nsp + GM_BM - 1) / GM_BM);
+    dim3 grid((unsigned)maxtiles, (unsigned)nsb);
+    QC_CHECK(cudaFuncSetAttribute(vxc_sb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
+    prof_begin(PROF_VXC_VB, st);
+    vxc_vb_sb_kernel<5><<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, weights, vrho, vgrad, vb_off, vb, vlapl);
+    prof_end(st);
+    prof_begin(PROF_VXC_GEMM, st);
+    vxc_sb_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, idx, ao, vb, vb_off, sbp, nao, mat, 0);
+    prof_end(st);
+    QC_LAUNCHED(2);
+    for (int dd = 1; dd <= 3; dd++) {
+        prof_begin(PROF_VXC_VB, st);
+        sb_scale_rows_kernel<<<nb1, wpb * 32, 0, st>>>(sbd, ao, sbp, ngl, dd, weights, vlapl, vkin, vb_off, vb);
+        prof_end(st);
+        prof_begin(PROF_VXC_GEMM, st);
+        vxc_sb_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, st>>>(sbd, idx, ao, vb, vb_off, sbp, nao, mat, dd);
+        prof_end(st);
+        QC_LAUNCHED(2);
+    }
     return 0;
 }

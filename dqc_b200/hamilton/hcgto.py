@@ -152,14 +152,15 @@ class HamiltonCGTO(BaseHamilton):
     def setup_grid(self, grid: BaseGrid, xc: Optional[BaseXC] = None) -> None:
         self.xc = xc
         self.xcfamily = 1 if xc is None else xc.family
-        if self.xcfamily not in (1, 2):
-            raise NotImplementedError("meta-GGA functionals are not on the B200 Fock-build path yet")
+        if self.xcfamily not in (1, 2, 4):
+            raise NotImplementedError("unknown functional family %s" % self.xcfamily)
         self.grid = grid
         assert grid.coord_type == "cart"
         rgrid_all = grid.get_rgrid().to(self.device).to(torch.float64).contiguous()
         dvol_all = grid.get_dvolume().to(self.device)
         self._ngrid_total = rgrid_all.shape[0]
-        deriv = 1 if self.xcfamily == 2 else 0
+        # AO components kept on the grid: LDA phi; GGA + grad phi; meta-GGA + lapl phi (hcgto.py:165-186)
+        deriv = {1: 0, 2: 1, 4: 2}[self.xcfamily]
         sbp, eps = config.SB_POINTS, config.AO_SCREEN
         s0, s1 = self.libcint_wrapper.shell_idxs
         logger.log("Calculating the basis values in the grid")
@@ -169,7 +170,10 @@ class HamiltonCGTO(BaseHamilton):
             flags = _lib.ao_screen(self._devbasis, s0, s1, rgrid_all, sbp, eps, deriv).cpu().numpy()
             sizes = np.diff(self._devbasis.ao_loc[s0:s1 + 1]).astype(np.float64)
             nsp = np.maximum(64.0, np.ceil((flags.astype(np.float64) * sizes[None, :]).sum(1) / 64.0) * 64.0)
-            csum = np.concatenate([[0.0], np.cumsum(nsp * nsp + 64.0 * nsp)])
+            # cost model of a superblock: the GEMM-shaped kernels go with nsp^2, the HBM-bound passes over the AO values
+            # with nsp; at C60 (sum nsp^2 = 6.2e8 -> 5 ms, sum nsp = 1.1e6 -> 8 ms) the ratio of the two coefficients is
+            # about 900
+            csum = np.concatenate([[0.0], np.cumsum(nsp * nsp + config.SB_COST_LINEAR * nsp)])
             world, rank = self._ctx.world, self._ctx.rank
             bounds = [int(np.searchsorted(csum, csum[-1] * r / world)) for r in range(world)] + [len(nsp)]
             bounds = [min(max(b, 0), len(nsp)) for b in bounds]
@@ -183,7 +187,8 @@ class HamiltonCGTO(BaseHamilton):
                                        i8_variant=config.I8_VARIANT, rho_i8_slices=config.RHO_I8_SLICES)
         self.is_grid_set = True
         self.is_ao_set = True
-        self.is_grad_ao_set = self.xcfamily == 2
+        self.is_grad_ao_set = self.xcfamily >= 2
+        self.is_lapl_ao_set = self.xcfamily == 4
 
     # the reference's attribute names, rebuilt on demand from the compact storage (API parity only)
     @property
@@ -192,7 +197,11 @@ class HamiltonCGTO(BaseHamilton):
 
     @property
     def grad_basis(self) -> torch.Tensor:
-        return self._gb.dense_ao()[1:]
+        return self._gb.dense_ao()[1:4]
+
+    @property
+    def lapl_basis(self) -> torch.Tensor:
+        return self._gb.dense_ao()[4]
 
     @property
     def basis_dvolume(self) -> torch.Tensor:
@@ -331,7 +340,15 @@ class HamiltonCGTO(BaseHamilton):
         bshape = potinfo.value.shape[:-1]
         n = potinfo.value.shape[-1]
         v2 = potinfo.value.reshape(-1, n)
-        g2 = potinfo.grad.reshape(-1, 3, n) if (self.xcfamily == 2 and potinfo.grad is not None) else None
+        g2 = potinfo.grad.reshape(-1, 3, n) if (self.xcfamily >= 2 and potinfo.grad is not None) else None
+        if self.xcfamily == 4:
+            # meta-GGA: + 2 vlapl lapl phi in vb and sum_d dphi_d^T w (2 vlapl + vkin / 2) dphi_d  (hcgto.py:473-489)
+            assert potinfo.lapl is not None and potinfo.kin is not None and g2 is not None
+            l2, k2 = potinfo.lapl.reshape(-1, n), potinfo.kin.reshape(-1, n)
+            ngl = self._gb.ngl
+            pad = lambda t: torch.nn.functional.pad(t, (0, ngl - n)).contiguous()
+            mats = [self._gb.vxc_mat_mgga(pad(v2[b]), pad(g2[b]), pad(l2[b]), pad(k2[b])) for b in range(v2.shape[0])]
+            return torch.stack(mats).reshape(*bshape, self._nao_ao, self._nao_ao)
         mats = [self._vmat_ao_partial(v2[b], None if g2 is None else g2[b]) for b in range(v2.shape[0])]
         return torch.stack(mats).reshape(*bshape, self._nao_ao, self._nao_ao)
 
@@ -343,10 +360,26 @@ class HamiltonCGTO(BaseHamilton):
         dmtot = dm.u + dm.d if polarized else dm
         assert dmtot.ndim == 2, "get_fock_2e handles one density at a time"
         parts: List[torch.Tensor] = []
+        side = None
         if self._df is not None:
             if exx != 0.0 and not config.DF_EXCHANGE:
                 raise RuntimeError("Exact exchange cannot be computed with density fitting")
-            parts.append(self._df.elrep_ao_partial(self._orthozer.unconvert_dm(dmtot).contiguous()))
+            dmao_j = self._orthozer.unconvert_dm(dmtot).contiguous()
+            if self._ctx.world > 1 and dmao_j.is_cuda and config.DFJ_SIDE_STREAM:
+                # sharded build: DF-J has a collective in its middle (the fitting coefficients need every rank's slice
+                # of temp).  It runs on a second stream so that the exchange and its latency hide behind the XC kernels
+                # of the main stream instead of stalling the step (round 1, 8 GPUs: 0.56 ms of the 3.97 ms step was in
+                # no kernel at all).  Every build starts with side.wait_stream(main): blocks the caching allocator hands
+                # back to either stream are not in use by the other.
+                main = torch.cuda.current_stream(self.device)
+                if getattr(self, "_side_stream", None) is None:
+                    self._side_stream = torch.cuda.Stream(device=self.device)
+                side = self._side_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    parts.append(self._df.elrep_ao_partial(dmao_j))
+            else:
+                parts.append(self._df.elrep_ao_partial(dmao_j))
             if exx != 0.0:
                 if polarized:
                     parts.extend([self._dfk_ao_partial(dm.u, 2.0), self._dfk_ao_partial(dm.d, 2.0)])
@@ -365,6 +398,8 @@ class HamiltonCGTO(BaseHamilton):
         if with_xc and self.xc is not None:
             vx = self._vxc_ao_partial(dm)
             parts.extend([vx.u, vx.d] if polarized else [vx])
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
         parts = self._ctx.allreduce_packed(parts)
         j_ao = _symm(parts[0])
         xcs = parts[1 + nk:]
@@ -436,6 +471,11 @@ class HamiltonCGTO(BaseHamilton):
         bshape, dm2 = self._flat(dm)
         dmdmt = self._orthozer.unconvert_dm(_symm(dm2))
         ng, gga = self.rgrid.shape[0], self.xcfamily == 2
+        if self.xcfamily == 4:
+            # meta-GGA: also lapl rho = 2 (sum X lapl phi + gg) and tau = gg / 2 (hcgto.py:420-438)
+            outs = [self._gb.rho_mgga(dmdmt[b].contiguous()) for b in range(dmdmt.shape[0])]
+            st = lambda i, *mid: torch.stack([o[i][..., :ng] for o in outs]).reshape(*bshape, *mid, ng)
+            return ValGrad(value=st(0), grad=st(1, 3), lapl=st(2), kin=st(3))
         vals, grads = [], []
         for b in range(dmdmt.shape[0]):
             rho, grad = self._gb.rho(dmdmt[b].contiguous(), gga)

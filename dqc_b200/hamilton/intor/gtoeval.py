@@ -11,7 +11,7 @@ __all__ = ["eval_gto", "eval_gradgto", "eval_laplgto", "eval_gto_padded"]
 
 
 def eval_gto_padded(wrapper: LibcintWrapper, rgrid: torch.Tensor, deriv: int) -> torch.Tensor:
-    """(ncomp, ngrid_ld, ao_ld) zero-padded; ncomp = 1 (values) or 4 (values, d/dx, d/dy, d/dz)."""
+    """(ncomp, ngrid_ld, ao_ld) zero-padded; ncomp = 1 (values), 4 (values, d/dx, d/dy, d/dz) or 5 (+ Laplacian)."""
     dev = rgrid.device if rgrid.is_cuda else _device(wrapper)
     db = wrapper.device_basis(dev)
     s0, s1 = wrapper.shell_idxs
@@ -29,4 +29,6 @@ def eval_gradgto(wrapper: LibcintWrapper, rgrid: torch.Tensor, *, to_transpose: 
 
 
 def eval_laplgto(wrapper: LibcintWrapper, rgrid: torch.Tensor, *, to_transpose: bool = False) -> torch.Tensor:
-    raise NotImplementedError("Laplacian AOs (meta-GGA) are not on the LDA/GGA Fock-build path (SURVEY 8f rank 4)")
+    """Laplacian of the AOs (the reference sums the xx, yy, zz components of GTOval_sph_deriv2, gtoeval.py:66-73)."""
+    ao = eval_gto_padded(wrapper, rgrid, 2)[4, :rgrid.shape[0], :wrapper.nao()]
+    return ao.contiguous() if to_transpose else ao.transpose(-2, -1).contiguous()

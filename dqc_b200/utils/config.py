@@ -44,6 +44,11 @@ class _Config:
     # without density fitting, keep both dense layouts of (ij|kl) in HBM when 2 * 8 * nao^4 bytes fit under
     # this (single GPU); beyond it J/K are built directly from Schwarz-screened quartets every iteration
     ERI_STORE_MAX_BYTES: int = int(float(os.environ.get("B200QC_ERI_STORE_MAX_BYTES", str(32 * 1024 ** 3))))
+    # sharded builds: run DF-J (whose fitting-coefficient exchange sits in the middle of it) on a second stream beside
+    # the XC kernels
+    DFJ_SIDE_STREAM: bool = os.environ.get("B200QC_DFJ_SIDE_STREAM", "1") != "0"
+    # weight of the linear term of the superblock cost model nsp^2 + c nsp used to deal superblocks to ranks
+    SB_COST_LINEAR: float = float(os.environ.get("B200QC_SB_COST_LINEAR", "900"))
     # a shell is dropped from a superblock when its envelope stays below this on every point of it
     # (0 keeps every shell everywhere, like the reference's non0tab = 1)
     AO_SCREEN: float = float(os.environ.get("B200QC_AO_SCREEN", "1e-12"))

@@ -1,4 +1,4 @@
-"""Built-in LDA / GGA functionals evaluated by the K3 CUDA kernel (b200qc_xc_unpol / _pol).
+"""Built-in LDA / GGA / meta-GGA functionals evaluated by the K3 CUDA kernel (b200qc_xc_unpol / _pol / _mgga_unpol).
 
 Plays the role of the reference's libxc bridge (dqc/xc/libxc.py:24-242 + libxc_wrapper.py:380-413):
 same inputs (rho, grad rho; SpinParam for polarised), same outputs (energy per unit VOLUME;
@@ -29,7 +29,38 @@ class B200XC(BaseXC):
         return self._family
 
     # ---- kernel plumbing: flatten the batch dimensions, one launch per batch entry ----
+    def _run_mgga(self, densinfo, want_e: bool, want_v: bool):
+        """Family 4.  Unpolarised: one launch of b200qc_xc_mgga_unpol per batch entry.  Polarised: the built-in
+        meta-GGA is an exchange functional, e[ru, rd] = (e[2 ru] + e[2 rd]) / 2 (the relation the reference's own test
+        uses, dqc/test/test_xc.py:272-273), i.e. the unpolarised kernel on the doubled spin densities; its potentials
+        with respect to the doubled inputs ARE the spin potentials (the factors 1/2 and 2 cancel)."""
+        for _, name in self.terms:
+            if _lib.FUNC_FAMILY[name] == 4 and "_x_" not in name:
+                raise NotImplementedError("spin-polarised meta-GGA correlation is not built in")
+
+        def one(info: ValGrad, scale: float):
+            rho = info.value
+            bshape, n = rho.shape[:-1], rho.shape[-1]
+            flat = lambda t, *mid: (t * scale).reshape(-1, *mid, n).contiguous()
+            r2, g2, l2, k2 = flat(rho), flat(info.grad, 3), flat(info.lapl), flat(info.kin)
+            outs = [_lib.xc_mgga_unpol(self.terms, r2[b], g2[b], l2[b], k2[b], want_e, want_v) for b in range(r2.shape[0])]
+            e = torch.stack([o[0] for o in outs]).reshape(*bshape, n) if want_e else None
+            if not want_v:
+                return e, None
+            st = lambda i, *mid: torch.stack([o[i] for o in outs]).reshape(*bshape, *mid, n)
+            return e, ValGrad(value=st(1), grad=st(2, 3), lapl=st(3), kin=st(4))
+        if isinstance(densinfo, ValGrad):
+            return one(densinfo, 1.0)
+        if any(_lib.FUNC_FAMILY[name] != 4 for _, name in self.terms):
+            raise NotImplementedError("spin-polarised sums of meta-GGA exchange with other functionals are not built in")
+        eu, vu = one(densinfo.u, 2.0)
+        ed, vd = one(densinfo.d, 2.0)
+        e = 0.5 * (eu + ed) if want_e else None
+        return e, (SpinParam(u=vu, d=vd) if want_v else None)
+
     def _run(self, densinfo, want_e: bool, want_v: bool):
+        if self._family == 4:
+            return self._run_mgga(densinfo, want_e, want_v)
         gga = self._family == 2
         if isinstance(densinfo, ValGrad):
             rho = densinfo.value

@@ -56,9 +56,10 @@ int b200qc_rys_upload(int nmax, double h, int deg, double xmax, const double *co
                       const double *const *h_herm);
 
 /* ---- K1: AO values on the grid -- replaces GTOval_sph / GTOval_ip_sph ------------------ */
-/* gtoeval.py:196-239 (eval_gto / eval_gradgto with to_transpose=True).
- * coords: (ngrid, 3).  ao: [ncomp][ngrid_ld][ao_ld] with ncomp = 1 (deriv 0: values) or
- * 4 (deriv 1: value, d/dx, d/dy, d/dz); rows >= ngrid and columns >= nao are left untouched. */
+/* gtoeval.py:196-260 (eval_gto / eval_gradgto / eval_laplgto with to_transpose=True).
+ * coords: (ngrid, 3).  ao: [ncomp][ngrid_ld][ao_ld] with ncomp = 1 (deriv 0: values), 4 (deriv 1: value, d/dx,
+ * d/dy, d/dz) or 5 (deriv 2: those and the Laplacian, the meta-GGA storage of hcgto.py:183-186); rows >= ngrid
+ * and columns >= nao are left untouched. */
 int b200qc_eval_gto(const b200qc_basis *basis, int sh0, int sh1, int deriv, const double *coords,
                     int64_t ngrid, double *ao, int64_t ngrid_ld, int64_t ao_ld, void *stream);
 
@@ -85,6 +86,13 @@ int b200qc_rho(const double *ao, int64_t ngrid_ld, int64_t ao_ld, const double *
 int b200qc_xc_unpol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n, int64_t ld,
                     const double *rho, const double *grad, double *edens, double *vrho, double *vgrad,
                     void *stream);
+/* meta-GGA (family 4) sums, unpolarised -- replaces the mgga branch of libxc.py:124-242 / libxc_wrapper.py:380-413:
+ * inputs rho (n), grad (3, ld), lapl (n; accepted, no built-in functional reads it), tau (n); outputs edens, vrho,
+ * vgrad = 2 (de/dsigma) grad, vlapl = de/d(lapl rho) (zero), vtau = de/dtau.  Extra func id: 201 mgga_x_scan (the
+ * closed form of dqc/test/test_xc.py:427-455); LDA / GGA ids may be mixed in. */
+int b200qc_xc_mgga_unpol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n, int64_t ld,
+                         const double *rho, const double *grad, const double *lapl, const double *tau, double *edens,
+                         double *vrho, double *vgrad, double *vlapl, double *vtau, void *stream);
 /* spin-polarised variant: rho (2, n) = up, down; grad (2, 3, n); vrho (2, n); vgrad (2, 3, n) */
 int b200qc_xc_pol(int nterm, const int *h_func_ids, const double *h_coefs, int64_t n, int64_t ld,
                   const double *rho, const double *grad, double *edens, double *vrho, double *vgrad,
@@ -106,7 +114,7 @@ int b200qc_vxc_mat(const double *ao, int64_t ngrid_ld, int64_t ao_ld, const doub
  * ao_off: start of the SB's compact AO block [ncomp][sbp][nsp] (doubles); d_off: start of its gathered
  * density (nsp x nsp) in the scratch; nsp: kept AOs padded to a multiple of 64; idx: AO index of every
  * compact column (padding = nao); shell_ids / shell_col: kept shells and their first compact column. */
-/* flags: (nsb, sh1 - sh0) bytes, 1 = shell kept on that SB; deriv = 1 also bounds the gradient */
+/* flags: (nsb, sh1 - sh0) bytes, 1 = shell kept on that SB; deriv = 1 also bounds the gradient, 2 the Laplacian */
 int b200qc_ao_screen(const b200qc_basis *basis, int sh0, int sh1, const double *coords, int64_t ngrid, int sbp,
                      double eps, int deriv, unsigned char *flags, void *stream);
 /* compact AO values (pre-zeroed buffer); same arithmetic as b200qc_eval_gto */
@@ -121,6 +129,17 @@ int b200qc_rho_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *
 int b200qc_vxc_sb(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
                   const double *weights, const double *vrho, const double *vgrad, int nao, const int64_t *vb_off,
                   double *vb, double *mat, void *stream);
+
+/* Meta-GGA forms of the two contractions on the 5-component storage [phi, dx, dy, dz, lapl] (b200qc_eval_gto_sb with
+ * deriv = 2), fp64 DMMA engine -- hcgto.py:420-438 and 473-489:
+ *   lapl = 2 (sum X lapl phi + gg), kin = gg / 2, gg = sum_d (d_d phi) D (d_d phi), X = phi D;
+ *   mat = sum_g w [phi^T (vrho phi + 2 vgrad . grad phi + 2 vlapl lapl phi) + sum_d (d_d phi)^T (2 vlapl + vkin / 2) (d_d phi)]. */
+int b200qc_rho_sb_mgga(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                       const double *dm, int nao, double *dsb, double *rho, double *grad, double *lapl, double *kin,
+                       void *stream);
+int b200qc_vxc_sb_mgga(const void *sbdesc, int nsb, int sbp, int max_nsp, const int *idx, const double *ao,
+                       const double *weights, const double *vrho, const double *vgrad, const double *vlapl,
+                       const double *vkin, int nao, const int64_t *vb_off, double *vb, double *mat, void *stream);
 
 /* K4 on tcgen05: the same contraction as b200qc_vxc_sb with the GEMM done as an error-free sliced int8
  * product (Ozaki scheme, nslice = 5 or 6 slices of 7 bits, tcgen05.mma.kind::i8 with int32 accumulation in

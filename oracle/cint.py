@@ -82,14 +82,15 @@ def int2e(atm, bas, env, shls=None):
 
 
 def eval_gto(atm, bas, env, coords, deriv=0, shls=None):
-    """deriv=0 -> (ngrid, nao); deriv=1 -> (3, ngrid, nao) (the to_transpose=True layouts)."""
+    """deriv=0 -> (ngrid, nao); deriv=1 -> (3, ngrid, nao); deriv=2 -> (ngrid, nao) Laplacian (the to_transpose=True
+    layouts of eval_gto / eval_gradgto / eval_laplgto)."""
     atm, bas, env = _prep(atm, bas, env)
     coords = np.ascontiguousarray(coords, dtype=np.float64)
     nb = len(bas)
     s = shls or (0, nb)
     ng = coords.shape[0]
     nao = _n(bas, s[0], s[1])
-    out = np.zeros((3, ng, nao) if deriv else (ng, nao))
+    out = np.zeros((3, ng, nao) if deriv == 1 else (ng, nao))
     ao_loc = ao_loc_sph(bas)
     sl = (ctypes.c_int * 2)(*s)
     lib().orc_eval_gto(ctypes.c_int(deriv), ctypes.c_int(ng), _p(coords), _p(out), sl, _p(ao_loc), _p(atm),

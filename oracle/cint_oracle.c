@@ -605,6 +605,8 @@ void orc_int2e(double *out, const int *shls_slice, const int *ao_loc, const int 
 }
 
 /* ------------------------------------------------------------------ AO values on grid points
+ * deriv = 2: out[g][mu] = Laplacian of phi_mu (eval_laplgto, to_transpose=True: the reference sums the xx, yy, zz
+ *            components of GTOval_sph_deriv2, dqc/hamilton/intor/gtoeval.py:66-73)
  * deriv = 0: out[g][mu]              (what eval_gto(..., to_transpose=True) returns)
  * deriv = 1: out[comp][g][mu], comp = 0 value? NO: reference keeps them separate; here
  *            out[0..2][g][mu] = d/dx, d/dy, d/dz phi_mu (eval_gradgto, to_transpose=True).
@@ -617,7 +619,7 @@ void orc_eval_gto(int deriv, int ngrid, const double *coords, double *out, const
     (void)nbas;
     int sh0 = shls_slice[0], sh1 = shls_slice[1];
     size_t nao = ao_loc[sh1] - ao_loc[sh0];
-    int ncomp = deriv ? 3 : 1;
+    int ncomp = deriv == 1 ? 3 : 1;
 #pragma omp parallel for schedule(static)
     for (int g = 0; g < ngrid; g++) {
         double cartv[3][NCART(LMAX)];
@@ -628,11 +630,12 @@ void orc_eval_gto(int deriv, int ngrid, const double *coords, double *out, const
             int l = S.l, nc = NCART(l), ns = 2 * l + 1;
             double x = coords[3 * g] - S.R[0], y = coords[3 * g + 1] - S.R[1], z = coords[3 * g + 2] - S.R[2];
             double r2 = x * x + y * y + z * z;
-            double rad = 0.0, drad = 0.0; /* sum c e^{-a r2}; sum -2 a c e^{-a r2} */
+            double rad = 0.0, drad = 0.0, d2rad = 0.0; /* sum c e^{-a r2}; sum -2 a c e^{-a r2}; Laplacian of the radial sum */
             for (int p = 0; p < S.nprim; p++) {
                 double e = S.co[p] * exp(-S.ex[p] * r2);
                 rad += e;
                 drad += -2.0 * S.ex[p] * e;
+                d2rad += (4.0 * S.ex[p] * S.ex[p] * r2 - 6.0 * S.ex[p]) * e;
             }
             cart_powers(l, lx, ly, lz);
             double px[LMAX + 2], py[LMAX + 2], pz[LMAX + 2];
@@ -647,6 +650,12 @@ void orc_eval_gto(int deriv, int ngrid, const double *coords, double *out, const
                 double mono = px[a] * py[b] * pz[cz];
                 if (!deriv) {
                     cartv[0][c] = mono * rad;
+                } else if (deriv == 2) {
+                    /* lapl (m R) = (lapl m) R + 2 grad m . grad R + m lapl R, grad R = r drad, grad m . r = l m */
+                    double lm = (a > 1 ? a * (a - 1) * px[a - 2] : 0.0) * py[b] * pz[cz] +
+                                px[a] * (b > 1 ? b * (b - 1) * py[b - 2] : 0.0) * pz[cz] +
+                                px[a] * py[b] * (cz > 1 ? cz * (cz - 1) * pz[cz - 2] : 0.0);
+                    cartv[0][c] = lm * rad + mono * (2.0 * l * drad + d2rad);
                 } else {
                     double dmx = (a ? a * px[a - 1] : 0.0) * py[b] * pz[cz];
                     double dmy = px[a] * (b ? b * py[b - 1] : 0.0) * pz[cz];

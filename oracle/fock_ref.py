@@ -103,6 +103,8 @@ class RefHamilton:
         self.basis_dvolume = self.basis * self.dvolume.unsqueeze(-1)
         if self.xcfamily >= 2:
             self.grad_basis = torch.as_tensor(cint.eval_gto(self.atm, self.bas, self.env, self.rgrid, 1, self.shl))
+        if self.xcfamily == 4:      # hcgto.py:183-186
+            self.lapl_basis = torch.as_tensor(cint.eval_gto(self.atm, self.bas, self.env, self.rgrid, 2, self.shl))
 
     # ---- orbital converter ----
     def conv2(self, m):
@@ -155,6 +157,45 @@ class RefHamilton:
                     gdens[d, i0:i1] = torch.einsum("ri,ri->r", dmao, self.grad_basis[d, i0:i1]) * 2
         return dens, gdens
 
+    def dm2densinfo_mgga(self, dm):
+        """hcgto.py:399-438 with xcfamily == 4: (dens, gdens, lapldens, kindens)."""
+        dmdmt = self.unconv_dm((dm + dm.transpose(-2, -1)) * 0.5)
+        ng, nb = self.basis.shape
+        dens, lapldens, kindens = (torch.empty(ng, dtype=torch.float64) for _ in range(3))
+        gdens = torch.empty(3, ng, dtype=torch.float64)
+        for i0, i1 in chunk_ranges(ng, nb):
+            b = self.basis[i0:i1]
+            dmao = torch.matmul(b, dmdmt)
+            dens[i0:i1] = torch.einsum("ri,ri->r", dmao, b)
+            gg = torch.zeros(i1 - i0, dtype=torch.float64)
+            for d in range(3):
+                gb = self.grad_basis[d, i0:i1]
+                gdens[d, i0:i1] = torch.einsum("ri,ri->r", dmao, gb) * 2
+                gg += torch.einsum("ri,ri->r", torch.matmul(gb, dmdmt), gb)
+            lapl_basis = torch.einsum("ri,ri->r", dmao, self.lapl_basis[i0:i1])
+            lapldens[i0:i1] = (lapl_basis + gg) * 2
+            kindens[i0:i1] = gg * 0.5
+        return dens, gdens, lapldens, kindens
+
+    def vxc_from_potinfo_mgga(self, vrho, vgrad, vlapl, vkin):
+        """hcgto.py:445-495 with xcfamily == 4."""
+        ng, nb = self.basis.shape
+        mat = torch.zeros(nb, nb, dtype=torch.float64)
+        for i0, i1 in chunk_ranges(ng, nb):
+            vb = vrho[i0:i1].unsqueeze(-1) * self.basis[i0:i1]
+            vg = vgrad[:, i0:i1] * 2
+            for d in range(3):
+                vb += vg[d].unsqueeze(-1) * self.grad_basis[d, i0:i1]
+            lapl, kin = vlapl[i0:i1], vkin[i0:i1]
+            vb += 2 * lapl.unsqueeze(-1) * self.lapl_basis[i0:i1]
+            mat += torch.matmul(self.basis_dvolume[i0:i1].T, vb)
+            lapl_kin_dvol = (2 * lapl + 0.5 * kin) * self.dvolume[i0:i1]
+            for d in range(3):
+                gb = self.grad_basis[d, i0:i1]
+                mat += torch.einsum("r,rb,rc->bc", lapl_kin_dvol, gb, gb)
+        mat = self.conv2(mat)
+        return (mat + mat.T) * 0.5
+
     def vxc_from_potinfo(self, vrho, vgrad):
         ng, nb = self.basis.shape
         mat = torch.zeros(nb, nb, dtype=torch.float64)
@@ -170,6 +211,13 @@ class RefHamilton:
 
     def get_vxc(self, dm):
         """dm: tensor (unpolarised) or (dm_u, dm_d) tuple."""
+        if self.xcfamily == 4:
+            if isinstance(dm, tuple):
+                du, dd = self.dm2densinfo_mgga(dm[0]), self.dm2densinfo_mgga(dm[1])
+                _, vu, vd = xc_ref.eval_pol_mgga(self.xcstr, du[0], dd[0], du[1], dd[1], du[2], dd[2], du[3], dd[3])
+                return self.vxc_from_potinfo_mgga(*vu), self.vxc_from_potinfo_mgga(*vd)
+            out = xc_ref.eval_unpol_mgga(self.xcstr, *self.dm2densinfo_mgga(dm))
+            return self.vxc_from_potinfo_mgga(*out[1:])
         if isinstance(dm, tuple):
             (ru, gu), (rd, gd) = self.dm2densinfo(dm[0]), self.dm2densinfo(dm[1])
             _, (vu, vd), vg = xc_ref.eval_pol(self.xcstr, ru, rd, gu, gd)
@@ -180,6 +228,13 @@ class RefHamilton:
         return self.vxc_from_potinfo(vrho, vgrad)
 
     def get_e_xc(self, dm):
+        if self.xcfamily == 4:
+            if isinstance(dm, tuple):
+                du, dd = self.dm2densinfo_mgga(dm[0]), self.dm2densinfo_mgga(dm[1])
+                e = xc_ref.eval_pol_mgga(self.xcstr, du[0], dd[0], du[1], dd[1], du[2], dd[2], du[3], dd[3])[0]
+            else:
+                e = xc_ref.eval_unpol_mgga(self.xcstr, *self.dm2densinfo_mgga(dm))[0]
+            return torch.sum(self.dvolume * e)
         if isinstance(dm, tuple):
             (ru, gu), (rd, gd) = self.dm2densinfo(dm[0]), self.dm2densinfo(dm[1])
             e = xc_ref.eval_pol(self.xcstr, ru, rd, gu, gd)[0]

@@ -6,6 +6,8 @@ here) is restated from the published functional forms:
   lda_c_pw    Perdew-Wang 92 (original parameters) -- pinned (rtol 1e-5) by test_xc.py:393-414
   gga_x_pbe   PBE exchange                         -- pinned (rtol 1e-5) by test_xc.py:419-425
   gga_c_pbe   PBE correlation on PW92-modified     -- PARITY UNPINNED in-tree (libxc formula restated)
+  mgga_x_scan SCAN exchange (Sun et al., PRL 115, 036402) -- pinned by the closed form the reference checks libxc
+              against (test_xc.py:427-455, unpolarised and by spin scaling polarised: :268-273)
 Conventions follow dqc/xc/libxc.py:124-242 and libxc_wrapper.py:380-413: the energy returned is
 per unit VOLUME (zk * rho); the potential bundle is value = de/drho, grad = 2 (de/dsigma) grad rho
 (unpolarised) -- which is exactly d e / d(grad rho), what autograd gives.
@@ -27,7 +29,7 @@ PBE_BETA = 0.06672455060314922
 PBE_MU = PBE_BETA * PI * PI / 3.0
 PBE_GAMMA = (1.0 - math.log(2.0)) / (PI * PI)
 FAMILY = {"lda_x": 1, "lda_c_pw": 1, "lda_c_pw_mod": 1, "gga_x_pbe": 2, "gga_c_pbe": 2,
-          "lda_c_vwn": 1, "lda_c_vwn_rpa": 1, "gga_x_b88": 2, "gga_c_lyp": 2}
+          "lda_c_vwn": 1, "lda_c_vwn_rpa": 1, "gga_x_b88": 2, "gga_c_lyp": 2, "mgga_x_scan": 4}
 # B88 / LYP / VWN: PARITY UNPINNED in-tree (the reference reaches them only through libxc, absent here, and its
 # tests hold no numbers for them).  Restated from the original papers; cross-checked against literature atomic
 # energies in tests/test_oracle_golden.py (flagged there as external, not from the reference).
@@ -128,6 +130,43 @@ def edens_pol(name, ru, rd, gu=None, gd=None):
     raise KeyError(name)
 
 
+def scan_x_unpol(rho, grad, tau):
+    """SCAN exchange energy per volume of an unpolarised density (Sun, Ruzsinszky, Perdew 2015, eqs. 5-9 and the
+    supplementary parameters): e = e_x^LDA(rho) F_x(s, alpha), s = |grad rho| / (2 rho kF),
+    alpha = (tau - |grad rho|^2 / (8 rho)) / (0.3 kF^2 rho).  lapl rho does not enter."""
+    a1, c1x, c2x, dx, k1, h0, b3 = 4.9479, 0.667, 0.8, 1.24, 0.065, 1.174, 0.5
+    mu_ak = 10.0 / 81.0
+    b2 = math.sqrt(5913.0 / 405000.0)
+    b1 = 511.0 / 13500.0 / (2.0 * b2)
+    b4 = mu_ak ** 2 / k1 - 1606.0 / 18225.0 - b1 ** 2
+    # densities at or below 1e-15 contribute exactly zero (libxc's dens_threshold; the CUDA kernel's XC_RHO_CUT): on a
+    # molecular grid rho underflows far from the nuclei and alpha would be 0 / 0
+    live = rho > 1e-15
+    rho_in = rho
+    rho = torch.where(live, rho, torch.ones_like(rho))
+    grad = torch.where(live, grad, torch.zeros_like(grad))
+    tau = torch.where(live, tau, torch.ones_like(tau))
+    sigma = (grad * grad).sum(0)
+    kf = (3.0 * PI * PI * rho) ** (1.0 / 3.0)
+    s2 = sigma / (4.0 * rho * rho * kf * kf)
+    alpha = (tau - sigma / (8.0 * rho)) / (0.3 * kf * kf * rho)
+    oma = 1.0 - alpha
+    x = mu_ak * s2 * (1.0 + b4 * s2 / mu_ak * torch.exp(-abs(b4) * s2 / mu_ak)) \
+        + (b1 * s2 + b2 * oma * torch.exp(-b3 * oma * oma)) ** 2
+    h1 = 1.0 + k1 - k1 / (1.0 + x / k1)
+    s2c = s2.clamp_min(1e-40)                                  # s -> 0: g -> 1 with vanishing derivatives
+    gs = 1.0 - torch.exp(-a1 / s2c ** 0.25)
+    pos, neg = oma > 1e-12, oma < -1e-12
+    # (each branch sees harmless arguments where it is masked out: an inf there would turn into NaN gradients)
+    op = torch.where(pos, oma, torch.ones_like(oma))
+    on = torch.where(neg, oma, -torch.ones_like(oma))
+    fa = torch.where(pos, torch.exp(-c1x * (1.0 - op) / op), torch.zeros_like(oma)) \
+        - torch.where(neg, dx * torch.exp(c2x / on), torch.zeros_like(oma))
+    fx = (h1 + fa * (h0 - h1)) * gs
+    e = -0.75 * (3.0 / PI) ** (1.0 / 3.0) * rho ** (4.0 / 3.0) * fx
+    return torch.where(live, e, 0.0 * rho_in)
+
+
 def edens_unpol(name, rho, grad=None):
     half_g = None if grad is None else 0.5 * grad
     return edens_pol(name, 0.5 * rho, 0.5 * rho, half_g, half_g)
@@ -186,3 +225,32 @@ def eval_pol(xcstr, ru, rd, gu=None, gd=None):
     if fam == 1:
         return e.detach(), (grads[0], grads[1]), None
     return e.detach(), (grads[0], grads[1]), (grads[2], grads[3])
+
+
+def eval_unpol_mgga(xcstr, rho, grad, lapl, kin):
+    """Family 4, unpolarised: (edens, vrho, vgrad (3, n), vlapl, vkin) -- potentials by autograd with respect to
+    (rho, grad rho, lapl rho, tau) like the reference's default route."""
+    rho = rho.detach().clone().requires_grad_(True)
+    g = grad.detach().clone().requires_grad_(True)
+    lp = lapl.detach().clone().requires_grad_(True)
+    k = kin.detach().clone().requires_grad_(True)
+    e = 0.0
+    for c, n in parse(xcstr):
+        if FAMILY[n] == 4:
+            assert n == "mgga_x_scan"
+            e = e + c * scan_x_unpol(rho, g, k)
+        else:
+            e = e + c * edens_unpol(n, rho, g if FAMILY[n] == 2 else None)
+    grads = torch.autograd.grad(e.sum(), (rho, g, lp, k), allow_unused=True)
+    grads = [x if x is not None else torch.zeros_like(i) for x, i in zip(grads, (rho, g, lp, k))]
+    return (e.detach(),) + tuple(x.detach() for x in grads)
+
+
+def eval_pol_mgga(xcstr, ru, rd, gu, gd, lu, ld, ku, kd):
+    """Family 4, polarised exchange by spin scaling e[ru, rd] = (e[2 ru] + e[2 rd]) / 2 (test_xc.py:272-273):
+    returns (edens, (v_u bundle), (v_d bundle)), each bundle = (vrho, vgrad, vlapl, vkin)."""
+    for _, n in parse(xcstr):
+        assert FAMILY[n] == 4 and "_x_" in n, "spin scaling holds for exchange functionals only"
+    eu = eval_unpol_mgga(xcstr, 2 * ru, 2 * gu, 2 * lu, 2 * ku)
+    ed = eval_unpol_mgga(xcstr, 2 * rd, 2 * gd, 2 * ld, 2 * kd)
+    return 0.5 * (eu[0] + ed[0]), eu[1:], ed[1:]

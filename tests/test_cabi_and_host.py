@@ -201,8 +201,9 @@ def test_get_xc_algebra_without_gpu():
     assert get_xc("2*lda_x").terms == [(2.0, "lda_x")] and get_xc("lda_x*2").terms == [(2.0, "lda_x")]
     with pytest.raises(NotImplementedError):
         get_xc("hyb_gga_xc_b3lyp")
+    assert get_xc("mgga_x_scan").family == 4 and get_xc("mgga_x_scan + gga_c_pbe").family == 4
     with pytest.raises(NotImplementedError):
-        get_xc("mgga_x_scan")
+        get_xc("mgga_c_scan")
 
     class MyLDA(BaseXC):          # user functional: default get_vxc goes through autograd (base_xc.py:39-125)
         @property

@@ -28,7 +28,7 @@ def test_ao_eval_matches_oracle(cuda, which, ngrid):
     atm, bas, env = w.atm_bas_env
     pts = util.random_points(ngrid, seed=ngrid)
     db = w.device_basis(cuda)
-    for deriv in (0, 1):
+    for deriv in (0, 1, 2):
         ao = _lib.eval_gto(db, 0, len(w), torch.tensor(pts, device=cuda), deriv)
         torch.cuda.synchronize()
         nao = w.nao()
@@ -37,7 +37,10 @@ def test_ao_eval_matches_oracle(cuda, which, ngrid):
         assert np.abs(got[0] - ref0).max() < 1e-12
         if deriv:
             ref1 = cint.eval_gto(atm, bas, env, pts, 1)
-            assert np.abs(got[1:] - ref1).max() < 1e-11
+            assert np.abs(got[1:4] - ref1).max() < 1e-11
+        if deriv == 2:          # Laplacian of the AOs (eval_laplgto, the meta-GGA storage)
+            ref2 = cint.eval_gto(atm, bas, env, pts, 2)
+            assert np.abs(got[4] - ref2).max() < 1e-10 * max(1.0, np.abs(ref2).max())
         # padding stays zero
         assert float(ao[:, ngrid:, :].abs().max()) == 0.0 if ao.shape[1] > ngrid else True
         assert float(ao[:, :, nao:].abs().max()) == 0.0 if ao.shape[2] > nao else True
@@ -337,3 +340,93 @@ def test_rho_tcgen05_int8_matches_fp64_path(cuda, nslice, tol, gga, mode):
     if gga:
         assert float((g - g_ref).abs().max()) < tol * float(g_ref.abs().max())
         assert torch.equal(g, g2)
+
+
+# ---- meta-GGA (reference: hcgto.py:183-186,420-438,473-489, libxc mgga_x_scan) ----
+def _mgga_inputs(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    rho = 10 ** (torch.rand(n, dtype=torch.float64, generator=g) * 7 - 5)
+    grad = torch.randn(3, n, dtype=torch.float64, generator=g) * rho ** (4.0 / 3) * 1.5
+    tau_w = (grad * grad).sum(0) / (8 * rho)
+    tau_unif = 0.3 * (3 * np.pi ** 2 * rho) ** (2.0 / 3) * rho
+    alpha = 10 ** (torch.rand(n, dtype=torch.float64, generator=g) * 3 - 2)          # 0.01 .. 10, both branches of f(alpha)
+    alpha = torch.where((alpha - 1).abs() < 0.02, alpha + 0.05, alpha)
+    return rho, grad, torch.randn(n, dtype=torch.float64, generator=g), tau_w + alpha * tau_unif
+
+
+@pytest.mark.parametrize("xcstr", ["mgga_x_scan", "mgga_x_scan + gga_c_pbe", "0.5*mgga_x_scan + 0.5*lda_x"])
+def test_xc_mgga_unpol_matches_autograd_oracle(cuda, xcstr):
+    from dqc_b200 import _lib
+    from oracle import xc_ref
+    rho, grad, lapl, tau = _mgga_inputs(4097, 7)
+    e_ref, vr_ref, vg_ref, vl_ref, vk_ref = xc_ref.eval_unpol_mgga(xcstr, rho, grad, lapl, tau)
+    e, vr, vg, vl, vk = _lib.xc_mgga_unpol(xc_ref.parse(xcstr), rho.to(cuda), grad.to(cuda).contiguous(), lapl.to(cuda),
+                                           tau.to(cuda))
+    rel = lambda a, b: float(((a.cpu() - b).abs() / (b.abs() + 1e-10 * b.abs().max())).max())
+    assert rel(e, e_ref) < 1e-10
+    assert rel(vr, vr_ref) < 1e-8
+    assert rel(vk, vk_ref) < 1e-8
+    assert float((vg.cpu() - vg_ref).abs().max() / vg_ref.abs().max()) < 1e-10
+    assert float(vl.abs().max()) == 0.0 and float(vl_ref.abs().max()) == 0.0
+
+
+def test_xc_mgga_pol_by_spin_scaling_matches_oracle(cuda):
+    from dqc_b200 import get_xc, ValGrad, SpinParam
+    from oracle import xc_ref
+    ru, gu, lu, ku = _mgga_inputs(2001, 8)
+    rd, gd, ld_, kd = _mgga_inputs(2001, 9)
+    e_ref, vu_ref, vd_ref = xc_ref.eval_pol_mgga("mgga_x_scan", ru, rd, gu, gd, lu, ld_, ku, kd)
+    xc = get_xc("mgga_x_scan")
+    mk = lambda r, g, l, k: ValGrad(value=r.to(cuda), grad=g.to(cuda), lapl=l.to(cuda), kin=k.to(cuda))
+    dens = SpinParam(u=mk(ru, gu, lu, ku), d=mk(rd, gd, ld_, kd))
+    e = xc.get_edensityxc(dens)
+    v = xc.get_vxc(dens)
+    rel = lambda a, b: float(((a.cpu() - b).abs() / (b.abs() + 1e-10 * b.abs().max())).max())
+    assert rel(e, e_ref) < 1e-10
+    for got, ref in ((v.u, vu_ref), (v.d, vd_ref)):
+        assert rel(got.value, ref[0]) < 1e-8 and rel(got.kin, ref[3]) < 1e-8
+        assert float((got.grad.cpu() - ref[1]).abs().max() / ref[1].abs().max()) < 1e-10
+    # unpolarised limit: both spins = rho / 2
+    half = lambda t: 0.5 * t
+    du = mk(half(ru), half(gu), half(lu), half(ku))
+    e_u = xc.get_edensityxc(mk(ru, gu, lu, ku))
+    e_p = xc.get_edensityxc(SpinParam(u=du, d=du))
+    assert torch.allclose(e_u, e_p, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("which", ["h2o-def2svp", "highl"])
+def test_mgga_densities_and_vxc_match_oracle(cuda, which):
+    """Meta-GGA K2 (rho, grad rho, lapl rho, tau) and K4 (with the lapl and tau terms) on the superblock storage with five
+    AO components, against oracle/fock_ref.py (hcgto.py:420-438, 473-489 restated) on a few thousand points."""
+    from dqc_b200 import _lib
+    from oracle import fock_ref, xc_ref
+    xcstr = "mgga_x_scan"
+    w, _ = util.make_wrapper(*util.H2O, "def2-svp") if which == "h2o-def2svp" else util.highl_wrapper()
+    ngrid = 2500
+    pts = util.random_points(ngrid, seed=13, span=2.5)
+    wts = np.random.RandomState(6).uniform(0.0, 0.3, ngrid)
+    h = fock_ref.RefHamilton(w, orthozer=False)
+    h.setup_grid(pts, wts, xcstr)
+    nao = w.nao()
+    dm = util.seeded_dm(nao, max(1, nao // 4), seed=4)
+    rho_ref, grad_ref, lapl_ref, kin_ref = h.dm2densinfo_mgga(dm)
+    db = w.device_basis(cuda)
+    gb = _lib.GridBlocks(db, 0, len(w), torch.tensor(pts, device=cuda), torch.tensor(wts, device=cuda), 2, sbp=512, eps=0.0)
+    rho, grad, lapl, kin = gb.rho_mgga(dm.to(cuda))
+    chk = lambda a, b, tol: float((a[..., :ngrid].cpu() - b).abs().max()) < tol * max(1.0, float(b.abs().max()))
+    assert chk(rho, rho_ref, 1e-11) and chk(grad, grad_ref, 1e-10) and chk(lapl, lapl_ref, 1e-10) and chk(kin, kin_ref, 1e-10)
+    # K4 from the oracle's potentials, then the whole chain on the device
+    _, vr_ref, vg_ref, vl_ref, vk_ref = xc_ref.eval_unpol_mgga(xcstr, rho_ref, grad_ref, lapl_ref, kin_ref)
+    # (a lapl-dependent potential too, so that the 2 vlapl lapl phi and 2 vlapl dphi dphi terms are exercised)
+    vl_test = 0.05 * torch.sin(torch.arange(ngrid, dtype=torch.float64))
+    mat_ref = h.vxc_from_potinfo_mgga(vr_ref, vg_ref, vl_test, vk_ref)
+    pad = lambda t: torch.nn.functional.pad(t.to(cuda), (0, gb.ngl - ngrid)).contiguous()
+    mat = gb.vxc_mat_mgga(pad(vr_ref), pad(vg_ref), pad(vl_test), pad(vk_ref))
+    mat = 0.5 * (mat + mat.T)
+    assert float((mat.cpu() - mat_ref).abs().max()) < 1e-10
+    e, vr, vg, vl, vk = _lib.xc_mgga_unpol(xc_ref.parse(xcstr), rho, grad, lapl, kin)
+    mat2 = gb.vxc_mat_mgga(vr, vg, vl, vk)
+    mat2 = 0.5 * (mat2 + mat2.T)
+    assert float((mat2.cpu() - h.vxc_from_potinfo_mgga(vr_ref, vg_ref, vl_ref, vk_ref)).abs().max()) < 1e-9
+    exc_ref = float((xc_ref.eval_unpol_mgga(xcstr, rho_ref, grad_ref, lapl_ref, kin_ref)[0] * torch.tensor(wts)).sum())
+    assert abs(float((e * gb.w).sum()) - exc_ref) < 1e-10

@@ -263,3 +263,71 @@ def test_pbe_c_formula_independent_restatement():
     A = beta / gamma / (torch.exp(-ec / gamma) - 1)
     H = gamma * torch.log(1 + beta / gamma * t ** 2 * (1 + A * t ** 2) / (1 + A * t ** 2 + A ** 2 * t ** 4))
     assert torch.allclose(xc_ref.edens_unpol("gga_c_pbe", rho, g), rho * (ec + H), rtol=1e-9)
+
+
+# ---- meta-GGA: SCAN exchange pinned by the closed form the reference checks libxc against
+def _scan_e_true(rho, gradn, lapl, tau):
+    # dqc/test/test_xc.py:427-455 (scan_e_true), restated here independently of oracle/xc_ref.py
+    kf = (3 * np.pi * np.pi * rho) ** (1. / 3)
+    norm_gradn = torch.sqrt((gradn * gradn).sum(0))
+    s = norm_gradn / (2 * rho * kf)
+    tau_w = norm_gradn ** 2 / (8 * rho)
+    tau_unif = 0.3 * kf ** 2 * rho
+    alpha = (tau - tau_w) / tau_unif
+    s2 = s * s
+    a1, c1x, c2x, dx = 4.9479, 0.667, 0.8, 1.24
+    mu_ak = 10. / 81
+    b2 = (5913 / 405000.) ** 0.5
+    b1 = 511 / 13500 / (2 * b2)
+    b3, k1 = 0.5, 0.065
+    b4 = mu_ak ** 2 / k1 - 1606 / 18225 - b1 ** 2
+    x = mu_ak * s2 * (1 + (b4 * s2 / mu_ak) * torch.exp(-abs(b4) * s2 / mu_ak)) + \
+        (b1 * s2 + b2 * (1 - alpha) * torch.exp(-b3 * (1 - alpha) ** 2)) ** 2
+    h1 = 1 + k1 * (1 - k1 / (k1 + x))
+    h0 = 1.174
+    gs = 1 - torch.exp(-a1 / torch.sqrt(s))
+    theta_1ma = ((1 - alpha) > 0) * 1.0
+    theta_am1 = ((alpha - 1) > 0) * 1.0
+    fa = torch.exp(-c1x * alpha / (1 - alpha)) * theta_1ma - dx * torch.exp(c2x / (1 - alpha)) * theta_am1
+    return -0.75 * (3 / np.pi) ** (1. / 3) * rho ** (4. / 3) * (h1 + fa * (h0 - h1)) * gs
+
+
+def _mgga_points(n=60, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    rho = 10 ** (torch.rand(n, dtype=dtype, generator=g) * 4 - 3)
+    grad = torch.randn(3, n, dtype=dtype, generator=g) * rho ** (4. / 3) * 1.5
+    tau_w = (grad * grad).sum(0) / (8 * rho)
+    tau_unif = 0.3 * (3 * np.pi ** 2 * rho) ** (2. / 3) * rho
+    alpha = torch.cat([torch.rand(n // 2, dtype=dtype, generator=g) * 0.95,          # both branches of f(alpha)
+                       1.05 + torch.rand(n - n // 2, dtype=dtype, generator=g) * 3])
+    tau = tau_w + alpha * tau_unif
+    lapl = torch.randn(n, dtype=dtype, generator=g)
+    return rho, grad, lapl, tau
+
+
+def test_scan_x_formula():
+    # unpolarised and, by spin scaling, polarised (test_xc.py:268-273)
+    rho, grad, lapl, tau = _mgga_points()
+    e = xc_ref.eval_unpol_mgga("mgga_x_scan", rho, grad, lapl, tau)[0]
+    assert torch.allclose(e, _scan_e_true(rho, grad, lapl, tau), rtol=1e-12)
+    ru, rd, gu, gd = 0.7 * rho, 0.3 * rho, 0.6 * grad, 0.4 * grad
+    ku, kd = 0.65 * tau, 0.35 * tau
+    ep = xc_ref.eval_pol_mgga("mgga_x_scan", ru, rd, gu, gd, 0.5 * lapl, 0.5 * lapl, ku, kd)[0]
+    etrue = 0.5 * (_scan_e_true(2 * ru, 2 * gu, lapl, 2 * ku) + _scan_e_true(2 * rd, 2 * gd, lapl, 2 * kd))
+    ok = torch.isfinite(etrue)       # (the reference's expression is inf * 0 where alpha is within ~1e-3 above 1)
+    assert int(ok.sum()) >= ok.numel() - 2 and torch.allclose(ep[ok], etrue[ok], rtol=1e-9)
+
+
+def test_scan_potentials_are_derivatives_of_the_energy():
+    rho, grad, lapl, tau = _mgga_points(40, seed=5)
+    e, vr, vg, vl, vk = xc_ref.eval_unpol_mgga("mgga_x_scan", rho, grad, lapl, tau)
+    f = lambda r, g, k: xc_ref.scan_x_unpol(r, g, k)
+    h = 1e-6
+    assert torch.allclose(vr, (f(rho * (1 + h), grad, tau) - f(rho * (1 - h), grad, tau)) / (2 * h * rho), rtol=2e-6, atol=1e-9)
+    assert torch.allclose(vk, (f(rho, grad, tau * (1 + h)) - f(rho, grad, tau * (1 - h))) / (2 * h * tau), rtol=2e-6, atol=1e-9)
+    for d in range(3):
+        dg = torch.zeros_like(grad)
+        dg[d] = h * grad[d].abs().clamp_min(1e-3)
+        fd = (f(rho, grad + dg, tau) - f(rho, grad - dg, tau)) / (2 * dg[d])
+        assert torch.allclose(vg[d], fd, rtol=5e-6, atol=1e-7)       # (atol: round-off of the difference quotient)
+    assert float(vl.abs().max()) == 0.0              # SCAN does not depend on lapl rho

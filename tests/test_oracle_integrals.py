@@ -112,3 +112,20 @@ def test_ao_gradient_is_the_derivative_of_the_value():
         e[d] = h
         fd = (cint.eval_gto(atm, bas, env, pts + e, 0) - cint.eval_gto(atm, bas, env, pts - e, 0)) / (2 * h)
         assert np.abs(fd - g[d]).max() < 1e-8
+
+
+def test_ao_laplacian_is_the_divergence_of_the_gradient():
+    """eval_gto(deriv=2) (the oracle of eval_laplgto) against central differences of the analytic gradient, l = 0..4."""
+    w, _ = util.highl_wrapper()
+    atm, bas, env = w.atm_bas_env
+    rng = np.random.RandomState(11)
+    pts = rng.uniform(-1.5, 1.5, size=(40, 3))
+    lap = cint.eval_gto(atm, bas, env, pts, 2)
+    h = 1e-4
+    fd = np.zeros_like(lap)
+    for d in range(3):
+        e = np.zeros(3)
+        e[d] = h
+        fd += (cint.eval_gto(atm, bas, env, pts + e, 1)[d] - cint.eval_gto(atm, bas, env, pts - e, 1)[d]) / (2 * h)
+    scale = np.abs(lap).max()
+    assert np.abs(lap - fd).max() < 1e-6 * scale
