@@ -19,6 +19,7 @@ _rys_loaded = set()      # CUDA device indices that hold the Rys table (constant
 GRID_ALIGN = 128  # leading dimension of the grid axis (K2/K4 CTA tile)
 AO_ALIGN = 64     # leading dimension of the AO axis
 
+LMAX = 4     # highest angular momentum of the kernels (B200QC_LMAX)
 FUNC_IDS = {"lda_x": 1, "lda_c_pw": 2, "lda_c_pw_mod": 3, "lda_c_vwn": 4, "lda_c_vwn_rpa": 5,
             "gga_x_pbe": 101, "gga_c_pbe": 102, "gga_x_b88": 103, "gga_c_lyp": 104, "mgga_x_scan": 201}
 FUNC_FAMILY = {name: (4 if fid >= 200 else 2 if fid >= 100 else 1) for name, fid in FUNC_IDS.items()}
@@ -37,6 +38,8 @@ _SIGS = {
     "b200qc_basis_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "b200qc_basis_set_cartesian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "b200qc_c2s_matrix": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "b200qc_rys_upload": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double,
                                          ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_eval_gto": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
@@ -256,8 +259,8 @@ class DeviceBasis(object):
     """Handle of a basis uploaded to the GPU (b200qc_basis_upload)."""
 
     def __init__(self, atm, bas, env, ao_loc, spherical=True, device=None):
-        if not spherical:
-            raise NotImplementedError("only spherical AOs (the reference's default everywhere) are built")
+        """spherical=False: raw cartesian output x^a y^b z^c sum_p c_p exp(-a_p r^2) of the integral kernels (ao_loc
+        counting (l + 1)(l + 2) / 2 per shell) -- the building block of the derivative integrals, not an AO basis."""
         lib = load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.atm = np.ascontiguousarray(atm, dtype=np.int32)
@@ -270,6 +273,8 @@ class DeviceBasis(object):
                                            _np(self.env), len(self.env), _np(self.ao_loc), ctypes.byref(h)),
                    "basis_upload")
         self.handle = h
+        if not spherical:
+            _check(lib.b200qc_basis_set_cartesian(self.handle, 1), "basis_set_cartesian")
 
     def __del__(self):
         try:
@@ -300,6 +305,13 @@ def eval_gto(basis: DeviceBasis, sh0: int, sh1: int, coords: torch.Tensor, deriv
     _check(lib.b200qc_eval_gto(basis.handle, sh0, sh1, deriv, _ptr(coords), ngrid, _ptr(ao), ngrid_ld, ao_ld,
                                _stream()), "eval_gto")
     return ao
+
+
+def c2s_matrix(l: int) -> np.ndarray:
+    """(2l + 1, (l + 1)(l + 2) / 2) cartesian -> real-spherical matrix the kernels apply (angular normalisation included)."""
+    out = np.zeros((2 * l + 1, (l + 1) * (l + 2) // 2), dtype=np.float64)
+    _check(load(require_cuda=False).b200qc_c2s_matrix(int(l), _np(out)), "c2s_matrix")
+    return out
 
 
 def becke_weights(xyz, owner, atompos, aij=None):

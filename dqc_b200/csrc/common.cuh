@@ -63,6 +63,9 @@ struct ShellRec {
 
 struct b200qc_basis {
     int device = -1;   // the CUDA device its arrays (and the constant tables uploaded with it) live on
+    int cart = 0;      // 1: the integral kernels return RAW CARTESIAN blocks x^a y^b z^c sum_p c_p e^(-a_p r^2) for every
+                       // shell of this basis (no real-spherical transform; ao_loc counts (l+1)(l+2)/2 per shell) -- the
+                       // form derivative integrals are assembled from (b200qc_basis_set_cartesian)
     int natm, nbas, nenv;
     std::vector<int> h_atm, h_bas, h_ao_loc;
     std::vector<double> h_env;

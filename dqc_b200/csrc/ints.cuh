@@ -47,6 +47,7 @@ struct IntClass {
     int c2s_off[4];         // offsets of the 4 c2s matrices in the CTA-shared area
     int head;               // doubles of the CTA-shared head (c2s matrices + component offsets)
     int ncharge;
+    int cart;               // raw cartesian output: the "c2s" matrices are identities (ns == nc)
 };
 
 struct IntArgs {
@@ -302,7 +303,8 @@ __device__ __forceinline__ void int_fill_head(const IntClass &K, double *head, i
     for (int s = 0; s < 4; s++) {
         if (!K.present[s]) continue;
         const double *M = c2s_ptr(K.l[s]);
-        for (int e = threadIdx.x; e < K.ns[s] * K.nc[s]; e += blockDim.x) head[K.c2s_off[s] + e] = M[e];
+        for (int e = threadIdx.x; e < K.ns[s] * K.nc[s]; e += blockDim.x)
+            head[K.c2s_off[s] + e] = K.cart ? ((e / K.nc[s] == e % K.nc[s]) ? 1.0 : 0.0) : M[e];
     }
     const int s1 = K.ljt + 1, s2 = K.l[2] + 1, s3 = K.l[3] + 1;
     for (int c = threadIdx.x; c < K.ncomp; c += blockDim.x) {
@@ -419,16 +421,18 @@ int_dense_kernel(const IntClass K, const IntArgs A) {
 // ---------------------------------------------------------------------------------------------
 // host side
 
-static int int_make_class(IntClass &K, int mode, int sink, const int l[4], const int present[4], int ncharge) {
+static int int_make_class(IntClass &K, int mode, int sink, const int l[4], const int present[4], int ncharge,
+                          int cart = 0) {
     K.mode = mode;
     K.sink = sink;
+    K.cart = cart;
     K.ncomp = 1;
     int L = 0;
     for (int s = 0; s < 4; s++) {
         K.l[s] = present[s] ? l[s] : 0;
         K.present[s] = present[s];
         K.nc[s] = NCART(K.l[s]);
-        K.ns[s] = 2 * K.l[s] + 1;
+        K.ns[s] = cart ? K.nc[s] : 2 * K.l[s] + 1;
         K.ncomp *= K.nc[s];
         L += K.l[s];
     }
@@ -553,7 +557,7 @@ static int int_run_eri(const b200qc_basis *B, PairLists &bra, PairLists &ket, bo
             IntClass K;
             const int l[4] = {bra.cls_la[cb], bra.cls_lb[cb], ket.cls_la[ck], ket.cls_lb[ck]};
             const int pr[4] = {1, bra_pair ? 1 : 0, 1, ket_pair ? 1 : 0};
-            if (int_make_class(K, INT_MODE_ERI, sink, l, pr, 0)) {
+            if (int_make_class(K, INT_MODE_ERI, sink, l, pr, 0, B->cart)) {
                 b200qc_set_error("angular-momentum class outside the supported range (<= 1312 cartesian components)");
                 rc = 2;
                 break;
@@ -618,7 +622,7 @@ extern "C" int b200qc_int1e(const b200qc_basis *basis, int kind, const int *sl, 
         IntClass K;
         const int l[4] = {bra.cls_la[cb], bra.cls_lb[cb], 0, 0};
         const int pr[4] = {1, 1, 0, 0};
-        if (int_make_class(K, mode, SINK_DENSE, l, pr, (int)ch.size() / 4)) {
+        if (int_make_class(K, mode, SINK_DENSE, l, pr, (int)ch.size() / 4, basis->cart)) {
             b200qc_set_error("unsupported angular momentum class");
             rc = 2;
             break;
@@ -704,12 +708,37 @@ extern "C" int b200qc_int2e(const b200qc_basis *basis, const int *sl, double *ou
     return rc;
 }
 
+// Raw cartesian output for every integral entry point of this basis handle (flag != 0), or back to real spherical AOs.
+// The caller's ao_loc (b200qc_basis_upload) must count (l + 1)(l + 2) / 2 functions per shell while the flag is set.
+// Derivative integrals are linear combinations of such blocks over shells with l + 1 (coefficients c_p 2 a_p) and
+// l - 1: d/dx [x^a y^b z^c e^(-a r^2)] = a x^(a-1) ... - 2 a x^(a+1) ...  (dqc_b200/hamilton/intor/deriv.py; the
+// reference gets them from libcint's int1e_ip* / int2e_ip1, molintor.py:178-578).
+extern "C" int b200qc_basis_set_cartesian(b200qc_basis *basis, int flag) {
+    QC_REQUIRE(basis != nullptr, "null basis");
+    if (flag) {
+        for (int i = 0; i < basis->nbas; i++)
+            QC_REQUIRE(basis->h_ao_loc[i + 1] - basis->h_ao_loc[i] == NCART(basis->h_shells[i].l),
+                       "ao_loc of a cartesian basis must count (l + 1)(l + 2) / 2 functions per shell");
+    }
+    basis->cart = flag ? 1 : 0;
+    return 0;
+}
+
+// Real-spherical transform of the kernels: out[(2 l + 1)][(l + 1)(l + 2) / 2], row m = -l..l (p: x, y, z), column =
+// cartesian component in libcint order, including the angular normalisation.
+extern "C" int b200qc_c2s_matrix(int l, double *h_out) {
+    QC_REQUIRE(l >= 0 && l <= B200QC_LMAX && h_out != nullptr, "bad arguments");
+    h_fill_c2s(l, h_out);
+    return 0;
+}
+
 // Stored-ERI regime (small molecules): both dense layouts of (ij|kl) over shells [sh0, sh1) filled from
 // the quartets with i >= j, k >= l (4-fold symmetry).  eri_j[i][j][k][l] = eri_k[i][k][j][l] = (ij|kl).
 extern "C" int b200qc_eri_store(const b200qc_basis *basis, int sh0, int sh1, double *eri_j, double *eri_k,
                                 void *stream) {
     if (int_require_ready(basis)) return 2;
     QC_REQUIRE(0 <= sh0 && sh0 < sh1 && sh1 <= basis->nbas && eri_j && eri_k, "bad arguments");
+    QC_REQUIRE(!basis->cart, "the stored-ERI regime works on spherical AOs");
     cudaStream_t st = as_stream(stream);
     PairLists bra, ket;
     make_pair_lists(basis, sh0, sh1, sh0, sh1, true, bra);

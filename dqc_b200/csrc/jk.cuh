@@ -230,6 +230,7 @@ extern "C" int b200qc_jkplan_free(b200qc_jkplan *p) {
 extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1, double thresh, b200qc_jkplan **out,
                                     void *stream) {
     if (int_require_ready(basis)) return 2;
+    QC_REQUIRE(!basis->cart, "the direct J/K engine works on spherical AOs");
     QC_REQUIRE(0 <= sh0 && sh0 < sh1 && sh1 <= basis->nbas && out, "bad arguments");
     cudaStream_t st = as_stream(stream);
     const int nb = basis->nbas;

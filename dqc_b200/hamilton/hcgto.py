@@ -48,6 +48,19 @@ def _symm(mat: torch.Tensor) -> torch.Tensor:
     return (mat + mat.transpose(-2, -1)) * 0.5
 
 
+_warned_graph = set()
+
+
+def _warn_if_in_graph(t: torch.Tensor, what: str) -> None:
+    """The contraction kernels (J/K digestion, density on the grid, Vxc integration) have no backward: a density matrix
+    that is part of an autograd graph leaves it here.  Say so once instead of silently returning constants (the
+    integral front-end IS differentiable with respect to the atomic positions: dqc_b200/hamilton/intor/deriv.py)."""
+    if torch.is_grad_enabled() and isinstance(t, torch.Tensor) and t.requires_grad and what not in _warned_graph:
+        _warned_graph.add(what)
+        warnings.warn("%s: the CUDA contraction kernels are forward-only; the result does not carry the autograd "
+                      "graph of the density matrix" % what, RuntimeWarning)
+
+
 class HamiltonCGTO(BaseHamilton):
     def __init__(self, atombases: List[AtomCGTOBasis], spherical: bool = True,
                  df: Optional[DensityFitInfo] = None,
@@ -359,6 +372,7 @@ class HamiltonCGTO(BaseHamilton):
         polarized = isinstance(dm, SpinParam)
         dmtot = dm.u + dm.d if polarized else dm
         assert dmtot.ndim == 2, "get_fock_2e handles one density at a time"
+        _warn_if_in_graph(dmtot, "get_fock_2e")
         parts: List[torch.Tensor] = []
         side = None
         if self._df is not None:
@@ -468,6 +482,7 @@ class HamiltonCGTO(BaseHamilton):
         # dm: (*BD, nao, nao) -> value (*BD, nr), grad (*BD, 3, nr)   (hcgto.py:371-443)
         if not self.is_ao_set:
             raise RuntimeError("Please call `setup_grid(grid, xc)` to call this function")
+        _warn_if_in_graph(dm, "_dm2densinfo")
         bshape, dm2 = self._flat(dm)
         dmdmt = self._orthozer.unconvert_dm(_symm(dm2))
         ng, gga = self.rgrid.shape[0], self.xcfamily == 2

@@ -19,6 +19,14 @@ def eval_gto_padded(wrapper: LibcintWrapper, rgrid: torch.Tensor, deriv: int) ->
 
 
 def eval_gto(wrapper: LibcintWrapper, rgrid: torch.Tensor, *, to_transpose: bool = False) -> torch.Tensor:
+    """AO values; differentiable (first order) with respect to the grid points and the atomic positions when either is
+    part of an autograd graph (the reference's _EvalGTO.backward, gtoeval.py:124-193)."""
+    pos = wrapper.parent.params[2]
+    if torch.is_grad_enabled() and (rgrid.requires_grad or pos.requires_grad):
+        from dqc_b200.hamilton.intor import deriv
+        dev = rgrid.device if rgrid.is_cuda else _device(wrapper)
+        ao = deriv.EvalGTOFunction.apply(rgrid.to(dev).to(torch.float64), pos, wrapper)
+        return ao if to_transpose else ao.transpose(-2, -1)
     ao = eval_gto_padded(wrapper, rgrid, 0)[0, :rgrid.shape[0], :wrapper.nao()]
     return ao.contiguous() if to_transpose else ao.transpose(-2, -1).contiguous()
 

@@ -27,18 +27,48 @@ def _device(wrapper: LibcintWrapper) -> torch.device:
     return dev
 
 
+def _wants_pos_grad(wrapper: LibcintWrapper) -> bool:
+    """True when the atomic positions behind the wrapper are part of an autograd graph; exponents / coefficients in a
+    graph are refused (their backward is not built: the result would silently carry no gradient)."""
+    coeffs, alphas, pos = wrapper.parent.params
+    if torch.is_grad_enabled() and (coeffs.requires_grad or alphas.requires_grad):
+        raise NotImplementedError("gradients with respect to basis exponents / coefficients are not built "
+                                  "(SURVEY 8f rank 1: only the atomic positions so far); detach them")
+    return torch.is_grad_enabled() and pos.requires_grad
+
+
+def _int1e_nograd(shortname: str, wrapper: LibcintWrapper, other: Optional[LibcintWrapper] = None,
+                  rinv_pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    other = wrapper if other is None else other
+    db = wrapper.device_basis(_device(wrapper))
+    orig = None if rinv_pos is None else rinv_pos.detach().cpu().numpy()
+    return _lib.int1e(db, shortname, (*wrapper.shell_idxs, *other.shell_idxs), orig)
+
+
 def int1e(shortname: str, wrapper: LibcintWrapper, other: Optional[LibcintWrapper] = None, *,
           rinv_pos: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """2-centre 1-electron integrals <wrapper| op |other>: shortname in "ovlp", "kin", "nuc", "rinv"."""
+    """2-centre 1-electron integrals <wrapper| op |other>: shortname in "ovlp", "kin", "nuc", "rinv", or their first
+    derivatives with respect to the electron coordinate of the bra, "ipovlp", "ipkin", "ipnuc", "iprinv" -> (3, nao, nao)
+    (libcint's int1e_ip*, molintor.py:178-300).  With atomic positions that require grad the plain integrals are
+    differentiable (first order, positions only)."""
+    same = other is None or other is wrapper
     other = wrapper if other is None else other
     _same_env(wrapper, other)
+    if shortname in ("ipovlp", "ipkin", "ipnuc", "iprinv"):
+        from dqc_b200.hamilton.intor import deriv
+        if not same:
+            raise NotImplementedError("derivative integrals between two different shell ranges are not built")
+        return deriv.ip1e(shortname[2:], wrapper, rinv_pos=rinv_pos)
     if shortname not in ("ovlp", "kin", "nuc", "rinv"):
         raise NotImplementedError("int1e_%s is outside the Fock-build path" % shortname)
     if shortname == "rinv":
         assert rinv_pos is not None and rinv_pos.numel() == 3, "rinv_pos must be given for rinv"
-    db = wrapper.device_basis(_device(wrapper))
-    orig = None if rinv_pos is None else rinv_pos.detach().cpu().numpy()
-    return _lib.int1e(db, shortname, (*wrapper.shell_idxs, *other.shell_idxs), orig)
+    if shortname != "rinv" and _wants_pos_grad(wrapper):
+        from dqc_b200.hamilton.intor import deriv
+        if not same:
+            raise NotImplementedError("position gradients of integrals between two different shell ranges are not built")
+        return deriv.Int1eFunction.apply(wrapper.parent.params[2], wrapper, shortname)
+    return _int1e_nograd(shortname, wrapper, other, rinv_pos)
 
 
 def int2c2e(shortname: str, wrapper: LibcintWrapper, other: Optional[LibcintWrapper] = None) -> torch.Tensor:
@@ -61,15 +91,33 @@ def int3c2e(shortname: str, wrapper: LibcintWrapper, other1: Optional[LibcintWra
     return _lib.int3c2e(db, (*wrapper.shell_idxs, *other1.shell_idxs, *other2.shell_idxs))
 
 
-def int2e(shortname: str, wrapper: LibcintWrapper, other1: Optional[LibcintWrapper] = None,
-          other2: Optional[LibcintWrapper] = None, other3: Optional[LibcintWrapper] = None) -> torch.Tensor:
-    if shortname not in ("ar12b",):
-        raise NotImplementedError("int2e_%s is outside the Fock-build path" % shortname)
-    others = [wrapper if o is None else o for o in (other1, other2, other3)]
-    _same_env(wrapper, *others)
+def _int2e_nograd(wrapper: LibcintWrapper, others=None) -> torch.Tensor:
+    others = [wrapper] * 3 if others is None else others
     db = wrapper.device_basis(_device(wrapper))
     sl = (*wrapper.shell_idxs, *others[0].shell_idxs, *others[1].shell_idxs, *others[2].shell_idxs)
     return _lib.int2e(db, sl)
+
+
+def int2e(shortname: str, wrapper: LibcintWrapper, other1: Optional[LibcintWrapper] = None,
+          other2: Optional[LibcintWrapper] = None, other3: Optional[LibcintWrapper] = None) -> torch.Tensor:
+    """(ij|kl), or with "ipar12b" its derivative with respect to the electron coordinate of i -> (3, nao, nao, nao, nao)
+    (libcint's int2e_ip1).  With atomic positions that require grad (ij|kl) is differentiable (first order)."""
+    same = all(o is None or o is wrapper for o in (other1, other2, other3))
+    others = [wrapper if o is None else o for o in (other1, other2, other3)]
+    _same_env(wrapper, *others)
+    if shortname == "ipar12b":
+        from dqc_b200.hamilton.intor import deriv
+        if not same:
+            raise NotImplementedError("derivative integrals between different shell ranges are not built")
+        return deriv.ip2e(wrapper)
+    if shortname not in ("ar12b",):
+        raise NotImplementedError("int2e_%s is outside the Fock-build path" % shortname)
+    if _wants_pos_grad(wrapper):
+        from dqc_b200.hamilton.intor import deriv
+        if not same:
+            raise NotImplementedError("position gradients of integrals between different shell ranges are not built")
+        return deriv.Int2eFunction.apply(wrapper.parent.params[2], wrapper)
+    return _int2e_nograd(wrapper, others)
 
 
 def overlap(wrapper, other=None):

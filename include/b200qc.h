@@ -49,6 +49,13 @@ int b200qc_peak_i8_mma(int iters, double *h_tops, void *stream);
 int b200qc_basis_upload(const int *h_atm, int natm, const int *h_bas, int nbas, const double *h_env,
                         int nenv, const int *h_ao_loc, b200qc_basis **out);
 int b200qc_basis_free(b200qc_basis *basis);
+/* flag != 0: every integral entry point below returns RAW CARTESIAN blocks x^a y^b z^c sum_p c_p exp(-a_p r^2) for the
+ * shells of this handle (libcint component order; the upload's h_ao_loc must then count (l + 1)(l + 2) / 2 functions
+ * per shell).  Derivative integrals -- libcint's int1e_ip*, int2e_ip1 behind molintor.py:178-578 -- are assembled from
+ * such blocks over shells of l + 1 and l - 1 (dqc_b200/hamilton/intor/deriv.py). */
+int b200qc_basis_set_cartesian(b200qc_basis *basis, int flag);
+/* the kernels' cartesian -> real-spherical matrix of angular momentum l: h_out[(2 l + 1)][(l + 1)(l + 2) / 2] (host) */
+int b200qc_c2s_matrix(int l, double *h_out);
 /* Rys-quadrature interpolation table (dqc_b200/data/rys_table.npz, tools/make_rys_table.py);
  * plays the role of libcint's built-in root tables / the `<intor>_optimizer` pair data
  * (molintor.py:695-708).  h_coef[n-1] points to (nint, 2n, deg+1) doubles, h_herm[n-1] to (2, n). */
