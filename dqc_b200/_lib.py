@@ -37,6 +37,9 @@ _SIGS = {
     "b200qc_peak_i8_mma": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_grid_assemble": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_free": (ctypes.c_int, [ctypes.c_void_p]),
     "b200qc_basis_set_cartesian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "b200qc_c2s_matrix": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
@@ -312,6 +315,24 @@ def c2s_matrix(l: int) -> np.ndarray:
     out = np.zeros((2 * l + 1, (l + 1) * (l + 2) // 2), dtype=np.float64)
     _check(load(require_cuda=False).b200qc_c2s_matrix(int(l), _np(out)), "c2s_matrix")
     return out
+
+
+def grid_assemble(atompos: torch.Tensor, atom_type, atom_npts, type_node_off, node_r, node_dv, node_ang_off, node_pt_off,
+                  ang: np.ndarray):
+    """Molecular grid on the device from per-type radial rules and Lebedev tables (b200qc_grid_assemble):
+    returns xyz (ngrid, 3), dvol (ngrid,) (radial x angular weights), owner (ngrid,) int32."""
+    dev = atompos.device
+    up = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(dev)
+    off = np.concatenate([[0], np.cumsum(np.asarray(atom_npts, dtype=np.int64))])
+    ngrid = int(off[-1])
+    xyz = torch.empty((ngrid, 3), dtype=torch.float64, device=dev)
+    dvol = torch.empty(ngrid, dtype=torch.float64, device=dev)
+    owner = torch.empty(ngrid, dtype=torch.int32, device=dev)
+    bufs = [up(atom_type, torch.int32), up(off, torch.int64), up(type_node_off, torch.int32), up(node_r, torch.float64),
+            up(node_dv, torch.float64), up(node_ang_off, torch.int32), up(node_pt_off, torch.int32), up(ang, torch.float64)]
+    _check(load().b200qc_grid_assemble(int(atompos.shape[0]), _ptr(atompos.contiguous()), *[_ptr(b) for b in bufs], ngrid,
+                                       _ptr(xyz), _ptr(dvol), _ptr(owner), _stream()), "grid_assemble")
+    return xyz, dvol, owner
 
 
 def becke_weights(xyz, owner, atompos, aij=None):

@@ -83,3 +83,58 @@ extern "C" int b200qc_becke_weights(const double *xyz, const int *owner, int64_t
     QC_CHECK(cudaFreeAsync(rinv, st));
     return 0;
 }
+
+// ---- molecular grid assembly: radial x Lebedev products of every atom, pruned, translated to the nuclei ----
+// Replaces the host-side torch construction of dqc/grid/lebedev_grid.py:33-60 (+ the per-slice products of
+// TruncatedLebedevGrid, :63-102) and the per-atom translation / concatenation of multiatoms_grid.py:158-171.
+// Per atom TYPE t the host passes only the 1-D radial rule and, per radial node, which Lebedev table it carries:
+//   node n in [type_node_off[t], type_node_off[t + 1]):  r = node_r[n], radial weight node_dv[n] (4 pi r^2 dr/dx w),
+//   angular rule = rows [node_ang_off[n], + node_nang[n]) of ang (sin theta, cos theta, sin phi, cos phi, w),
+//   node_pt_off[n] = index of its first point inside the atomic grid of the type.
+// One thread per molecular grid point: atom by binary search over atom_pt_off, node by binary search over the type's
+// node_pt_off.  Point = r (sin theta cos phi, sin theta sin phi, cos theta) + R_atom, evaluated with the same
+// operation order as the reference's torch code (no fused multiply-adds), so the grid is bit-identical to the host's.
+__global__ void grid_assemble_kernel(int natom, const double *__restrict__ atompos, const int *__restrict__ atom_type,
+                                     const int64_t *__restrict__ atom_pt_off, const int *__restrict__ type_node_off,
+                                     const double *__restrict__ node_r, const double *__restrict__ node_dv,
+                                     const int *__restrict__ node_ang_off, const int *__restrict__ node_pt_off,
+                                     const double *__restrict__ ang, int64_t ngrid, double *__restrict__ xyz,
+                                     double *__restrict__ dvol, int *__restrict__ owner) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngrid) return;
+    int lo = 0, hi = natom;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    const int a = lo, t = atom_type[a];
+    const int p = (int)(g - atom_pt_off[a]);
+    int n0 = type_node_off[t], n1 = type_node_off[t + 1];
+    while (n1 - n0 > 1) {
+        const int mid = (n0 + n1) >> 1;
+        if (node_pt_off[mid] <= p) n0 = mid; else n1 = mid;
+    }
+    const int k = p - node_pt_off[n0];
+    const double *row = ang + (int64_t)(node_ang_off[n0] + k) * 5;
+    const double r = node_r[n0];
+    const double rs = __dmul_rn(r, row[0]);
+    xyz[3 * g] = __dadd_rn(__dmul_rn(rs, row[3]), atompos[3 * a]);
+    xyz[3 * g + 1] = __dadd_rn(__dmul_rn(rs, row[2]), atompos[3 * a + 1]);
+    xyz[3 * g + 2] = __dadd_rn(__dmul_rn(r, row[1]), atompos[3 * a + 2]);
+    dvol[g] = __dmul_rn(node_dv[n0], row[4]);
+    owner[g] = a;
+}
+
+extern "C" int b200qc_grid_assemble(int natom, const double *atompos, const int *atom_type, const int64_t *atom_pt_off,
+                                    const int *type_node_off, const double *node_r, const double *node_dv,
+                                    const int *node_ang_off, const int *node_pt_off, const double *ang, int64_t ngrid,
+                                    double *xyz, double *dvol, int *owner, void *stream) {
+    QC_REQUIRE(natom >= 1 && xyz && dvol && owner, "bad arguments");
+    if (ngrid == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    grid_assemble_kernel<<<(unsigned)((ngrid + 255) / 256), 256, 0, st>>>(natom, atompos, atom_type, atom_pt_off, type_node_off,
+                                                                         node_r, node_dv, node_ang_off, node_pt_off, ang, ngrid,
+                                                                         xyz, dvol, owner);
+    QC_LAUNCHED(1);
+    return 0;
+}

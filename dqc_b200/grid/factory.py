@@ -83,8 +83,14 @@ def get_grid(atomzs, atompos: torch.Tensor, *, lattice=None,
         "no": lambda: NoTrunc(),
     })()
 
-    # atomic grids are small: built on the host once per distinct Z, then moved to the device
     host = torch.device("cpu")
+    if torch.device(device).type == "cuda":
+        # On a GPU only the 1-D radial rules (tens of numbers per element) are formed on the host; the radial x Lebedev
+        # products with their pruning, the translation to the nuclei and the Becke weights are CUDA kernels
+        # (b200qc_grid_assemble, b200qc_becke_weights) -- bit-identical points to the host construction below.
+        return _device_grid(zs, atompos.to(device), nr, radgrid_generator, tf_of_z, prec, trunc, atomradii, multiatoms_scheme,
+                            dtype)
+    # host path (CPU tensors: the oracle's grids in the tests): atomic grids built once per distinct Z
     per_z: Dict[int, BaseGrid] = {}
     sph: List[BaseGrid] = []
     for z in zs:
@@ -123,3 +129,44 @@ def get_predefined_grid(grid_inp: Union[int, str], atomzs, atompos: torch.Tensor
                         radgrid_generator="chebyshev2", radgrid_transform="treutlerm4", atom_radii="bragg",
                         multiatoms_scheme="treutler", truncate="nwchem", dtype=dtype, device=device)
     raise TypeError("Unknown type of grid_inp: %s" % type(grid_inp))
+
+
+def _device_grid(zs, atompos, nr, radgrid_generator, tf_of_z, prec, trunc, atomradii, multiatoms_scheme, dtype) -> BaseGrid:
+    import numpy as np
+    from dqc_b200 import _lib
+    from dqc_b200.grid.lebedev_grid import load_lebedev
+    if multiatoms_scheme not in ("becke", "treutler"):
+        raise ValueError("Unknown multiatoms scheme: %s" % multiatoms_scheme)
+    host = torch.device("cpu")
+    types = sorted(set(zs))
+    ang_rows, ang_off = [], {}
+    node_r, node_dv, node_ang, node_pt, type_node_off, type_npts = [], [], [], [], [0], {}
+
+    def table(p: int) -> int:
+        if p not in ang_off:
+            t = np.asarray(load_lebedev(p), dtype=np.float64)                 # (phi, theta, w)
+            phi, theta = torch.tensor(t[:, 0]), torch.tensor(t[:, 1])         # same sin / cos as LebedevGrid (torch, host)
+            rows = torch.stack([torch.sin(theta), torch.cos(theta), torch.sin(phi), torch.cos(phi), torch.tensor(t[:, 2])], dim=1)
+            ang_off[p] = (sum(r.shape[0] for r in ang_rows), rows.shape[0])
+            ang_rows.append(rows.numpy())
+        return p
+    for z in types:
+        rad = RadialGrid(_val(nr, z), grid_integrator=radgrid_generator, grid_transform=tf_of_z(z), dtype=dtype, device=host)
+        r_all, dv_all = rad.get_rgrid().reshape(-1).numpy(), rad.get_dvolume().reshape(-1).numpy()
+        if trunc.to_truncate(z):
+            pieces = list(zip(trunc.rad_slices(z, rad), trunc.precs(z, rad)))
+        else:
+            pieces = [(slice(0, len(r_all)), _val(prec, z))]
+        npt = 0
+        for sl, p in pieces:
+            o, n = ang_off[table(int(p))]
+            for i in range(*sl.indices(len(r_all))):
+                node_r.append(r_all[i]); node_dv.append(dv_all[i]); node_ang.append(o); node_pt.append(npt)
+                npt += n
+        type_node_off.append(len(node_r))
+        type_npts[z] = npt
+    tid = {z: i for i, z in enumerate(types)}
+    xyz, dvol_atoms, owner = _lib.grid_assemble(atompos.to(torch.float64), [tid[z] for z in zs], [type_npts[z] for z in zs],
+                                                type_node_off, node_r, node_dv, node_ang, node_pt, np.concatenate(ang_rows))
+    return BeckeGrid(None, atompos, atomradii=atomradii, ratom_adjust="becke" if multiatoms_scheme == "becke" else "treutler",
+                     prebuilt=(xyz, dvol_atoms, owner, [type_npts[z] for z in zs]))

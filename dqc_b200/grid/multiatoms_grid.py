@@ -19,20 +19,26 @@ __all__ = ["BeckeGrid"]
 
 
 class BeckeGrid(BaseGrid):
-    def __init__(self, atomgrid: List[BaseGrid], atompos: torch.Tensor,
-                 atomradii: Optional[torch.Tensor] = None, ratom_adjust: str = "becke") -> None:
-        assert atompos.shape[0] == len(atomgrid), "The lengths of atomgrid and atompos must be the same"
-        assert len(atomgrid) > 0
-        self._dtype = atomgrid[0].dtype
-        self._device = atompos.device
+    def __init__(self, atomgrid: Optional[List[BaseGrid]], atompos: torch.Tensor,
+                 atomradii: Optional[torch.Tensor] = None, ratom_adjust: str = "becke", prebuilt=None) -> None:
+        """prebuilt = (xyz, dvol_atoms, owner, counts): the points already assembled on the device
+        (b200qc_grid_assemble, dqc_b200/grid/factory.py); atomgrid is then not used."""
         if ratom_adjust not in ("becke", "treutler"):
             raise ValueError("Unknown atom adjustment: %s. Available: ['becke', 'treutler']" % ratom_adjust)
-
+        self._device = atompos.device
         dev = self._device
-        pts = [gr.get_rgrid().to(dev) + pos for gr, pos in zip(atomgrid, atompos)]
-        self._rgrid = torch.cat(pts, dim=0).contiguous()
-        dvol_atoms = torch.cat([gr.get_dvolume().to(dev) for gr in atomgrid], dim=0)
-        counts = [p.shape[0] for p in pts]
+        owner_pre = None
+        if prebuilt is not None:
+            self._rgrid, dvol_atoms, owner_pre, counts = prebuilt
+            self._dtype = self._rgrid.dtype
+        else:
+            assert atompos.shape[0] == len(atomgrid), "The lengths of atomgrid and atompos must be the same"
+            assert len(atomgrid) > 0
+            self._dtype = atomgrid[0].dtype
+            pts = [gr.get_rgrid().to(dev) + pos for gr, pos in zip(atomgrid, atompos)]
+            self._rgrid = torch.cat(pts, dim=0).contiguous()
+            dvol_atoms = torch.cat([gr.get_dvolume().to(dev) for gr in atomgrid], dim=0)
+            counts = [p.shape[0] for p in pts]
         self._atom_ngrids = counts
 
         natoms = atompos.shape[0]
@@ -47,8 +53,8 @@ class BeckeGrid(BaseGrid):
                 aij = torch.clamp(uij / (uij * uij - 1), min=-0.45, max=0.45).contiguous()
             else:
                 aij = None
-            owner = torch.repeat_interleave(torch.arange(natoms, device=dev, dtype=torch.int32),
-                                            torch.tensor(counts, device=dev))
+            owner = owner_pre if owner_pre is not None else torch.repeat_interleave(
+                torch.arange(natoms, device=dev, dtype=torch.int32), torch.tensor(counts, device=dev))
             w = _lib.becke_weights(self._rgrid, owner, atompos.contiguous(), aij)
         self._dvolume = dvol_atoms * w
 

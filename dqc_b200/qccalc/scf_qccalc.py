@@ -92,16 +92,47 @@ def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, 
     if method != "diis":
         raise RuntimeError("Unknown equilibrium method: %s (available: diis, broyden1, simple)" % method)
     ys, rs = [], []
+    # Convergence is tested WITHOUT stalling the device queue: the residual norm of iteration k travels to pinned host
+    # memory behind an event and is looked at while iteration k + lag is being enqueued (lag = config.SCF_CHECK_LAG, 0 =
+    # test every iteration synchronously like the reference's solver).  A converged iterate found that way is returned as
+    # it was; the `lag` builds enqueued after it are discarded.  (torch.linalg.eigh inside scp2dm still checks its own
+    # status on the host; the DIIS solve below does not.)
+    lag = int(config.SCF_CHECK_LAG) if y0.is_cuda else 0
+    pending = []            # (iteration, pinned residual, event, iterate)
+
+    def poll(force: bool):
+        nonlocal err
+        while pending and (force or len(pending) > lag or pending[0][2].query()):
+            it_k, host, ev, fy_k = pending.pop(0)
+            ev.synchronize()
+            err = float(host)
+            if verbose:
+                print("diis iter %3d  max|f| = %.3e" % (it_k, err))
+            if err < f_tol:
+                if info is not None:
+                    info.update(converged=True, niter=it_k + 1, residual=err)
+                return fy_k
+        return None
     for it in range(maxiter):
         fy = fcn(y)
         r = (fy - y).reshape(-1)
-        err = float(r.abs().max())
-        if verbose:
-            print("diis iter %3d  max|f| = %.3e" % (it, err))
-        if err < f_tol:
-            if info is not None:
-                info.update(converged=True, niter=it + 1, residual=err)
-            return fy
+        if lag > 0:
+            host = torch.empty((), dtype=r.dtype, pin_memory=True)
+            host.copy_(r.abs().max(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((it, host, ev, fy))
+            done = poll(False)
+            if done is not None:
+                return done
+        else:
+            err = float(r.abs().max())
+            if verbose:
+                print("diis iter %3d  max|f| = %.3e" % (it, err))
+            if err < f_tol:
+                if info is not None:
+                    info.update(converged=True, niter=it + 1, residual=err)
+                return fy
         ys.append(fy.reshape(-1))
         rs.append(r)
         ys, rs = ys[-history:], rs[-history:]
@@ -115,13 +146,15 @@ def equilibrium(fcn, y0: torch.Tensor, method: str = "diis", maxiter: int = 50, 
         B[n, :n] = B[:n, n] = -1.0
         rhs = torch.zeros(n + 1, dtype=R.dtype, device=R.device)
         rhs[n] = -1.0
-        try:
-            c = torch.linalg.solve(B, rhs)[:n]
-        except torch.linalg.LinAlgError:      # singular DIIS matrix (linearly dependent residuals): restart the history
-            ys, rs = ys[-1:], rs[-1:]
-            y = fy
-            continue
-        y = (c.unsqueeze(-1) * torch.stack(ys)).sum(0).reshape(shape)
+        # solve_ex: no status round trip; a singular DIIS matrix (linearly dependent residuals) gives info != 0 and the
+        # plain iterate is used for this step (selected on the device)
+        c, status = torch.linalg.solve_ex(B, rhs)
+        c = torch.nan_to_num(c[:n], nan=0.0, posinf=0.0, neginf=0.0)
+        ymix = (c.unsqueeze(-1) * torch.stack(ys)).sum(0)
+        y = torch.where(status == 0, ymix, fy.reshape(-1)).reshape(shape)
+    done = poll(True)
+    if done is not None:
+        return done
     _not_converged(method, maxiter, err, f_tol, info)
     return y
 

@@ -44,6 +44,9 @@ class _Config:
     # without density fitting, keep both dense layouts of (ij|kl) in HBM when 2 * 8 * nao^4 bytes fit under
     # this (single GPU); beyond it J/K are built directly from Schwarz-screened quartets every iteration
     ERI_STORE_MAX_BYTES: int = int(float(os.environ.get("B200QC_ERI_STORE_MAX_BYTES", str(32 * 1024 ** 3))))
+    # SCF fixed-point iteration: the convergence scalar of iteration k is read on the host while iteration k + lag is
+    # being enqueued (0 = synchronous test every iteration)
+    SCF_CHECK_LAG: int = int(os.environ.get("B200QC_SCF_CHECK_LAG", "1"))
     # sharded builds: run DF-J (whose fitting-coefficient exchange sits in the middle of it) on a second stream beside
     # the XC kernels
     DFJ_SIDE_STREAM: bool = os.environ.get("B200QC_DFJ_SIDE_STREAM", "1") != "0"

@@ -70,6 +70,17 @@ int b200qc_rys_upload(int nmax, double h, int deg, double xmax, const double *co
 int b200qc_eval_gto(const b200qc_basis *basis, int sh0, int sh1, int deriv, const double *coords,
                     int64_t ngrid, double *ao, int64_t ngrid_ld, int64_t ao_ld, void *stream);
 
+/* ---- molecular grid points -- replaces the host construction of lebedev_grid.py:33-102 and the per-atom translation
+ * of multiatoms_grid.py:158-171.  Per atom TYPE: radial nodes [type_node_off[t], type_node_off[t+1]) with radius node_r,
+ * radial weight node_dv, angular rule = rows [node_ang_off[n], ...) of ang (n, 5) = (sin theta, cos theta, sin phi,
+ * cos phi, w) and first point node_pt_off[n] inside the atomic grid; atom a has type atom_type[a] and owns the points
+ * [atom_pt_off[a], atom_pt_off[a+1]).  Outputs xyz (ngrid, 3), dvol (ngrid) = radial x angular weight (no partition
+ * weight yet), owner (ngrid).  All pointers device. */
+int b200qc_grid_assemble(int natom, const double *atompos, const int *atom_type, const int64_t *atom_pt_off,
+                         const int *type_node_off, const double *node_r, const double *node_dv, const int *node_ang_off,
+                         const int *node_pt_off, const double *ang, int64_t ngrid, double *xyz, double *dvol, int *owner,
+                         void *stream);
+
 /* ---- grid weights -- replaces the torch loop of multiatoms_grid.py:173-273 ------------- */
 /* owner[g] = atom the point belongs to; aij = (natom, natom) hetero-nuclear shifts or NULL;
  * w[g] = P_owner / sum_k P_k. */

@@ -267,3 +267,24 @@ def test_dfk_split_k_plan():
         assert pc >= 1 and kc == pc * npad and kc <= lim and kc % 32 == 0
         assert ktot == nl * npad and (nchunk - 1) * kc + k_last == ktot and 0 < k_last <= kc and k_last % 32 == 0
         assert nchunk == -(-nl // pc)
+
+
+def test_equilibrium_solvers_on_a_contraction_map():
+    """The fixed-point solvers of the SCF driver (scf_qccalc.equilibrium: DIIS default, Broyden-1, simple) on
+    y = A y + b with ||A|| < 1, against the linear solve; and the convergence flag when maxiter is too small."""
+    import warnings
+    from dqc_b200.qccalc.scf_qccalc import equilibrium, ConvergenceWarning
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(12, 12, dtype=dtype, generator=g)
+    a = 0.5 * a / torch.linalg.matrix_norm(a, 2)
+    b = torch.randn(12, dtype=dtype, generator=g)
+    exact = torch.linalg.solve(torch.eye(12, dtype=dtype) - a, b)
+    for method in ("diis", "broyden1", "simple"):
+        info = {}
+        y = equilibrium(lambda v: a @ v + b, torch.zeros(12, dtype=dtype), method=method, maxiter=200, f_tol=1e-12, info=info)
+        assert info["converged"] and float((y - exact).abs().max()) < 1e-10, method
+    info = {}
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        equilibrium(lambda v: a @ v + b, torch.zeros(12, dtype=dtype), method="simple", maxiter=2, f_tol=1e-12, info=info)
+    assert not info["converged"] and any(issubclass(r.category, ConvergenceWarning) for r in rec)

@@ -286,3 +286,39 @@ def test_hybrid_composition(cuda):
     e_b = KS(mk(), xc="0.8*lda_x + lda_c_pw", exx_fraction=0.2).run().energy()
     e_l = KS(mk(), xc="lda_x + lda_c_pw").run().energy()
     assert abs(float(e_b - e_l)) < 0.05 and float(e_b) != float(e_l)
+
+
+def test_scf_lagged_convergence_check_gives_the_same_energy(cuda, monkeypatch):
+    """The DIIS loop reads the convergence scalar of iteration k while iteration k + 1 is being enqueued (no stall of the
+    device queue, config.SCF_CHECK_LAG = 1); the converged energy equals the synchronous loop's."""
+    from dqc_b200 import HF
+    from dqc_b200.utils.config import config as cfg
+    es = []
+    for lag in (0, 1, 2):
+        monkeypatch.setattr(cfg, "SCF_CHECK_LAG", lag)
+        qc = HF(_mol(*_diatomic([7, 7], 2.0), "3-21g", cuda), restricted=True).run()
+        assert qc.converged
+        es.append(float(qc.energy()))
+    assert abs(es[0] - es[1]) < 1e-9 and abs(es[0] - es[2]) < 1e-9
+    assert abs(es[0] - (-1.08298897e+02)) < 2e-5        # the reference's golden RHF energy of N2 / 3-21G (test_hf.py:18-51)
+
+
+@pytest.mark.parametrize("gridname", ["sg2", "sg3", 3, 4])
+def test_device_grid_is_bit_identical_to_the_host_construction(cuda, gridname):
+    """Grid construction on the GPU: radial x Lebedev products, pruning and translation in
+    b200qc_grid_assemble against the torch classes on the host (lebedev_grid.py / multiatoms_grid.py restated): the same
+    points and radial x angular weights bit for bit, for both predefined families (Dasgupta and NWChem pruning)."""
+    from dqc_b200.grid.factory import get_predefined_grid
+    from dqc_b200.grid import factory
+    zs, pos = util.H2O
+    p = torch.tensor(pos, dtype=dtype)
+    dev_grid = get_predefined_grid(gridname, zs, p.to(cuda), device=cuda)
+    one = {z: get_predefined_grid(gridname, [z], torch.zeros(1, 3, dtype=dtype), device=torch.device("cpu")) for z in set(zs)}
+    xyz_host = torch.cat([one[z].get_rgrid() + p[i] for i, z in enumerate(zs)])
+    assert torch.equal(dev_grid.get_rgrid().cpu(), xyz_host)
+    # single-atom grids have unit partition weights: their dvolume is the radial x angular weight itself
+    dv_host = torch.cat([one[z].get_dvolume() for z in zs])
+    w = dev_grid.get_dvolume().cpu() / dv_host
+    assert float(w.max()) <= 1.0 + 1e-12 and float(w.min()) >= 0.0
+    f = torch.exp(-0.5 * ((dev_grid.get_rgrid().cpu() - p[0]) ** 2).sum(-1))
+    assert abs(float((f * dev_grid.get_dvolume().cpu()).sum()) - (2 * np.pi) ** 1.5) < 2e-3
