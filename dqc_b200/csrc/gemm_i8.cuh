@@ -87,9 +87,11 @@ i8_slice_rc_kernel(I8SliceArgs a) {
         }
         uint4 q[S];
         i8_quantise16<S>(x, inv, q);
-        signed char *Q = P + (int64_t)(kg >> 1) * S * PL + (kg & 1) * (W * 16);
+        // B role (W = 64): [K chunk][slice][row] so that consecutive slices form one K-major operand (see gemm_i8_kernel)
+        constexpr int KC = (W == I8_BN) ? S * W * 16 : W * 16, SL = (W == I8_BN) ? W * 16 : PL;
+        signed char *Q = P + (int64_t)(kg >> 1) * S * PL + (kg & 1) * KC;
 #pragma unroll
-        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * PL) = q[s];
+        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * SL) = q[s];
     }
 }
 
@@ -123,9 +125,11 @@ i8_slice_kc_kernel(I8SliceArgs a) {
         for (int j = 0; j < 16; j++) x[j] = (rv && k0 + j < Kb) ? X[k0 + j] : 0.0;
         uint4 q[S];
         i8_quantise16<S>(x, inv, q);
-        signed char *Q = P + (int64_t)(kg >> 1) * S * PL + (kg & 1) * (W * 16);
+        // B role (W = 64): [K chunk][slice][row] so that consecutive slices form one K-major operand (see gemm_i8_kernel)
+        constexpr int KC = (W == I8_BN) ? S * W * 16 : W * 16, SL = (W == I8_BN) ? W * 16 : PL;
+        signed char *Q = P + (int64_t)(kg >> 1) * S * PL + (kg & 1) * KC;
 #pragma unroll
-        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * PL) = q[s];
+        for (int s = 0; s < S; s++) *reinterpret_cast<uint4 *>(Q + s * SL) = q[s];
     }
 }
 
@@ -211,7 +215,7 @@ i8_slice_dual_kernel(I8Slice2Args a) {
             for (int s = 0; s < S; s++) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(&sm[wrow][s][wgrp * 16]);
                 if (wa) *reinterpret_cast<uint4 *>(PA + (int64_t)(kg >> 1) * S * 4096 + s * 4096 + (kg & 1) * 2048) = v;
-                if (wb) *reinterpret_cast<uint4 *>(PB + (int64_t)(kg >> 1) * S * 2048 + s * 2048 + (kg & 1) * 1024) = v;
+                if (wb) *reinterpret_cast<uint4 *>(PB + (int64_t)(kg >> 1) * S * 2048 + (kg & 1) * (S * 1024) + s * 1024) = v;
             }
         }
         __syncthreads();
@@ -308,7 +312,9 @@ gemm_i8_kernel(I8GemmArgs g) {
     } else if (warp == 1) {
         // ===== MMA issuer: K-major, no swizzle (LBO = stride between the two 16-byte K chunks, SBO = 128) =====
         if (lane == 0) {
-            const uint64_t da0 = umma_desc(sbase, 2048, 128), db0 = umma_desc(sbase + A_STAGE, 1024, 128);
+            // B stage: [K chunk][slice][64 rows][16 B] -- the slices t0 .. t0 + n - 1 are ONE operand of 64 n rows
+            const uint64_t da0 = umma_desc(sbase, 2048, 128), db0 = umma_desc(sbase + A_STAGE, S * 1024, 128);
+            constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BM >> 4) << 24);
             int it = 0, nt = 0;
             for (int u = blockIdx.x; u < nunits; u += gridDim.x, nt++) {
                 const int b = u / g.units_per_batch;
@@ -320,13 +326,17 @@ gemm_i8_kernel(I8GemmArgs g) {
                     mbar_wait(&full_bar[slot], (it / GI8_STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = da0 + (uint64_t)((slot * STAGE) >> 4), db = db0 + (uint64_t)((slot * STAGE) >> 4);
+                    // A slice s2 against the B slices t0 .. t0 + n - 1 (N = 64 n <= 256) -> the adjacent accumulators
+                    // s2 + t0 ..: 8 MMAs per K step instead of 21 at S = 6, 40 % fewer shared-memory operand bytes
 #pragma unroll
-                    for (int dd = 0; dd < S; dd++)
+                    for (int s2 = 0; s2 < S; s2++)
 #pragma unroll
-                        for (int s2 = 0; s2 <= dd; s2++)
-                            umma_i8(tmem + dd * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
-                                    db + (uint64_t)(((dd - s2) * I8_B_PLANE) >> 4), RI8_IDESC,
+                        for (int t0 = 0; t0 < S - s2; t0 += 4) {
+                            const int n = (S - s2 - t0) < 4 ? (S - s2 - t0) : 4;
+                            umma_i8(tmem + (s2 + t0) * I8_BN, da + (uint64_t)((s2 * I8_A_PLANE) >> 4),
+                                    db + (uint64_t)((t0 * 1024) >> 4), IDESC0 | ((uint32_t)((n * I8_BN) >> 3) << 17),
                                     (kt > 0 || s2 > 0) ? 1u : 0u);
+                        }
                     umma_commit(&empty_bar[slot]);
                 }
                 umma_commit(&accum_full);
