@@ -46,6 +46,13 @@ WORKLOADS = {
     # B3LYP as libxc composes it (0.08 Slater + 0.72 B88 + 0.19 VWN-RPA + 0.81 LYP + 0.20 exact exchange)
     "c60-b3lyp-df": ("c60", "def2-svp", B3LYP_SL, "etb-jfit", 0.20, "sg3"),
     "taxol-like-b3lyp-df": ("taxol_like", "def2-svp", B3LYP_SL, "etb-jfit", 0.20, "sg3"),
+    # nbasis / grid sweep (BASELINE configs[4]): simple-cubic carbon clusters, 14 AOs and ~17.7e3 sg3 points per atom --
+    # nao 504 / 1008 / 2002 with 0.64e6 / 1.27e6 / 2.5e6 points, through the same sharded Fock build (1, 2, 4, 8 GPUs)
+    "cluster36-pbe-df": ("carbon_cluster_36", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
+    "cluster72-pbe-df": ("carbon_cluster_72", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
+    "cluster143-pbe-df": ("carbon_cluster_143", "def2-svp", "gga_x_pbe + gga_c_pbe", "etb-jfit", 0.0, "sg3"),
+    # meta-GGA (SCAN exchange) through the fp64 superblock engine
+    "benzene-scan-4c": ("benzene", "cc-pvdz", "mgga_x_scan", None, 0.0, "sg3"),
     # the same with the direct 4-centre J/K engine (no density fitting): seconds per build -- the weak kernel of
     # DESIGN.md section 7; use --steps 1 --warmup 3
     "taxol-like-b3lyp-4c": ("taxol_like", "def2-svp", B3LYP_SL, None, 0.20, "sg3"),
@@ -55,6 +62,8 @@ METRIC = "fock_build_wall_ms_per_scf_iter"
 
 def geometry(name):
     from dqc_b200.utils import systems
+    if name.startswith("carbon_cluster_"):
+        return systems.carbon_cluster(int(name.rsplit("_", 1)[1]))
     return getattr(systems, name)()
 
 
@@ -466,7 +475,7 @@ def main():
               "K = 32, operands resident in shared memory, best of 3); for comparison 2 x bf16_tflops of "
               "MEASURED_PEAKS.json = %.0f" % (2.0 * peaks.get("bf16_tflops", 1590.0)))
     gb = h._gb if xc is not None else None
-    ncomp = 4 if (xc is not None and h.xcfamily == 2) else 1
+    ncomp = {1: 1, 2: 4, 4: 5}[h.xcfamily] if xc is not None else 1
     xc_flops = gb.flops_per_pass if gb is not None else 0.0      # 2 * sum_sb SBP * nsp^2 (K2 and K4 GEMM each)
     if gb is not None:
         impl_config.update(sb_points=gb.sbp, ao_screen=gb.eps, kept_ao_fraction=round(gb.kept_fraction, 4),
@@ -498,18 +507,30 @@ def main():
             hbm_view = {"algorithmic_bytes_per_launch": hb, "achieved_GBps": hb / t / 1e9, "peak_GBps": hbm_peak,
                         "frac": hb / t / 1e9 / hbm_peak,
                         "measured_traffic_frac_of_peak": (traffic.get(kname) / t / 1e9 / hbm_peak) if traffic.get(kname) else None}
-            return {"kernel": kname, "bound": "tensor", "achieved": ops / t / 1e12, "peak": peak, "unit": "TOP/s (int8)",
-                    "frac": ops / t / 1e12 / peak, "traffic": traffic.get(kname), "hbm_view": hbm_view,
-                    "peak_source": i8_src,
-                    "algorithmic_ops_per_launch": ops, "int8_slice_products": nprod,
-                    "fp64_equivalent_tflops": xc_flops / t / 1e12,
-                    "fp64_equivalent_vs_dmma_peak": xc_flops / t / 1e12 / dmma_peak}
-        ach = xc_flops / t / 1e12
+            tensor_view = {"achieved": ops / t / 1e12, "peak": peak, "unit": "TOP/s (int8)", "frac": ops / t / 1e12 / peak,
+                           "peak_source": i8_src, "algorithmic_ops_per_launch": ops, "int8_slice_products": nprod,
+                           "fp64_equivalent_tflops": xc_flops / t / 1e12,
+                           "fp64_equivalent_vs_dmma_peak": xc_flops / t / 1e12 / dmma_peak}
+            # the binding roofline is the one with the larger lower bound on the launch time: algorithmic bytes at the
+            # measured HBM rate against algorithmic int8 ops at the measured tcgen05 rate
+            if hb / (hbm_peak * 1e9) > ops / (peak * 1e12):
+                return {"kernel": kname, "bound": "hbm", "achieved": hb / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hb / t / 1e9 / hbm_peak, "traffic": traffic.get(kname), "peak_source": hbm_src,
+                        "algorithmic_bytes_per_launch": hb,
+                        "lower_bounds_ms": {"hbm": hb / (hbm_peak * 1e9) * 1e3, "tensor": ops / (peak * 1e12) * 1e3},
+                        "tensor_view": tensor_view}
+            out = {"kernel": kname, "bound": "tensor", "traffic": traffic.get(kname), "hbm_view": hbm_view,
+                   "lower_bounds_ms": {"hbm": hb / (hbm_peak * 1e9) * 1e3, "tensor": ops / (peak * 1e12) * 1e3}}
+            out.update(tensor_view)
+            return out
+        # meta-GGA: four GEMMs per pass (phi and the three gradient components on the left, hcgto.py:427-429, 485-489)
+        ngemm = 4 if (xc is not None and h.xcfamily == 4) else 1
+        ach = ngemm * xc_flops / t / 1e12
         return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
                 "frac": ach / dmma_peak, "traffic": traffic.get(kname),
                 "peak_source": "fp64 DMMA (mma.sync m8n8k4) issue-rate microbenchmark run in this process "
                                "(b200qc_peak_fp64_dmma); MEASURED_PEAKS.json has no fp64 entry",
-                "algorithmic_flops_per_launch": xc_flops}
+                "algorithmic_flops_per_launch": ngemm * xc_flops}
     def dfk_roofline():
         """DF-K: both tcgen05 GEMM launches of a build together.  Algorithmic fp64 flops: stage 1
         2 nao^2 naux nocc, stage 2 (symmetric) nao^2 naux nocc; each is S (S + 1) / 2 int8 products."""
@@ -572,9 +593,12 @@ def main():
     for k in ("rho_kernel", "vxc_gemm_kernel"):
         if k in kern and gb is not None:
             r = gemm_roofline(k)
-            extra[k] = {kk: r[kk] for kk in ("achieved", "peak", "unit", "frac") if kk in r}
-            if "fp64_equivalent_tflops" in r:
-                extra[k]["fp64_equivalent_tflops"] = r["fp64_equivalent_tflops"]
+            extra[k] = {kk: r[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "lower_bounds_ms") if kk in r}
+            tv = r.get("tensor_view", r)
+            if "fp64_equivalent_tflops" in tv:
+                extra[k]["fp64_equivalent_tflops"] = tv["fp64_equivalent_tflops"]
+                extra[k]["int8_tops"] = tv["achieved"]
+                extra[k]["frac_of_int8_peak"] = tv["frac"]
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
