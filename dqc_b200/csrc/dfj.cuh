@@ -59,6 +59,43 @@ dfj_pass1_kernel(const double *__restrict__ B, int64_t npair, int64_t ld, const 
         if (ok[s]) *reinterpret_cast<double2 *>(out + s * 2 * DFJ_TPB) = acc[s];
 }
 
+// Narrow slabs (ld <= 512: the aux slice of one rank in an 8-GPU build is 428 columns): one double2 column slot per
+// thread would leave a single load in flight per thread (0.6 of the HBM rate on the 8-GPU C60 build); here a thread
+// keeps FOUR consecutive rows in flight for its column pair.
+__global__ void __launch_bounds__(DFJ_TPB)
+dfj_pass1_narrow_kernel(const double *__restrict__ B, int64_t npair, int64_t ld, const double *__restrict__ dvec,
+                        int64_t rows_per_cta, double *__restrict__ partial) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(r0 + rows_per_cta, npair);
+    const int64_t c0 = 2 * threadIdx.x;
+    if (c0 >= ld) return;
+    double2 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[u] = make_double2(0.0, 0.0);
+    const double *row = B + r0 * ld + c0;
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4, row += 4 * ld) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldcs(reinterpret_cast<const double2 *>(row + u * ld));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const double d = __ldg(dvec + r + u);
+            acc[u].x += d * v[u].x;
+            acc[u].y += d * v[u].y;
+        }
+    }
+    for (; r < r1; r++, row += ld) {
+        const double d = __ldg(dvec + r);
+        const double2 v = __ldcs(reinterpret_cast<const double2 *>(row));
+        acc[0].x += d * v.x;
+        acc[0].y += d * v.y;
+    }
+    // fixed order: the four row phases, then (dfj_reduce_kernel) the slabs
+    *reinterpret_cast<double2 *>(partial + (int64_t)blockIdx.x * ld + c0) =
+        make_double2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
+}
+
 __global__ void dfj_reduce_kernel(const double *__restrict__ partial, int nslab, int64_t ld, int64_t n, double *__restrict__ t) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -163,7 +200,8 @@ extern "C" int b200qc_dfj_pass1(const double *j3c, int64_t nao, int64_t naux, in
     const int64_t rows = (npair + nslab - 1) / nslab;
     dim3 grid((unsigned)nslab, (unsigned)((ld + DFJ_COLS - 1) / DFJ_COLS));
     prof_begin(PROF_DFJ_PASS1, st);
-    dfj_pass1_kernel<<<grid, DFJ_TPB, 0, st>>>(j3c, npair, ld, dvec, rows, partial);
+    if (ld <= 2 * DFJ_TPB) dfj_pass1_narrow_kernel<<<grid, DFJ_TPB, 0, st>>>(j3c, npair, ld, dvec, rows, partial);
+    else dfj_pass1_kernel<<<grid, DFJ_TPB, 0, st>>>(j3c, npair, ld, dvec, rows, partial);
     prof_end(st);
     QC_LAUNCHED(1);
     prof_begin(PROF_DFJ_SMALL, st);

@@ -73,8 +73,7 @@ class HamiltonCGTO(BaseHamilton):
                  jk_thresh: float = 1e-13,
                  ctx: Optional[ParallelContext] = None) -> None:
         _lib.load()  # raises without the CUDA library or without a device
-        if efield is not None:
-            raise NotImplementedError("electric-field terms (int1e_r*) are outside the Fock-build path")
+        self._efield = efield
         if aoparamzer not in ("qr", "matexp"):
             raise RuntimeError("Unknown ao parameterizer: %s. Available options are: ['qr', 'matexp']" % aoparamzer)
         self.atombases = atombases
@@ -139,6 +138,14 @@ class HamiltonCGTO(BaseHamilton):
             nucl_mat = intor.nuclattr(self.libcint_wrapper)
             self.nucl_mat = nucl_mat
             self.kinnucl_mat = kin_mat + nucl_mat
+            if self._efield is not None:
+                # electric field: + sum_n <r^(n+1)> . E_n / (n+1)!  (hcgto.py:118-127; efield[n] flattened to 3^(n+1))
+                fac = 1.0
+                for n_, ef in enumerate(self._efield):
+                    fac *= n_ + 1
+                    mats = intor.int1e("r0" * (n_ + 1), self.libcint_wrapper)
+                    e = ef.reshape(-1).to(mats.device).to(mats.dtype)
+                    self.kinnucl_mat = self.kinnucl_mat + torch.einsum("dab,d->ab", mats, e) / fac
             if self._df is None:
                 s0, s1 = self.libcint_wrapper.shell_idxs
                 n = self._nao_ao

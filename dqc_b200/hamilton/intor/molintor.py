@@ -59,6 +59,12 @@ def int1e(shortname: str, wrapper: LibcintWrapper, other: Optional[LibcintWrappe
         if not same:
             raise NotImplementedError("derivative integrals between two different shell ranges are not built")
         return deriv.ip1e(shortname[2:], wrapper, rinv_pos=rinv_pos)
+    if shortname in ("r0", "r0r0", "r0r0r0"):
+        # multipole integrals of the electric-field terms (hcgto.py:118-127): 3, 9, 27 components
+        from dqc_b200.hamilton.intor import multipole
+        if not same:
+            raise NotImplementedError("multipole integrals between two different shell ranges are not built")
+        return multipole.multipole1e(len(shortname) // 2, wrapper)
     if shortname not in ("ovlp", "kin", "nuc", "rinv"):
         raise NotImplementedError("int1e_%s is outside the Fock-build path" % shortname)
     if shortname == "rinv":

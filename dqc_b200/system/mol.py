@@ -35,6 +35,14 @@ class Mol(BaseSystem):
         self._basis_inp = basis
         self._grid: Optional[BaseGrid] = None
         self._vext = vext
+        # electric field: a tensor (3,) or a tuple (E (3,), grad E (3, 3), ...), flattened per order like the reference's
+        # _normalize_efield / _preprocess_efield (mol.py:445-473)
+        if isinstance(efield, torch.Tensor):
+            efield = (efield,)
+        if efield is not None:
+            for i, ef in enumerate(efield):
+                assert ef.numel() == 3 ** (i + 1), "The %d-th tuple element of efield must have %d elements" % (i, 3 ** (i + 1))
+            efield = tuple(ef.reshape(-1) for ef in efield)
         self._efield = efield
         self._jk_thresh = jk_thresh
         self._ctx = ctx

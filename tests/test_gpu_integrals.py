@@ -193,3 +193,55 @@ def test_dfj_large_random(cuda):
     temp = torch.einsum("ij,ijl->l", dm, full)
     ref = torch.einsum("k,ijk->ij", temp @ inv, full)
     assert float((vj - ref).abs().max() / ref.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("which", ["h2o-def2svp", "highl-sp"])
+def test_multipole_integrals_match_grid_quadrature_and_symmetry(cuda, which):
+    """int1e_r / int1e_rr / int1e_rrr (the electric-field terms of the core Hamiltonian, hcgto.py:118-127) from the
+    overlap kernel's raw cartesian mode, against numerical quadrature of phi_i r_a r_b phi_j with the ORACLE's AO values
+    on a Becke grid, and against the exact identities (symmetry in i, j and in the component indices; the dipole of an
+    s-function pair at the same centre is the centre times the overlap)."""
+    from dqc_b200.hamilton.intor import molintor as intor
+    from dqc_b200.grid.factory import get_predefined_grid
+    from oracle import cint
+    zs, pos = util.H2O
+    basis = "def2-svp" if which == "h2o-def2svp" else "3-21g"
+    w, _ = util.make_wrapper(zs, [list(map(float, p)) for p in pos], basis)
+    s = intor.overlap(w)
+    orders = (1, 2) if which == "h2o-def2svp" else (1, 2, 3)
+    grid = get_predefined_grid(4, zs, torch.tensor(pos, dtype=torch.float64, device=cuda), device=cuda)
+    xyz, dv = grid.get_rgrid().cpu().numpy(), grid.get_dvolume().cpu().numpy()
+    ao = cint.eval_gto(*w.atm_bas_env, xyz, 0)
+    for n in orders:
+        m = intor.int1e("r0" * n, w)
+        assert m.shape == (3 ** n, w.nao(), w.nao())
+        assert float((m - m.transpose(-2, -1)).abs().max()) < 1e-12
+        mm = m.reshape(*([3] * n), w.nao(), w.nao())
+        if n == 2:
+            assert float((mm - mm.transpose(0, 1)).abs().max()) < 1e-12
+        for ic in range(3 ** n):
+            comps = np.unravel_index(ic, [3] * n)
+            f = np.prod([xyz[:, d] for d in comps], axis=0)
+            quad = (ao * (f * dv)[:, None]).T @ ao
+            assert np.abs(m[ic].cpu().numpy() - quad).max() < 2e-5, (n, ic)
+    # first s function of the oxygen with itself: <r> = R_O S
+    d1 = intor.int1e("r0", w)
+    for d in range(3):
+        assert abs(float(d1[d, 0, 0]) - float(pos[0][d]) * float(s[0, 0])) < 1e-12
+
+
+def test_efield_enters_the_core_hamiltonian(cuda):
+    """Mol(..., efield=E): h = T + V + sum_d E_d <r_d> (hcgto.py:118-127) -- through HamiltonCGTO.build, and the HF energy
+    responds to the field with the dipole moment (finite difference of E(field) = -mu . E to first order ... here just
+    the sign convention: the core Hamiltonian difference equals the dipole matrix contracted with the field)."""
+    from dqc_b200 import Mol
+    from dqc_b200.hamilton.intor import molintor as intor
+    zs, pos = util.H2O
+    e = torch.tensor([0.01, -0.02, 0.03], dtype=torch.float64)
+    mk = lambda ef: Mol((torch.tensor(zs), torch.tensor(pos, dtype=torch.float64)), basis="3-21g", device=cuda,
+                        orthogonalize_basis=False, efield=ef).get_hamiltonian().build()
+    h0, h1 = mk(None), mk(e)
+    w, _ = util.make_wrapper(zs, [list(map(float, p)) for p in pos], "3-21g")
+    dip = intor.int1e("r0", w)
+    diff = h1.get_kinnucl().fullmatrix() - h0.get_kinnucl().fullmatrix()
+    assert float((diff - torch.einsum("dab,d->ab", dip, e.to(dip.device))).abs().max()) < 1e-12
