@@ -118,6 +118,7 @@ _SIGS = {
     "b200qc_jkplan_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                             ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_jkplan_nquartets": (ctypes.c_int64, [ctypes.c_void_p]),
+    "b200qc_jkplan_nquartets_reg": (ctypes.c_int64, [ctypes.c_void_p]),
     "b200qc_jkplan_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200qc_jkplan_free": (ctypes.c_int, [ctypes.c_void_p]),
@@ -531,6 +532,7 @@ class JKPlan(object):
                    "jkplan_create")
         self.handle = h
         self.nquartets = int(lib.b200qc_jkplan_nquartets(h))
+        self.nquartets_reg = int(lib.b200qc_jkplan_nquartets_reg(h))   # on the register-resident engine (l <= 1 classes)
 
     def run(self, dm: torch.Tensor, with_j=True, with_k=True, rank=0, world=1):
         """dm (nset, nao, nao) symmetric -> vj, vk (nset, nao, nao); partial sums when world > 1."""

@@ -21,6 +21,9 @@ if newer build/b200qc_tc.o b200qc_tc.cu common.cuh sb_common.cuh vxc_i8.cuh rho_
         ../../include/b200qc.h build.sh; then
     $NVCC $FLAGS -c -o build/b200qc_tc.o b200qc_tc.cu & PIDS="$PIDS $!"
 fi
+if newer build/b200qc_jk.o b200qc_jk.cu common.cuh jk_reg.cuh ../../include/b200qc.h build.sh; then
+    $NVCC $FLAGS -c -o build/b200qc_jk.o b200qc_jk.cu & PIDS="$PIDS $!"
+fi
 for p in $PIDS; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o ../libb200qc.so build/b200qc.o build/b200qc_tc.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o ../libb200qc.so build/b200qc.o build/b200qc_tc.o build/b200qc_jk.o
 echo "built $(realpath ../libb200qc.so)"

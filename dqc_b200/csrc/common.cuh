@@ -112,6 +112,42 @@ static bool g_rys_ready[64] = {};   // per device (tables.cuh)
 
 static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 
+// ---- direct J/K, register-resident quartet engine (jk_reg.cuh, third translation unit b200qc_jk.cu) ----
+// The plan (jk.cuh) hands it shell-pair records with their primitive-pair data precomputed once per geometry.
+struct JKPair {            // one shell pair, canonical order l(i) >= l(j)
+    double ax, ay, az;     // centre of shell i
+    double abx, aby, abz;  // A - B
+    int ish, jsh;          // shell indices (symmetry factors only)
+    int ao_i, ao_j;        // first AO of each shell relative to the plan's slice
+    int npp, pp_off;       // primitive pairs [pp_off, pp_off + npp) of the plan's JKPrim array
+};
+struct JKPrim {            // one primitive pair (a_i, a_j) of a shell pair
+    double p, hp;          // a_i + a_j, 1 / (2 p)
+    double px, py, pz;     // P = (a_i A + a_j B) / p
+    double c;              // c_i c_j exp(-a_i a_j |AB|^2 / p) / p  x  the s / p real-spherical constants of both shells
+};
+#define JKR_MAXROOTS 5
+struct JKRArgs {
+    int l[4];                     // (li lj | lk ll), li >= lj, lk >= ll
+    const JKPair *bra, *ket;      // class slices of the plan's pair records
+    const JKPrim *prims;
+    const int2 *items;            // work items: (bra index, first ket index); kets [k0, min(k0 + JKR_CHUNK, nket_of_bra))
+    const int *nket_of_bra;
+    int64_t nitems;
+    int item0, item_stride;       // this rank digests items item0, item0 + item_stride, ...
+    const double *dm;             // (nao, nao) symmetric
+    double *vj, *vk;              // (nao, nao) accumulators or NULL
+    int nao;
+    const double *rys_coef;       // device, (nint, 2 nroots, deg + 1) of this class's root count
+    int rys_nint, rys_deg;
+    double rys_h, rys_xmax;
+    double herm_u[JKR_MAXROOTS], herm_w[JKR_MAXROOTS];   // large-x rule: u_r = herm_u[r] / x, w_r = herm_w[r] / sqrt(x)
+};
+#define JKR_CHUNK 128      // kets per work item (four per lane)
+#define JKR_MAXPP 36       // primitive pairs per shell pair the engine stages (6 x 6)
+QC_HIDDEN int jkr_supported(const int l[4]);
+QC_HIDDEN int jkr_launch(const JKRArgs &A, cudaStream_t st);
+
 // ---- optional per-kernel timing (bench.py's roofline numbers) ------------------------------
 // When enabled every major launch is bracketed by CUDA events on its own stream; reading the
 // profile synchronises once and returns, per kernel id, launch count and summed device time.

@@ -15,6 +15,7 @@
 #pragma once
 #include "ints.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 #define JK_CHUNK 16
 #define JK_MAXSET 2
@@ -26,6 +27,8 @@ struct JKClassPair {
     int *d_nket_of_bra = nullptr;        // admissible kets per bra
     int64_t nitems = 0;
     int same;
+    int reg = 0;                         // 1: register-resident quartet engine (jk_reg.cuh), work items in d_items
+    int2 *d_items = nullptr;             // (bra, first ket) per chunk of JKR_CHUNK kets
 };
 
 struct b200qc_jkplan {
@@ -33,9 +36,23 @@ struct b200qc_jkplan {
     int sh0, sh1, ao0, nao;
     int2 *d_pairs = nullptr;
     double *d_q = nullptr;
+    JKPair *d_jkpairs = nullptr;         // the same pairs as d_pairs with their geometry (register engine)
+    JKPrim *d_prims = nullptr;           // primitive-pair data, pp_off of a pair points in here
     std::vector<JKClassPair> cps;
-    int64_t nquartets = 0;
+    int64_t nquartets = 0, nquartets_reg = 0;
 };
+
+// Primitive pairs whose Gaussian-product factor exp(-a_i a_j |AB|^2 / (a_i + a_j)) is below e^-50 = 2e-22 are left out
+// of the register engine's pair data (the shared-memory engine skips primitive quartets beyond e^-80).
+#define JKR_EACUT 50.0
+static const int g_jkr_buckets[] = {1, 2, 3, 4, 6, 9, 16, JKR_MAXPP};
+#define JKR_NBUCKET ((int)(sizeof(g_jkr_buckets) / sizeof(int)))
+// bucket of a primitive-pair count: lanes of a warp walk kets of one bucket, so their trip counts are close
+static int jkr_bucket(int npp) {
+    for (int b = 0; b < JKR_NBUCKET; b++)
+        if (npp <= g_jkr_buckets[b]) return b;
+    return JKR_NBUCKET;   // too many primitive pairs to stage: shared-memory engine
+}
 
 template <int G, int NACC>
 __global__ void __launch_bounds__(INT_THREADS)
@@ -219,9 +236,12 @@ extern "C" int b200qc_jkplan_free(b200qc_jkplan *p) {
     if (!p) return 0;
     cudaFree(p->d_pairs);
     cudaFree(p->d_q);
+    cudaFree(p->d_jkpairs);
+    cudaFree(p->d_prims);
     for (auto &cp : p->cps) {
         cudaFree(cp.d_work_off);
         cudaFree(cp.d_nket_of_bra);
+        cudaFree(cp.d_items);
     }
     delete p;
     return 0;
@@ -269,48 +289,103 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
     double qmax = 0.0;
     for (const int2 &p : tri.h) qmax = std::max(qmax, q[(size_t)p.x * nb + p.y]);
 
-    // 2. per class: drop pairs that cannot pass with any partner, sort by Q descending
+    // 2. surviving pairs in canonical orientation l(i) >= l(j), with their primitive-pair data; classes =
+    //    (l_i, l_j, bucket of the primitive-pair count), inside a class sorted by Q descending
     auto *plan = new b200qc_jkplan();
     plan->basis = basis;
     plan->sh0 = sh0; plan->sh1 = sh1;
     plan->ao0 = basis->h_ao_loc[sh0];
     plan->nao = basis->h_ao_loc[sh1] - plan->ao0;
+    struct PairTmp {
+        int2 p;
+        double q;
+        int key;                 // (l_i * 8 + l_j) * 16 + bucket
+        std::vector<JKPrim> prims;
+    };
+    std::vector<PairTmp> all;
+    static const double c2s_const[2] = {0.282094791773878143, 0.488602511902919921};   // s, p (tables.cuh)
+    const bool reg_ok = !getenv("B200QC_JK_NOREG");
+    for (size_t e = 0; e < tri.h.size(); e++) {
+        int2 p = tri.h[e];
+        const double qq = q[(size_t)p.x * nb + p.y];
+        if (qq * qmax < thresh) continue;
+        if (basis->h_shells[p.x].l < basis->h_shells[p.y].l) std::swap(p.x, p.y);
+        const ShellRec &si = basis->h_shells[p.x], &sj = basis->h_shells[p.y];
+        PairTmp t;
+        t.p = p;
+        t.q = qq;
+        const double abx = si.x - sj.x, aby = si.y - sj.y, abz = si.z - sj.z;
+        const double ab2 = abx * abx + aby * aby + abz * abz;
+        const double sc = (si.l <= 1 ? c2s_const[si.l] : 1.0) * (sj.l <= 1 ? c2s_const[sj.l] : 1.0);
+        for (int ip = 0; ip < si.nprim; ip++)
+            for (int jp = 0; jp < sj.nprim; jp++) {
+                const double ai = basis->h_env[si.ptr_exp + ip], aj = basis->h_env[sj.ptr_exp + jp];
+                const double pp = ai + aj, ea = ai * aj / pp * ab2;
+                if (ea > JKR_EACUT) continue;
+                JKPrim r;
+                r.p = pp;
+                r.hp = 0.5 / pp;
+                r.px = (ai * si.x + aj * sj.x) / pp;
+                r.py = (ai * si.y + aj * sj.y) / pp;
+                r.pz = (ai * si.z + aj * sj.z) / pp;
+                r.c = sc * basis->h_env[si.ptr_coef + ip] * basis->h_env[sj.ptr_coef + jp] * std::exp(-ea) / pp;
+                t.prims.push_back(r);
+            }
+        const int bucket = reg_ok ? jkr_bucket((int)t.prims.size()) : JKR_NBUCKET;
+        t.key = (si.l * 8 + sj.l) * 16 + bucket;
+        all.push_back(std::move(t));
+    }
+    std::stable_sort(all.begin(), all.end(), [](const PairTmp &a, const PairTmp &b) {
+        return a.key != b.key ? a.key < b.key : a.q > b.q;
+    });
     std::vector<int2> pairs;
     std::vector<double> qs;
-    std::vector<int> coff, cla, clb;
-    for (size_t c = 0; c + 1 < tri.cls_off.size(); c++) {
-        std::vector<std::pair<double, int2>> v;
-        for (int e = tri.cls_off[c]; e < tri.cls_off[c + 1]; e++) {
-            const int2 p = tri.h[e];
-            const double qq = q[(size_t)p.x * nb + p.y];
-            if (qq * qmax >= thresh) v.push_back({qq, p});
+    std::vector<JKPair> jkpairs;
+    std::vector<JKPrim> prims;
+    std::vector<int> coff, cla, clb, cbucket;
+    for (size_t e = 0; e < all.size(); e++) {
+        const PairTmp &t = all[e];
+        if (e == 0 || t.key != all[e - 1].key) {
+            coff.push_back((int)e);
+            cla.push_back(t.key / 128);
+            clb.push_back((t.key / 16) % 8);
+            cbucket.push_back(t.key % 16);
         }
-        std::stable_sort(v.begin(), v.end(), [](const std::pair<double, int2> &a, const std::pair<double, int2> &b) {
-            return a.first > b.first;
-        });
-        if (v.empty()) continue;
-        coff.push_back((int)pairs.size());
-        cla.push_back(tri.cls_la[c]);
-        clb.push_back(tri.cls_lb[c]);
-        for (auto &e : v) {
-            pairs.push_back(e.second);
-            qs.push_back(e.first);
-        }
+        const ShellRec &si = basis->h_shells[t.p.x], &sj = basis->h_shells[t.p.y];
+        JKPair r;
+        r.ax = si.x; r.ay = si.y; r.az = si.z;
+        r.abx = si.x - sj.x; r.aby = si.y - sj.y; r.abz = si.z - sj.z;
+        r.ish = t.p.x; r.jsh = t.p.y;
+        r.ao_i = si.ao_off - plan->ao0; r.ao_j = sj.ao_off - plan->ao0;
+        r.npp = (int)t.prims.size();
+        r.pp_off = (int)prims.size();
+        prims.insert(prims.end(), t.prims.begin(), t.prims.end());
+        jkpairs.push_back(r);
+        pairs.push_back(t.p);
+        qs.push_back(t.q);
     }
     coff.push_back((int)pairs.size());
     if (pairs.empty()) {
         *out = plan;
         return 0;
     }
+    if (prims.empty()) prims.push_back(JKPrim{1.0, 0.5, 0.0, 0.0, 0.0, 0.0});
     QC_CHECK(cudaMalloc(&plan->d_pairs, sizeof(int2) * pairs.size()));
     QC_CHECK(cudaMemcpy(plan->d_pairs, pairs.data(), sizeof(int2) * pairs.size(), cudaMemcpyHostToDevice));
-    // 3. class pairs (bra class >= ket class) with their work-item prefix tables
+    QC_CHECK(cudaMalloc(&plan->d_jkpairs, sizeof(JKPair) * jkpairs.size()));
+    QC_CHECK(cudaMemcpy(plan->d_jkpairs, jkpairs.data(), sizeof(JKPair) * jkpairs.size(), cudaMemcpyHostToDevice));
+    QC_CHECK(cudaMalloc(&plan->d_prims, sizeof(JKPrim) * prims.size()));
+    QC_CHECK(cudaMemcpy(plan->d_prims, prims.data(), sizeof(JKPrim) * prims.size(), cudaMemcpyHostToDevice));
+    // 3. class pairs (bra class >= ket class) with their work items
+    const RysTable &rt = g_rys_host[basis->device];
     const size_t ncls = cla.size();
     for (size_t cb = 0; cb < ncls; cb++)
         for (size_t ck = 0; ck <= cb; ck++) {
             JKClassPair cp;
             const int l[4] = {cla[cb], clb[cb], cla[ck], clb[ck]};
             const int pr[4] = {1, 1, 1, 1};
+            cp.reg = cbucket[cb] < JKR_NBUCKET && cbucket[ck] < JKR_NBUCKET && jkr_supported(l) &&
+                     rt.nint == 64 && rt.deg == 13;
             if (int_make_class(cp.K, INT_MODE_ERI, SINK_JK, l, pr, 0)) {
                 b200qc_jkplan_free(plan);
                 b200qc_set_error("J/K class outside the supported range");
@@ -319,9 +394,12 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
             cp.bra_off = coff[cb]; cp.nbra = coff[cb + 1] - coff[cb];
             cp.ket_off = coff[ck]; cp.nket = coff[ck + 1] - coff[ck];
             cp.same = cb == ck;
+            const int chunk = cp.reg ? JKR_CHUNK : JK_CHUNK;
             std::vector<int64_t> woff(cp.nbra + 1, 0);
             std::vector<int> nkb(cp.nbra, 0);
+            std::vector<int2> items;
             const double *qk = qs.data() + cp.ket_off;
+            int64_t nq = 0;
             for (int b = 0; b < cp.nbra; b++) {
                 const double qb = qs[cp.bra_off + b];
                 // kets sorted descending: count those with qb * qk >= thresh
@@ -333,15 +411,24 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
                 int n = lo;
                 if (cp.same) n = std::min(n, b + 1);
                 nkb[b] = n;
-                woff[b + 1] = woff[b] + (n + JK_CHUNK - 1) / JK_CHUNK;
-                plan->nquartets += n;
+                woff[b + 1] = woff[b] + (n + chunk - 1) / chunk;
+                if (cp.reg)
+                    for (int k0 = 0; k0 < n; k0 += chunk) items.push_back(make_int2(b, k0));
+                nq += n;
             }
+            plan->nquartets += nq;
+            if (cp.reg) plan->nquartets_reg += nq;
             cp.nitems = woff[cp.nbra];
             if (cp.nitems == 0) continue;
-            QC_CHECK(cudaMalloc(&cp.d_work_off, sizeof(int64_t) * woff.size()));
             QC_CHECK(cudaMalloc(&cp.d_nket_of_bra, sizeof(int) * nkb.size()));
-            QC_CHECK(cudaMemcpy(cp.d_work_off, woff.data(), sizeof(int64_t) * woff.size(), cudaMemcpyHostToDevice));
             QC_CHECK(cudaMemcpy(cp.d_nket_of_bra, nkb.data(), sizeof(int) * nkb.size(), cudaMemcpyHostToDevice));
+            if (cp.reg) {
+                QC_CHECK(cudaMalloc(&cp.d_items, sizeof(int2) * items.size()));
+                QC_CHECK(cudaMemcpy(cp.d_items, items.data(), sizeof(int2) * items.size(), cudaMemcpyHostToDevice));
+            } else {
+                QC_CHECK(cudaMalloc(&cp.d_work_off, sizeof(int64_t) * woff.size()));
+                QC_CHECK(cudaMemcpy(cp.d_work_off, woff.data(), sizeof(int64_t) * woff.size(), cudaMemcpyHostToDevice));
+            }
             plan->cps.push_back(cp);
         }
     *out = plan;
@@ -349,6 +436,8 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
 }
 
 extern "C" int64_t b200qc_jkplan_nquartets(const b200qc_jkplan *p) { return p ? p->nquartets : 0; }
+// quartets that go through the register-resident engine (jk_reg.cuh); the rest use the shared-memory engine
+extern "C" int64_t b200qc_jkplan_nquartets_reg(const b200qc_jkplan *p) { return p ? p->nquartets_reg : 0; }
 
 // dm: (nset, nao, nao) symmetric; vj / vk: (nset, nao, nao) or NULL.  rank / world: this process
 // digests work items rank, rank + world, ... (partial J / K; the caller all-reduces).
@@ -360,7 +449,36 @@ extern "C" int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, in
     const int64_t nn = (int64_t)plan->nao * plan->nao;
     if (vj) QC_CHECK(cudaMemsetAsync(vj, 0, sizeof(double) * nn * nset, st));
     if (vk) QC_CHECK(cudaMemsetAsync(vk, 0, sizeof(double) * nn * nset, st));
+    const RysTable &rt = g_rys_host[plan->basis->device];
     for (const JKClassPair &cp : plan->cps) {
+        if (cp.reg) {
+            JKRArgs R = {};
+            for (int s = 0; s < 4; s++) R.l[s] = cp.K.l[s];
+            R.bra = plan->d_jkpairs + cp.bra_off;
+            R.ket = plan->d_jkpairs + cp.ket_off;
+            R.prims = plan->d_prims;
+            R.items = cp.d_items;
+            R.nket_of_bra = cp.d_nket_of_bra;
+            R.nitems = cp.nitems;
+            R.item0 = rank; R.item_stride = world;
+            R.nao = plan->nao;
+            const int nr = cp.K.nroots;
+            R.rys_coef = rt.coef[nr - 1];
+            R.rys_nint = rt.nint; R.rys_deg = rt.deg;
+            R.rys_h = rt.h; R.rys_xmax = rt.xmax;
+            for (int r = 0; r < nr; r++) {
+                R.herm_u[r] = rt.herm[nr - 1][0][r];
+                R.herm_w[r] = rt.herm[nr - 1][1][r];
+            }
+            for (int s = 0; s < nset; s++) {   // one density per launch: the block stays in registers
+                R.dm = dm + s * nn;
+                R.vj = vj ? vj + s * nn : nullptr;
+                R.vk = vk ? vk + s * nn : nullptr;
+                int rc = jkr_launch(R, st);
+                if (rc) return rc;
+            }
+            continue;
+        }
         IntArgs A = {};
         A.shells = plan->basis->d_shells;
         A.env = plan->basis->d_env;

@@ -215,7 +215,8 @@ extern "C" int b200qc_basis_free(b200qc_basis *b) {
     return 0;
 }
 
-static std::vector<double *> g_rys_dev[QC_MAX_DEVICES];   // per device, like the __constant__ RysTable that points at them
+static std::vector<double *> g_rys_dev[QC_MAX_DEVICES];
+static RysTable g_rys_host[QC_MAX_DEVICES];   // host copy of each device's table descriptor (jk.cuh hands it to jk_reg.cuh)   // per device, like the __constant__ RysTable that points at them
 
 extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
                                  const double *const *h_coef, const double *const *h_herm) {
@@ -244,6 +245,7 @@ extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
         }
     }
     QC_CHECK(cudaMemcpyToSymbol(c_rys, &t, sizeof(t)));
+    g_rys_host[dev] = t;
     g_rys_ready[dev] = true;
     return 0;
 }

@@ -255,6 +255,9 @@ typedef struct b200qc_jkplan b200qc_jkplan;
 int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1, double thresh, b200qc_jkplan **out,
                          void *stream);
 int64_t b200qc_jkplan_nquartets(const b200qc_jkplan *plan);
+/* of those, the quartets of classes with l <= 1 on every shell: they run on the register-resident engine (one lane =
+ * one contracted quartet, a warp = one bra pair x 128 kets; csrc/jk_reg.cuh), the others on the shared-memory engine */
+int64_t b200qc_jkplan_nquartets_reg(const b200qc_jkplan *plan);
 int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, int nset, double *vj, double *vk, int rank,
                       int world, void *stream);
 int b200qc_jkplan_free(b200qc_jkplan *plan);

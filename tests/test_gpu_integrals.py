@@ -150,6 +150,36 @@ def test_jk_direct_matches_dense_contraction(cuda, which, nset):
     assert float((k0 + k1 - kref.to(cuda)).abs().max()) < 1e-10
 
 
+def test_jk_register_engine_matches_stored_eri_and_shared_engine(cuda, monkeypatch):
+    """The register-resident quartet engine (csrc/jk_reg.cuh: every class pair of an s/p basis) on a 14-atom carbon
+    cluster / 3-21G -- several primitive-count buckets, bras with more than one 128-ket work item, partial last rounds --
+    against the stored-ERI GEMVs (Rys integrals pinned by the oracle above) and the shared-memory engine it replaces."""
+    from dqc_b200 import _lib
+    from dqc_b200.utils import systems
+    zs, pos = systems.carbon_cluster(14)
+    w, _ = util.make_wrapper(zs, pos.tolist(), "3-21g")
+    nb, nao = len(w), w.nao()
+    db = w.device_basis(cuda)
+    dms = torch.stack([util.seeded_dm(nao, nao // 4, seed=1), util.seeded_dm(nao, nao // 5, seed=2)]).to(cuda)
+    plan = _lib.JKPlan(db, 0, nb, 1e-14)
+    assert plan.nquartets_reg == plan.nquartets > 0       # s and p shells only: nothing left on the other engine
+    vj, vk = plan.run(dms)
+    js, ks = _lib.StoredERI(db, 0, nb).run(dms)
+    assert float((vj - js).abs().max()) < 1e-10 and float((vk - ks).abs().max()) < 1e-10
+    # J only / K only launches, and three "ranks" adding up
+    j_only, _ = plan.run(dms, True, False)
+    _, k_only = plan.run(dms, False, True)
+    assert float((j_only - js).abs().max()) < 1e-10 and float((k_only - ks).abs().max()) < 1e-10
+    parts = [plan.run(dms[:1], rank=r, world=3) for r in range(3)]
+    assert float((sum(p[0] for p in parts) - js[:1]).abs().max()) < 1e-10
+    assert float((sum(p[1] for p in parts) - ks[:1]).abs().max()) < 1e-10
+    monkeypatch.setenv("B200QC_JK_NOREG", "1")
+    old = _lib.JKPlan(db, 0, nb, 1e-14)
+    assert old.nquartets_reg == 0 and old.nquartets == plan.nquartets
+    oj, ok = old.run(dms)
+    assert float((vj - oj).abs().max()) < 1e-10 and float((vk - ok).abs().max()) < 1e-10
+
+
 def test_dfj_matches_oracle(cuda):
     """K9 against the reference's DF-J ops (dfmol.py:66-76) on oracle integrals."""
     from dqc_b200 import _lib
