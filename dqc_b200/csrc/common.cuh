@@ -142,6 +142,7 @@ struct JKRArgs {
     int rys_nint, rys_deg;
     double rys_h, rys_xmax;
     double herm_u[JKR_MAXROOTS], herm_w[JKR_MAXROOTS];   // large-x rule: u_r = herm_u[r] / x, w_r = herm_w[r] / sqrt(x)
+    double c2s_d[30];             // cart -> real-spherical matrix of d shells, [m][c] (tables.cuh)
 };
 #define JKR_CHUNK 128      // kets per work item (four per lane)
 #define JKR_MAXPP 36       // primitive pairs per shell pair the engine stages (6 x 6)

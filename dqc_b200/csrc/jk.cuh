@@ -470,6 +470,7 @@ extern "C" int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, in
                 R.herm_u[r] = rt.herm[nr - 1][0][r];
                 R.herm_w[r] = rt.herm[nr - 1][1][r];
             }
+            h_fill_c2s(2, R.c2s_d);
             for (int s = 0; s < nset; s++) {   // one density per launch: the block stays in registers
                 R.dm = dm + s * nn;
                 R.vj = vj ? vj + s * nn : nullptr;

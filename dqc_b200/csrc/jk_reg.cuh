@@ -17,9 +17,13 @@
 //   * digestion: the lane contracts its block with the six density tiles; the bra-tile J_ij stays in registers across
 //     the lane's kets, is summed over the warp by shuffles and leaves as ONE atomic per element per work item; the
 //     ket-side J_kl and the four K tiles go out with fp64 atomics (RED.E.ADD.F64.STRONG.GPU).
-// Shells with l <= 1 only: their real-spherical transform is a constant per shell that the plan folds into the
-// primitive coefficients, so the cartesian block IS the spherical one.  Classes with d shells and above stay on the
-// shared-memory engine of jk.cuh.
+// s, p and d shells.  For l <= 1 the real-spherical transform is a constant per shell that the plan folds into the
+// primitive coefficients; d shells are digested in CARTESIAN components: the density tiles are expanded with the 5 x 6
+// c2s matrix when they are loaded and the J / K tiles contracted with it before they are added (J = C J_cart C^T with
+// D_cart = C^T D C), so the 6-component block never needs transforming.  Classes whose block exceeds the registers
+// ((dp|pp) and up) run as several passes over slices of the bra components, each pass recomputing roots and tables and
+// keeping <= 72 integrals per lane (the unused table entries of a pass are dead code).  Classes with f shells and
+// above stay on the shared-memory engine of jk.cuh.
 #pragma once
 #include "common.cuh"
 #include <utility>
@@ -28,7 +32,8 @@
 #define JKR_WARPS (JKR_THREADS / 32)
 #define JKR_NINT 64
 #define JKR_NCOEF 14
-#define JKR_WSM (JKR_MAXPP * 6 + 40)   // doubles of shared memory per warp: bra primitive pairs + D_ij tile
+#define JKR_WSM (JKR_MAXPP * 6 + 36 + 36 + 32)   // doubles of shared memory per warp: bra primitive pairs, D_ij and J_ij
+                                                // tiles (cartesian), D_ij as stored
 
 namespace jkr {
 
@@ -110,18 +115,6 @@ __device__ __forceinline__ void build_table(double (&T)[Shape<LI, LJ, LK, LL>::T
     }
 }
 
-template <class S, int C>
-__device__ __forceinline__ void acc_one(double (&acc)[S::NC], const double (&Tx)[S::TS], const double (&Ty)[S::TS],
-                                        const double (&Tz)[S::TS]) {
-    constexpr int ix = S::comp_index(C, 0), iy = S::comp_index(C, 1), iz = S::comp_index(C, 2);
-    acc[C] += Tx[ix] * Ty[iy] * Tz[iz];
-}
-template <class S, int... Cs>
-__device__ __forceinline__ void acc_all(double (&acc)[S::NC], const double (&Tx)[S::TS], const double (&Ty)[S::TS],
-                                        const double (&Tz)[S::TS], std::integer_sequence<int, Cs...>) {
-    (acc_one<S, Cs>(acc, Tx, Ty, Tz), ...);
-}
-
 // nodes u_r = t_r^2 and weights of the NR-point Rys rule at x: same arithmetic as rys_eval (rys.cuh), all 2 NR
 // Clenshaw recurrences interleaved, table rt[(k * 2 NR + f) * JKR_NINT + interval] in shared memory
 template <int NR>
@@ -160,24 +153,350 @@ __device__ __forceinline__ void rys_roots(double x, const double *__restrict__ r
     }
 }
 
-template <int LI, int LJ, int LK, int LL, bool DOJ, bool DOK>
+// ---- real-spherical <-> cartesian on the AO side ---------------------------------------------------------------
+// l <= 1: the engine's cartesian functions ARE the AOs (constant folded into the coefficients); l == 2: the five real
+// d functions, c2s matrix (5 x 6, rows m = -2..2 = xy, yz, z^2, xz, x^2 - y^2; tables.cuh) in JKRArgs::c2s_d.
+template <int L> struct Sph { static constexpr int n = L <= 1 ? ncart(L) : 2 * L + 1; };
+__host__ __device__ constexpr bool d_nz(int m, int c) {   // cartesian order xx xy xz yy yz zz
+    return m == 0 ? c == 1 : m == 1 ? c == 4 : m == 2 ? (c == 0 || c == 3 || c == 5) : m == 3 ? c == 2 : (c == 0 || c == 3);
+}
+template <int L> __host__ __device__ constexpr bool c2s_nz(int m, int c) { return L <= 1 ? m == c : d_nz(m, c); }
+template <int L> __device__ __forceinline__ double c2s_v(const JKRArgs &A, int m, int c) {
+    return L <= 1 ? 1.0 : A.c2s_d[m * 6 + c];
+}
+
+// t[ca][cb] (cartesian) of the density block with first AOs (ra, cb0)
+template <int LA, int LB>
+__device__ __forceinline__ void load_tile(const double *__restrict__ D, int ra, int cb0, int nao, const JKRArgs &A,
+                                          double (&t)[ncart(LA) * ncart(LB)]) {
+    constexpr int NSA = Sph<LA>::n, NSB = Sph<LB>::n, NCA = ncart(LA), NCB = ncart(LB);
+    double s[NSA * NSB];
+#pragma unroll
+    for (int e = 0; e < NSA * NSB; e++) s[e] = D[(int64_t)(ra + e / NSB) * nao + cb0 + e % NSB];
+    double h[NCA * NSB];
+    if constexpr (LA <= 1) {
+#pragma unroll
+        for (int e = 0; e < NCA * NSB; e++) h[e] = s[e];
+    } else {
+#pragma unroll
+        for (int ca = 0; ca < NCA; ca++) {
+#pragma unroll
+            for (int mb = 0; mb < NSB; mb++) {
+                double v = 0.0;
+#pragma unroll
+                for (int ma = 0; ma < NSA; ma++)
+                    if (c2s_nz<LA>(ma, ca)) v += c2s_v<LA>(A, ma, ca) * s[ma * NSB + mb];
+                h[ca * NSB + mb] = v;
+            }
+        }
+    }
+    if constexpr (LB <= 1) {
+#pragma unroll
+        for (int e = 0; e < NCA * NCB; e++) t[e] = h[e];
+    } else {
+#pragma unroll
+        for (int ca = 0; ca < NCA; ca++) {
+#pragma unroll
+            for (int cb = 0; cb < NCB; cb++) {
+                double v = 0.0;
+#pragma unroll
+                for (int mb = 0; mb < NSB; mb++)
+                    if (c2s_nz<LB>(mb, cb)) v += c2s_v<LB>(A, mb, cb) * h[ca * NSB + mb];
+                t[ca * NCB + cb] = v;
+            }
+        }
+    }
+}
+
+struct AllRows { __host__ __device__ static constexpr bool has(int) { return true; } };
+
+// M[ra + ma][cb0 + mb] += scale * (c2s_A t c2s_B^T)[ma][mb]; cartesian rows of t outside RM::has are absent (zero):
+// only the AO rows they reach are touched
+template <int LA, int LB, class RM>
+__device__ __forceinline__ void add_tile(double *__restrict__ M, int ra, int cb0, int nao, const JKRArgs &A,
+                                         const double (&t)[ncart(LA) * ncart(LB)], double scale) {
+    constexpr int NSA = Sph<LA>::n, NSB = Sph<LB>::n, NCA = ncart(LA), NCB = ncart(LB);
+#pragma unroll
+    for (int ma = 0; ma < NSA; ma++) {
+        bool touched = false;
+#pragma unroll
+        for (int ca = 0; ca < NCA; ca++) touched = touched || (RM::has(ca) && c2s_nz<LA>(ma, ca));
+        if (!touched) continue;
+        double h[NCB];
+#pragma unroll
+        for (int cb = 0; cb < NCB; cb++) {
+            double v = 0.0;
+#pragma unroll
+            for (int ca = 0; ca < NCA; ca++)
+                if (RM::has(ca) && c2s_nz<LA>(ma, ca)) v += c2s_v<LA>(A, ma, ca) * t[ca * NCB + cb];
+            h[cb] = v;
+        }
+#pragma unroll
+        for (int mb = 0; mb < NSB; mb++) {
+            double v = 0.0;
+#pragma unroll
+            for (int cb = 0; cb < NCB; cb++)
+                if (c2s_nz<LB>(mb, cb)) v += c2s_v<LB>(A, mb, cb) * h[cb];
+            atomicAdd(M + (int64_t)(ra + ma) * nao + cb0 + mb, scale * v);
+        }
+    }
+}
+
+// A pass = the bra components e = ci * NJ + cj in [E0, E1): their NE x NKL integrals are the register block.
+template <class S, int E0_, int E1_>
+struct Pass {
+    static constexpr int E0 = E0_, E1 = E1_, NE = E1_ - E0_, NACC = NE * S::NKL;
+    static constexpr int A0 = E0_ / S::NJ, A1 = (E1_ - 1) / S::NJ;
+    __host__ __device__ static constexpr bool has(int a, int b) { return a * S::NJ + b >= E0_ && a * S::NJ + b < E1_; }
+    struct RowsA { __host__ __device__ static constexpr bool has(int a) { return a >= A0 && a <= A1; } };
+    struct RowsB {
+        __host__ __device__ static constexpr bool has(int b) {
+            return A1 > A0 + 1 ? true
+                 : A1 == A0 ? (b >= E0_ % S::NJ && b <= (E1_ - 1) % S::NJ)
+                            : (b >= E0_ % S::NJ || b <= (E1_ - 1) % S::NJ);
+        }
+    };
+};
+
+template <class S, class P, int C>
+__device__ __forceinline__ void acc_one(double (&acc)[P::NACC], const double (&Tx)[S::TS], const double (&Ty)[S::TS],
+                                        const double (&Tz)[S::TS]) {
+    constexpr int cg = P::E0 * S::NKL + C;   // component index in the full block
+    constexpr int ix = S::comp_index(cg, 0), iy = S::comp_index(cg, 1), iz = S::comp_index(cg, 2);
+    acc[C] += Tx[ix] * Ty[iy] * Tz[iz];
+}
+template <class S, class P, int... Cs>
+__device__ __forceinline__ void acc_all(double (&acc)[P::NACC], const double (&Tx)[S::TS], const double (&Ty)[S::TS],
+                                        const double (&Tz)[S::TS], std::integer_sequence<int, Cs...>) {
+    (acc_one<S, P, Cs>(acc, Tx, Ty, Tz), ...);
+}
+
+// a[r] without run-time indexing of a register array
+template <int N> __device__ __forceinline__ double pick(const double (&a)[N], int r) {
+    double v = a[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) v = r == i ? a[i] : v;
+    return v;
+}
+
+// One pass over one contracted quartet per lane (valid lanes): integrals of the pass's bra components, digestion.
+// Every lane of the warp calls it (the J_ij partial sums are reduced over the warp at the end).
+template <int LI, int LJ, int LK, int LL, class P, bool DOJ, bool DOK>
+__device__ __forceinline__ void quartet_pass(bool valid, const JKPair &bp, const JKPair &kp, const double *wprim,
+                                             const double *wdij, double *wjij, const double *__restrict__ rt,
+                                             const JKRArgs &A, double ih, int lane) {
+    using S = Shape<LI, LJ, LK, LL>;
+    constexpr int NI = S::NI, NJ = S::NJ, NK = S::NK, NL = S::NL, NR = S::NR, NKL = S::NKL;
+    constexpr int E0 = P::E0, NE = P::NE;
+    double jc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; e++) jc[e] = 0.0;
+    if (valid) {
+        const int nao = A.nao;
+        const double *__restrict__ D = A.dm;
+        double acc[P::NACC];
+#pragma unroll
+        for (int c = 0; c < P::NACC; c++) acc[c] = 0.0;
+        const JKPrim *__restrict__ kpr = A.prims + kp.pp_off;
+        for (int pk = 0; pk < kp.npp; pk++) {
+            const JKPrim kq = kpr[pk];
+            const double qcx = kq.px - kp.ax, qcy = kq.py - kp.ay, qcz = kq.pz - kp.az;
+            for (int pb = 0; pb < bp.npp; pb++) {
+                const double p = wprim[pb * 6], hp = wprim[pb * 6 + 1];
+                const double px = wprim[pb * 6 + 2], py = wprim[pb * 6 + 3], pz = wprim[pb * 6 + 4];
+                const double pq = p + kq.p;
+                const double rs = rsqrt(pq);
+                const double ipq = rs * rs;
+                const double dx = px - kq.px, dy = py - kq.py, dz = pz - kq.pz;
+                const double x = p * kq.p * ipq * (dx * dx + dy * dy + dz * dz);
+                const double pref = wprim[pb * 6 + 5] * kq.c * 34.98683665524972497 /* 2 pi^2.5 */ * rs;
+                const double a0 = kq.p * ipq, a1 = p * ipq;
+                double u[NR], w[NR];
+                rys_roots<NR>(x, rt, A, ih, u, w);
+                const double pax = px - bp.ax, pay = py - bp.ay, paz = pz - bp.az;
+                // d classes with three and more roots: the loop over roots stays rolled (a quarter of the code)
+#pragma unroll((LI >= 2 && NR >= 3) ? 1 : NR)
+                for (int r = 0; r < NR; r++) {
+                    const double ur = pick<NR>(u, r), wr = pick<NR>(w, r);
+                    const double a0u = a0 * ur, a1u = a1 * ur;
+                    const double b10 = (1.0 - a0u) * hp, b01 = (1.0 - a1u) * kq.hp, b00 = 0.5 * ur * ipq;
+                    double Tx[S::TS], Ty[S::TS], Tz[S::TS];
+                    build_table<LI, LJ, LK, LL>(Tx, 1.0, pax - a0u * dx, qcx + a1u * dx, b10, b01, b00, bp.abx, kp.abx);
+                    build_table<LI, LJ, LK, LL>(Ty, 1.0, pay - a0u * dy, qcy + a1u * dy, b10, b01, b00, bp.aby, kp.aby);
+                    build_table<LI, LJ, LK, LL>(Tz, wr * pref, paz - a0u * dz, qcz + a1u * dz, b10, b01, b00, bp.abz,
+                                                kp.abz);
+                    acc_all<S, P>(acc, Tx, Ty, Tz, std::make_integer_sequence<int, P::NACC>());
+                }
+            }
+        }
+        // ---- digestion (the sums of jk_kernel, in cartesian components; D symmetric, the caller adds the transpose) ----
+        double f = 1.0;
+        if (bp.ish == bp.jsh) f *= 0.5;
+        if (kp.ish == kp.jsh) f *= 0.5;
+        if (bp.ish == kp.ish && bp.jsh == kp.jsh) f *= 0.5;
+        const int ai = bp.ao_i, aj = bp.ao_j, ak = kp.ao_i, al = kp.ao_j;
+        if (DOJ) {
+            const double f2 = 2.0 * f;
+            {   // J_ij += 2f sum_kl B D_kl
+                double t[NKL];
+                load_tile<LK, LL>(D, ak, al, nao, A, t);
+#pragma unroll
+                for (int e = 0; e < NE; e++) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NKL; c++) v += acc[e * NKL + c] * t[c];
+                    jc[e] = f2 * v;
+                }
+            }
+            {   // J_kl += 2f sum_ij B D_ij
+                double t[NKL];
+#pragma unroll
+                for (int c = 0; c < NKL; c++) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int e = 0; e < NE; e++) v += acc[e * NKL + c] * wdij[E0 + e];
+                    t[c] = v;
+                }
+                add_tile<LK, LL, AllRows>(A.vj, ak, al, nao, A, t, f2);
+            }
+        }
+        if (DOK) {
+            {   // K_ik += f sum_jl B D_jl
+                double d[NJ * NL], t[NI * NK];
+                load_tile<LJ, LL>(D, aj, al, nao, A, d);
+#pragma unroll
+                for (int a = 0; a < NI; a++) {
+                    if (!P::RowsA::has(a)) continue;
+#pragma unroll
+                    for (int c = 0; c < NK; c++) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int b = 0; b < NJ; b++) {
+                            if (!P::has(a, b)) continue;
+#pragma unroll
+                            for (int dd = 0; dd < NL; dd++)
+                                v += acc[((a * NJ + b - E0) * NK + c) * NL + dd] * d[b * NL + dd];
+                        }
+                        t[a * NK + c] = v;
+                    }
+                }
+                add_tile<LI, LK, typename P::RowsA>(A.vk, ai, ak, nao, A, t, f);
+            }
+            {   // K_jk += f sum_il B D_il
+                double d[NI * NL], t[NJ * NK];
+                load_tile<LI, LL>(D, ai, al, nao, A, d);
+#pragma unroll
+                for (int b = 0; b < NJ; b++) {
+                    if (!P::RowsB::has(b)) continue;
+#pragma unroll
+                    for (int c = 0; c < NK; c++) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int a = 0; a < NI; a++) {
+                            if (!P::has(a, b)) continue;
+#pragma unroll
+                            for (int dd = 0; dd < NL; dd++)
+                                v += acc[((a * NJ + b - E0) * NK + c) * NL + dd] * d[a * NL + dd];
+                        }
+                        t[b * NK + c] = v;
+                    }
+                }
+                add_tile<LJ, LK, typename P::RowsB>(A.vk, aj, ak, nao, A, t, f);
+            }
+            {   // K_il += f sum_jk B D_jk
+                double d[NJ * NK], t[NI * NL];
+                load_tile<LJ, LK>(D, aj, ak, nao, A, d);
+#pragma unroll
+                for (int a = 0; a < NI; a++) {
+                    if (!P::RowsA::has(a)) continue;
+#pragma unroll
+                    for (int dd = 0; dd < NL; dd++) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int b = 0; b < NJ; b++) {
+                            if (!P::has(a, b)) continue;
+#pragma unroll
+                            for (int c = 0; c < NK; c++)
+                                v += acc[((a * NJ + b - E0) * NK + c) * NL + dd] * d[b * NK + c];
+                        }
+                        t[a * NL + dd] = v;
+                    }
+                }
+                add_tile<LI, LL, typename P::RowsA>(A.vk, ai, al, nao, A, t, f);
+            }
+            {   // K_jl += f sum_ik B D_ik
+                double d[NI * NK], t[NJ * NL];
+                load_tile<LI, LK>(D, ai, ak, nao, A, d);
+#pragma unroll
+                for (int b = 0; b < NJ; b++) {
+                    if (!P::RowsB::has(b)) continue;
+#pragma unroll
+                    for (int dd = 0; dd < NL; dd++) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int a = 0; a < NI; a++) {
+                            if (!P::has(a, b)) continue;
+#pragma unroll
+                            for (int c = 0; c < NK; c++)
+                                v += acc[((a * NJ + b - E0) * NK + c) * NL + dd] * d[a * NK + c];
+                        }
+                        t[b * NL + dd] = v;
+                    }
+                }
+                add_tile<LJ, LL, typename P::RowsB>(A.vk, aj, al, nao, A, t, f);
+            }
+        }
+    }
+    if (DOJ) {
+        // bra-tile J_ij: summed over the warp, kept (cartesian) in the warp's shared memory until the work item ends
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            double v = jc[e];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) wjij[E0 + e] += v;
+        }
+    }
+}
+
+template <int LI, int LJ, int LK, int LL, int NPASS, int P0, bool DOJ, bool DOK, int... Ps>
+__device__ __forceinline__ void quartet_passes(bool valid, const JKPair &bp, const JKPair &kp, const double *wprim,
+                                               const double *wdij, double *wjij, const double *__restrict__ rt,
+                                               const JKRArgs &A, double ih, int lane, std::integer_sequence<int, Ps...>) {
+    using S = Shape<LI, LJ, LK, LL>;
+    (quartet_pass<LI, LJ, LK, LL, Pass<S, (P0 + Ps) * S::NIJ / NPASS, (P0 + Ps + 1) * S::NIJ / NPASS>, DOJ, DOK>(
+         valid, bp, kp, wprim, wdij, wjij, rt, A, ih, lane), ...);
+}
+
+// c2s coefficient with run-time indices (staging code only): c2sd = the d matrix in shared memory
+__device__ __forceinline__ double c2s_rt(int l, int m, int c, const double *c2sd) {
+    return l <= 1 ? (m == c ? 1.0 : 0.0) : c2sd[m * 6 + c];
+}
+
+// passes [P0, P1) of the NPASS passes over the bra components (the many-pass classes are split over several kernels)
+template <int LI, int LJ, int LK, int LL, int NPASS, int P0, int P1, bool DOJ, bool DOK>
 __global__ void __launch_bounds__(JKR_THREADS) jk_reg_kernel(const JKRArgs A) {
     using S = Shape<LI, LJ, LK, LL>;
-    constexpr int NI = S::NI, NJ = S::NJ, NK = S::NK, NL = S::NL, NR = S::NR, NC = S::NC, NKL = S::NKL, NIJ = S::NIJ;
+    constexpr int NI = S::NI, NJ = S::NJ, NR = S::NR, NIJ = S::NIJ;
+    constexpr int NSI = Sph<LI>::n, NSJ = Sph<LJ>::n;
+    static_assert(NIJ % NPASS == 0, "passes must divide the bra components");
     extern __shared__ __align__(16) double jkr_smem[];
     double *rt = jkr_smem;
+    double *c2sd = jkr_smem + JKR_NCOEF * 2 * NR * JKR_NINT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *wprim = jkr_smem + JKR_NCOEF * 2 * NR * JKR_NINT + warp * JKR_WSM;
-    double *wdij = wprim + JKR_MAXPP * 6;
+    double *wprim = c2sd + 32 + warp * JKR_WSM;
+    double *wdij = wprim + JKR_MAXPP * 6;      // D_ij, cartesian
+    double *wjij = wdij + 36;                  // J_ij of the work item, cartesian
+    double *wsph = wjij + 36;                  // D_ij as stored (spherical AOs)
     for (int e = threadIdx.x; e < JKR_NINT * 2 * NR * JKR_NCOEF; e += JKR_THREADS) {
         const int it = e / (2 * NR * JKR_NCOEF), rem = e - it * (2 * NR * JKR_NCOEF);
         const int f = rem / JKR_NCOEF, k = rem - f * JKR_NCOEF;
         rt[(k * 2 * NR + f) * JKR_NINT + it] = A.rys_coef[e];
     }
+    if (threadIdx.x < 30) c2sd[threadIdx.x] = A.c2s_d[threadIdx.x];
     __syncthreads();
     const int nao = A.nao;
     const double ih = 1.0 / A.rys_h;
-    const double *__restrict__ D = A.dm;
     const int64_t wstride = (int64_t)gridDim.x * JKR_WARPS;
     for (int64_t slot = (int64_t)blockIdx.x * JKR_WARPS + warp;; slot += wstride) {
         const int64_t item = A.item0 + slot * A.item_stride;
@@ -189,175 +508,47 @@ __global__ void __launch_bounds__(JKR_THREADS) jk_reg_kernel(const JKRArgs A) {
         {
             const double *src = reinterpret_cast<const double *>(A.prims + bp.pp_off);
             for (int e = lane; e < bp.npp * 6; e += 32) wprim[e] = src[e];
-            for (int e = lane; e < NIJ; e += 32) wdij[e] = D[(int64_t)(bp.ao_i + e / NJ) * nao + bp.ao_j + e % NJ];
+            for (int e = lane; e < NSI * NSJ; e += 32)
+                wsph[e] = A.dm[(int64_t)(bp.ao_i + e / NSJ) * nao + bp.ao_j + e % NSJ];
         }
         __syncwarp();
-        const int ai = bp.ao_i, aj = bp.ao_j;
-        double jij[NIJ];
-#pragma unroll
-        for (int e = 0; e < NIJ; e++) jij[e] = 0.0;
+        for (int e = lane; e < NIJ; e += 32) {
+            const int ca = e / NJ, cb = e - ca * NJ;
+            double v = 0.0;
+            for (int ma = 0; ma < NSI; ma++)
+                for (int mb = 0; mb < NSJ; mb++)
+                    v += c2s_rt(LI, ma, ca, c2sd) * c2s_rt(LJ, mb, cb, c2sd) * wsph[ma * NSJ + mb];
+            wdij[e] = v;
+            wjij[e] = 0.0;
+        }
+        __syncwarp();
         for (int kk0 = k0; kk0 < k1; kk0 += 32) {
             const int kk = kk0 + lane;
-            if (kk < k1) {
-                const JKPair kp = A.ket[kk];
-                double acc[NC];
-#pragma unroll
-                for (int c = 0; c < NC; c++) acc[c] = 0.0;
-                const JKPrim *__restrict__ kpr = A.prims + kp.pp_off;
-                for (int pk = 0; pk < kp.npp; pk++) {
-                    const JKPrim kq = kpr[pk];
-                    const double qcx = kq.px - kp.ax, qcy = kq.py - kp.ay, qcz = kq.pz - kp.az;
-                    for (int pb = 0; pb < bp.npp; pb++) {
-                        const double p = wprim[pb * 6], hp = wprim[pb * 6 + 1];
-                        const double px = wprim[pb * 6 + 2], py = wprim[pb * 6 + 3], pz = wprim[pb * 6 + 4];
-                        const double pq = p + kq.p;
-                        const double rs = rsqrt(pq);
-                        const double ipq = rs * rs;
-                        const double dx = px - kq.px, dy = py - kq.py, dz = pz - kq.pz;
-                        const double x = p * kq.p * ipq * (dx * dx + dy * dy + dz * dz);
-                        const double pref = wprim[pb * 6 + 5] * kq.c * 34.98683665524972497 /* 2 pi^2.5 */ * rs;
-                        const double a0 = kq.p * ipq, a1 = p * ipq;
-                        double u[NR], w[NR];
-                        rys_roots<NR>(x, rt, A, ih, u, w);
-                        const double pax = px - bp.ax, pay = py - bp.ay, paz = pz - bp.az;
-#pragma unroll
-                        for (int r = 0; r < NR; r++) {
-                            const double a0u = a0 * u[r], a1u = a1 * u[r];
-                            const double b10 = (1.0 - a0u) * hp, b01 = (1.0 - a1u) * kq.hp, b00 = 0.5 * u[r] * ipq;
-                            double Tx[S::TS], Ty[S::TS], Tz[S::TS];
-                            build_table<LI, LJ, LK, LL>(Tx, 1.0, pax - a0u * dx, qcx + a1u * dx, b10, b01, b00, bp.abx,
-                                                        kp.abx);
-                            build_table<LI, LJ, LK, LL>(Ty, 1.0, pay - a0u * dy, qcy + a1u * dy, b10, b01, b00, bp.aby,
-                                                        kp.aby);
-                            build_table<LI, LJ, LK, LL>(Tz, w[r] * pref, paz - a0u * dz, qcz + a1u * dz, b10, b01, b00,
-                                                        bp.abz, kp.abz);
-                            acc_all<S>(acc, Tx, Ty, Tz, std::make_integer_sequence<int, NC>());
-                        }
-                    }
-                }
-                // ---- digestion (same sums as jk_kernel; D symmetric, the caller adds the transpose at the end) ----
-                double f = 1.0;
-                if (bp.ish == bp.jsh) f *= 0.5;
-                if (kp.ish == kp.jsh) f *= 0.5;
-                if (bp.ish == kp.ish && bp.jsh == kp.jsh) f *= 0.5;
-                const int ak = kp.ao_i, al = kp.ao_j;
-                if (DOJ) {
-                    double *__restrict__ J = A.vj;
-                    double t[NKL];
-#pragma unroll
-                    for (int c = 0; c < NKL; c++) t[c] = D[(int64_t)(ak + c / NL) * nao + al + c % NL];
-                    const double f2 = 2.0 * f;
-#pragma unroll
-                    for (int e = 0; e < NIJ; e++) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int c = 0; c < NKL; c++) v += acc[e * NKL + c] * t[c];
-                        jij[e] += f2 * v;
-                    }
-#pragma unroll
-                    for (int c = 0; c < NKL; c++) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int e = 0; e < NIJ; e++) v += acc[e * NKL + c] * wdij[e];
-                        atomicAdd(J + (int64_t)(ak + c / NL) * nao + al + c % NL, f2 * v);
-                    }
-                }
-                if (DOK) {
-                    double *__restrict__ Kx = A.vk;
-                    {   // K_ik += f sum_jl B D_jl
-                        double t[NJ * NL];
-#pragma unroll
-                        for (int e = 0; e < NJ * NL; e++) t[e] = D[(int64_t)(aj + e / NL) * nao + al + e % NL];
-#pragma unroll
-                        for (int a = 0; a < NI; a++) {
-#pragma unroll
-                            for (int c = 0; c < NK; c++) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int b = 0; b < NJ; b++) {
-#pragma unroll
-                                    for (int d = 0; d < NL; d++) v += acc[((a * NJ + b) * NK + c) * NL + d] * t[b * NL + d];
-                                }
-                                atomicAdd(Kx + (int64_t)(ai + a) * nao + ak + c, f * v);
-                            }
-                        }
-                    }
-                    {   // K_jk += f sum_il B D_il
-                        double t[NI * NL];
-#pragma unroll
-                        for (int e = 0; e < NI * NL; e++) t[e] = D[(int64_t)(ai + e / NL) * nao + al + e % NL];
-#pragma unroll
-                        for (int b = 0; b < NJ; b++) {
-#pragma unroll
-                            for (int c = 0; c < NK; c++) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int a = 0; a < NI; a++) {
-#pragma unroll
-                                    for (int d = 0; d < NL; d++) v += acc[((a * NJ + b) * NK + c) * NL + d] * t[a * NL + d];
-                                }
-                                atomicAdd(Kx + (int64_t)(aj + b) * nao + ak + c, f * v);
-                            }
-                        }
-                    }
-                    {   // K_il += f sum_jk B D_jk
-                        double t[NJ * NK];
-#pragma unroll
-                        for (int e = 0; e < NJ * NK; e++) t[e] = D[(int64_t)(aj + e / NK) * nao + ak + e % NK];
-#pragma unroll
-                        for (int a = 0; a < NI; a++) {
-#pragma unroll
-                            for (int d = 0; d < NL; d++) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int b = 0; b < NJ; b++) {
-#pragma unroll
-                                    for (int c = 0; c < NK; c++) v += acc[((a * NJ + b) * NK + c) * NL + d] * t[b * NK + c];
-                                }
-                                atomicAdd(Kx + (int64_t)(ai + a) * nao + al + d, f * v);
-                            }
-                        }
-                    }
-                    {   // K_jl += f sum_ik B D_ik
-                        double t[NI * NK];
-#pragma unroll
-                        for (int e = 0; e < NI * NK; e++) t[e] = D[(int64_t)(ai + e / NK) * nao + ak + e % NK];
-#pragma unroll
-                        for (int b = 0; b < NJ; b++) {
-#pragma unroll
-                            for (int d = 0; d < NL; d++) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int a = 0; a < NI; a++) {
-#pragma unroll
-                                    for (int c = 0; c < NK; c++) v += acc[((a * NJ + b) * NK + c) * NL + d] * t[a * NK + c];
-                                }
-                                atomicAdd(Kx + (int64_t)(aj + b) * nao + al + d, f * v);
-                            }
-                        }
-                    }
-                }
-            }
+            const bool valid = kk < k1;
+            const JKPair kp = A.ket[valid ? kk : k0];
+            quartet_passes<LI, LJ, LK, LL, NPASS, P0, DOJ, DOK>(valid, bp, kp, wprim, wdij, wjij, rt, A, ih, lane,
+                                                                std::make_integer_sequence<int, P1 - P0>());
         }
         if (DOJ) {
-            // J_ij of the bra tile: one sum over the warp, one atomic per element per work item
-#pragma unroll
-            for (int e = 0; e < NIJ; e++) {
-                double v = jij[e];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == (e & 31)) atomicAdd(A.vj + (int64_t)(ai + e / NJ) * nao + aj + e % NJ, v);
+            __syncwarp();
+            for (int e = lane; e < NSI * NSJ; e += 32) {
+                const int ma = e / NSJ, mb = e - ma * NSJ;
+                double v = 0.0;
+                for (int ca = 0; ca < NI; ca++)
+                    for (int cb = 0; cb < NJ; cb++)
+                        v += c2s_rt(LI, ma, ca, c2sd) * c2s_rt(LJ, mb, cb, c2sd) * wjij[ca * NJ + cb];
+                atomicAdd(A.vj + (int64_t)(bp.ao_i + ma) * nao + bp.ao_j + mb, v);
             }
         }
     }
 }
 
-template <int LI, int LJ, int LK, int LL, bool DOJ, bool DOK>
+template <int LI, int LJ, int LK, int LL, int NPASS, int P0, int P1, bool DOJ, bool DOK>
 static int launch_t(const JKRArgs &A, cudaStream_t st) {
     using S = Shape<LI, LJ, LK, LL>;
-    static_assert(S::NR <= JKR_MAXROOTS && S::NIJ <= 40, "class outside the staged sizes");
-    const size_t smem = sizeof(double) * ((size_t)JKR_NCOEF * 2 * S::NR * JKR_NINT + (size_t)JKR_WARPS * JKR_WSM);
-    auto kern = jk_reg_kernel<LI, LJ, LK, LL, DOJ, DOK>;
+    static_assert(S::NR <= JKR_MAXROOTS && S::NIJ <= 36, "class outside the staged sizes");
+    const size_t smem = sizeof(double) * ((size_t)JKR_NCOEF * 2 * S::NR * JKR_NINT + 32 + (size_t)JKR_WARPS * JKR_WSM);
+    auto kern = jk_reg_kernel<LI, LJ, LK, LL, NPASS, P0, P1, DOJ, DOK>;
     QC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     QC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JKR_THREADS, smem));
@@ -372,32 +563,10 @@ static int launch_t(const JKRArgs &A, cudaStream_t st) {
     return 0;
 }
 
-template <int LI, int LJ, int LK, int LL>
-static int launch_mode(const JKRArgs &A, cudaStream_t st) {
-    if (A.vj && A.vk) return launch_t<LI, LJ, LK, LL, true, true>(A, st);
-    if (A.vj) return launch_t<LI, LJ, LK, LL, true, false>(A, st);
-    if (A.vk) return launch_t<LI, LJ, LK, LL, false, true>(A, st);
-    return 0;
-}
-
 }  // namespace jkr
 
-// classes the engine is instantiated for: li >= lj, lk >= ll, (li, lj) >= (lk, ll), all l <= 1
-#define JKR_CLASSES(X) X(0, 0, 0, 0) X(1, 0, 0, 0) X(1, 0, 1, 0) X(1, 1, 0, 0) X(1, 1, 1, 0) X(1, 1, 1, 1)
-
-int jkr_supported(const int l[4]) {
-#define JKR_X(a, b, c, d) if (l[0] == a && l[1] == b && l[2] == c && l[3] == d) return 1;
-    JKR_CLASSES(JKR_X)
-#undef JKR_X
-    return 0;
-}
-
-int jkr_launch(const JKRArgs &A, cudaStream_t st) {
-    QC_REQUIRE(A.rys_nint == JKR_NINT && A.rys_deg + 1 == JKR_NCOEF, "Rys table shape differs from the compiled one");
-#define JKR_X(a, b, c, d) \
-    if (A.l[0] == a && A.l[1] == b && A.l[2] == c && A.l[3] == d) return jkr::launch_mode<a, b, c, d>(A, st);
-    JKR_CLASSES(JKR_X)
-#undef JKR_X
-    b200qc_set_error("jkr_launch: class not instantiated");
-    return 2;
-}
+// Class table, entry definitions per translation unit and the dispatcher: generated by tools/gen_jk_units.py
+#ifndef JKR_UNIT
+#define JKR_UNIT 0
+#endif
+#include "jk_reg_units.inc"

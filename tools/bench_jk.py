@@ -24,7 +24,8 @@ def timed(fn, reps):
 
 
 for spec in (sys.argv[1:] or ["taxol_like:3-21g"]):
-    name, basis = spec.split(":")
+    name, basis = spec.split(":")[:2]
+    with_shared = not spec.endswith(":noshared")
     zs, pos = systems.carbon_cluster(int(name[14:])) if name.startswith("carbon_cluster") else getattr(systems, name)()
     w, _ = util.make_wrapper(zs, pos.tolist(), basis)
     nb, nao = len(w), w.nao()
@@ -33,6 +34,8 @@ for spec in (sys.argv[1:] or ["taxol_like:3-21g"]):
     res = {"system": name, "basis": basis, "nao": nao, "nshell": nb}
     out = {}
     for label, env in (("register", None), ("shared", "1")):
+        if label == "shared" and not with_shared:
+            continue
         if env is None:
             os.environ.pop("B200QC_JK_NOREG", None)
         else:
@@ -53,7 +56,8 @@ for spec in (sys.argv[1:] or ["taxol_like:3-21g"]):
             if mode == "jk":
                 out[label] = o
         del plan
-    res["max_abs_diff_J"] = float((out["register"][0] - out["shared"][0]).abs().max())
-    res["max_abs_diff_K"] = float((out["register"][1] - out["shared"][1]).abs().max())
-    res["max_abs_J"] = float(out["shared"][0].abs().max())
+    if with_shared:
+      res["max_abs_diff_J"] = float((out["register"][0] - out["shared"][0]).abs().max())
+      res["max_abs_diff_K"] = float((out["register"][1] - out["shared"][1]).abs().max())
+    res["max_abs_J"] = float(out["register"][0].abs().max())
     print(json.dumps(res))
