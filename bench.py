@@ -570,9 +570,22 @@ def main():
     elif dominant == "gemm_i8_kernel":
         roofline = dfk_roofline()
     elif dominant == "jk_kernel":
-        roofline = {"kernel": dominant, "bound": "fp64-alu", "achieved": h._jkplan.nquartets / (
-            sum(ms for k, (c, ms) in prof.items() if k == "jk_kernel") / args.steps * 1e-3), "peak": None,
-            "unit": "contracted shell quartets/s", "frac": None, "traffic": None}
+        # direct 4-centre J/K (csrc/jk_reg.cuh): fp64-pipe bound.  achieved = the plan's operation count (Rys roots,
+        # 2-D tables and root sums once per primitive quartet + the tile contractions, b200qc_jkplan_flops) over the
+        # summed launch time of the class kernels; peak = the DFMA issue rate measured in this process.
+        jk_ms = sum(ms for k, (c, ms) in prof.items() if k == "jk_kernel") / args.steps
+        hybrid = exx != 0.0
+        fl = h._jkplan.flops(True, hybrid)
+        fma_peak = _lib.peak_fp64_fma(20000)
+        ach = fl / (jk_ms * 1e-3) / 1e12
+        roofline = {"kernel": dominant, "bound": "fp64-alu", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s",
+                    "frac": ach / fma_peak, "traffic": traffic.get(dominant),
+                    "peak_source": "DFMA issue-rate peak measured in this process (b200qc_peak_fp64_fma); "
+                                   "MEASURED_PEAKS.json has no fp64 entry",
+                    "algorithmic_flops_per_build": fl,
+                    "contracted_shell_quartets_per_s": h._jkplan.nquartets / (jk_ms * 1e-3),
+                    "quartets": h._jkplan.nquartets, "quartets_register_engine": h._jkplan.nquartets_reg,
+                    "launches_per_build": prof["jk_kernel"][0] / args.steps}
     # secondary rooflines (HBM-bound kernels) for context
     extra = {}
     if "dfj_pass1_kernel" in kern and h.df is not None and h.df._j3c_packed is not None:

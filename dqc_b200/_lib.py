@@ -34,6 +34,7 @@ _SIGS = {
     "b200qc_profile_name": (ctypes.c_char_p, [ctypes.c_int]),
     "b200qc_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_peak_fp64_dmma": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_peak_fp64_fma": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_peak_i8_mma": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_basis_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
@@ -119,6 +120,7 @@ _SIGS = {
                                             ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_jkplan_nquartets": (ctypes.c_int64, [ctypes.c_void_p]),
     "b200qc_jkplan_nquartets_reg": (ctypes.c_int64, [ctypes.c_void_p]),
+    "b200qc_jkplan_flops": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "b200qc_jkplan_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200qc_jkplan_free": (ctypes.c_int, [ctypes.c_void_p]),
@@ -227,6 +229,15 @@ def peak_fp64_dmma(iters: int = 20000) -> float:
     scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
     out = ctypes.c_double(0.0)
     _check(lib.b200qc_peak_fp64_dmma(iters, _ptr(scratch), ctypes.byref(out), _stream()), "peak_fp64_dmma")
+    return float(out.value)
+
+
+def peak_fp64_fma(iters: int = 20000) -> float:
+    """Measured plain fp64 pipe (DFMA) peak (TFLOP/s) of the current device."""
+    lib = load()
+    scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
+    out = ctypes.c_double(0.0)
+    _check(lib.b200qc_peak_fp64_fma(iters, _ptr(scratch), ctypes.byref(out), _stream()), "peak_fp64_fma")
     return float(out.value)
 
 
@@ -533,6 +544,10 @@ class JKPlan(object):
         self.handle = h
         self.nquartets = int(lib.b200qc_jkplan_nquartets(h))
         self.nquartets_reg = int(lib.b200qc_jkplan_nquartets_reg(h))   # on the register-resident engine (l <= 1 classes)
+
+    def flops(self, with_j=True, with_k=True) -> float:
+        """fp64 operations of one build of one density (integrals once per quartet + digestion)."""
+        return float(load().b200qc_jkplan_flops(self.handle, int(with_j), int(with_k)))
 
     def run(self, dm: torch.Tensor, with_j=True, with_k=True, rank=0, world=1):
         """dm (nset, nao, nao) symmetric -> vj, vk (nset, nao, nao); partial sums when world > 1."""

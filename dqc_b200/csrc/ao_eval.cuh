@@ -26,6 +26,9 @@ __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const doubl
     double rad = 0.0, drad = 0.0, d2rad = 0.0;
     for (int p = 0; p < sh.nprim; p++) {
         const double a = env[sh.ptr_exp + p];
+        // a primitive below e^-50 = 2e-22 on all 32 points of the warp is skipped (tight core functions away from their
+        // nucleus: most of the exps of a contracted s shell); the branch is warp-uniform
+        if (!__any_sync(0xffffffffu, a * r2 < 50.0)) continue;
         const double e = env[sh.ptr_coef + p] * exp(-a * r2);
         rad += e;
         if (DERIV) drad -= 2.0 * a * e;

@@ -40,7 +40,24 @@ struct b200qc_jkplan {
     JKPrim *d_prims = nullptr;           // primitive-pair data, pp_off of a pair points in here
     std::vector<JKClassPair> cps;
     int64_t nquartets = 0, nquartets_reg = 0;
+    double flops_int = 0.0;              // integral evaluation (roots, 2-D tables, sum over roots), one pass per quartet
+    double ncomp_total = 0.0;            // sum over quartets of the cartesian block size (digestion: 2 flops per use)
 };
+
+// fp64 operations of ONE primitive quartet of a class as the Rys scheme needs them (each class evaluated in one pass):
+// 2 nr Clenshaw sums of the root table, per (root, xyz) the vertical recurrence and both horizontal transfers, then
+// nr (2 mul + 1 add) per cartesian component.  The roofline numerator of the J/K kernels (bench.py).
+static double jk_prim_flops(const int l[4]) {
+    const int nr = (l[0] + l[1] + l[2] + l[3]) / 2 + 1;
+    const int nij = l[0] + l[1] + 1, nkl = l[2] + l[3] + 1;
+    double tab = 0.0;
+    tab += 3.0 * (nij - 1);                              // n recurrence at m = 0
+    tab += 5.0 * nij * (nkl - 1);                        // m recurrence
+    for (int j = 1; j <= l[1]; j++) tab += 2.0 * (nij - j) * nkl;
+    for (int ll = 1; ll <= l[3]; ll++) tab += 2.0 * (nkl - ll) * (l[0] + 1) * (l[1] + 1);
+    const double ncomp = (double)NCART(l[0]) * NCART(l[1]) * NCART(l[2]) * NCART(l[3]);
+    return 40.0 + 2.0 * nr * (2.0 * 13 + 2) + nr * (3.0 * tab + 12.0) + 3.0 * nr * ncomp;
+}
 
 // Primitive pairs whose Gaussian-product factor exp(-a_i a_j |AB|^2 / (a_i + a_j)) is below e^-50 = 2e-22 are left out
 // of the register engine's pair data (the shared-memory engine skips primitive quartets beyond e^-80).
@@ -418,6 +435,14 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
             }
             plan->nquartets += nq;
             if (cp.reg) plan->nquartets_reg += nq;
+            {   // operation counts: sum_b npp_b * (sum of npp over its admissible kets)
+                std::vector<double> pre(cp.nket + 1, 0.0);
+                for (int k = 0; k < cp.nket; k++) pre[k + 1] = pre[k] + jkpairs[cp.ket_off + k].npp;
+                double nprimq = 0.0;
+                for (int b = 0; b < cp.nbra; b++) nprimq += (double)jkpairs[cp.bra_off + b].npp * pre[nkb[b]];
+                plan->flops_int += nprimq * jk_prim_flops(l);
+                plan->ncomp_total += (double)nq * NCART(l[0]) * NCART(l[1]) * NCART(l[2]) * NCART(l[3]);
+            }
             cp.nitems = woff[cp.nbra];
             if (cp.nitems == 0) continue;
             QC_CHECK(cudaMalloc(&cp.d_nket_of_bra, sizeof(int) * nkb.size()));
@@ -436,6 +461,10 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
 }
 
 extern "C" int64_t b200qc_jkplan_nquartets(const b200qc_jkplan *p) { return p ? p->nquartets : 0; }
+// fp64 operations of one build (integrals once per quartet + digestion: 2 tile contractions for J, 4 for K)
+extern "C" double b200qc_jkplan_flops(const b200qc_jkplan *p, int with_j, int with_k) {
+    return p ? p->flops_int + 2.0 * p->ncomp_total * (2.0 * (with_j != 0) + 4.0 * (with_k != 0)) : 0.0;
+}
 // quartets that go through the register-resident engine (jk_reg.cuh); the rest use the shared-memory engine
 extern "C" int64_t b200qc_jkplan_nquartets_reg(const b200qc_jkplan *p) { return p ? p->nquartets_reg : 0; }
 

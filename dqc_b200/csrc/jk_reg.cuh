@@ -565,6 +565,44 @@ static int launch_t(const JKRArgs &A, cudaStream_t st) {
 
 }  // namespace jkr
 
+#if !defined(JKR_UNIT) || JKR_UNIT == 0
+// Measured issue-rate peak of the plain fp64 pipe (DFMA, 8 independent chains per thread): the roofline denominator of
+// the J/K quartet kernels (MEASURED_PEAKS.json has no fp64 entry).
+__global__ void __launch_bounds__(256, 2) dfma_peak_kernel(int iters, double *out) {
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = 1e-3 * (threadIdx.x + i);
+    const double a = 1.0 - 1e-9 * threadIdx.x, b = 1e-9 * (threadIdx.x + 1);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i];
+    if (s == 123.456) out[0] = s;   // keeps the loop alive
+}
+extern "C" int b200qc_peak_fp64_fma(int iters, double *scratch, double *tflops, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    const int nblk = NUM_SMS * 8;
+    cudaEvent_t e0, e1;
+    QC_CHECK(cudaEventCreate(&e0));
+    QC_CHECK(cudaEventCreate(&e1));
+    dfma_peak_kernel<<<nblk, 256, 0, st>>>(iters / 8 + 1, scratch);   // warm-up
+    QC_CHECK(cudaEventRecord(e0, st));
+    dfma_peak_kernel<<<nblk, 256, 0, st>>>(iters, scratch);
+    QC_CHECK(cudaEventRecord(e1, st));
+    QC_LAUNCHED(2);
+    QC_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    QC_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *tflops = 2.0 * 8.0 * iters * 256.0 * nblk / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+#endif
+
 // Class table, entry definitions per translation unit and the dispatcher: generated by tools/gen_jk_units.py
 #ifndef JKR_UNIT
 #define JKR_UNIT 0

@@ -72,8 +72,10 @@ extern "C" int b200qc_ao_screen(const b200qc_basis *basis, int sh0, int sh1, con
 }
 
 // ---- compact AO evaluation: same per-shell arithmetic as ao_eval.cuh, columns = kept shells of the SB ----
-template <int DERIV>
-__global__ void __launch_bounds__(AO_THREADS)
+// LMAX = highest angular momentum of the basis (2: s, p, d only -- the f / g code paths of LMAX = 4 cost 228 registers per
+// thread, one CTA per SM; without them two to three CTAs fit)
+template <int DERIV, int LMAX>
+__global__ void __launch_bounds__(AO_THREADS, LMAX <= 2 ? 2 : 1)
 ao_eval_sb_kernel(const ShellRec *__restrict__ shells, const double *__restrict__ env, const SBDesc *__restrict__ sbd,
                   const int *__restrict__ shell_ids, const int *__restrict__ shell_col,
                   const double *__restrict__ coords, int64_t ngrid, int sbp, double *__restrict__ ao) {
@@ -102,12 +104,20 @@ ao_eval_sb_kernel(const ShellRec *__restrict__ shells, const double *__restrict_
             const ShellRec sh = shells[ids[s]];
             const double x = gx - sh.x, y = gy - sh.y, z = gz - sh.z;
             const int col0 = cols[s] - c0;
-            switch (sh.l) {
-                case 0: ao_shell_to_tile<0, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
-                case 1: ao_shell_to_tile<1, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
-                case 2: ao_shell_to_tile<2, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
-                case 3: ao_shell_to_tile<3, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
-                default: ao_shell_to_tile<4, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+            if (LMAX <= 2) {
+                switch (sh.l) {
+                    case 0: ao_shell_to_tile<0, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                    case 1: ao_shell_to_tile<1, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                    default: ao_shell_to_tile<2, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                }
+            } else {
+                switch (sh.l) {
+                    case 0: ao_shell_to_tile<0, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                    case 1: ao_shell_to_tile<1, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                    case 2: ao_shell_to_tile<2, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                    case 3: ao_shell_to_tile<3, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                    default: ao_shell_to_tile<4, DERIV>(sh, env, x, y, z, col0, lane, tile); break;
+                }
             }
         }
         __syncthreads();
@@ -142,19 +152,23 @@ extern "C" int b200qc_eval_gto_sb(const b200qc_basis *basis, int deriv, const do
     const size_t smem = sizeof(double) * AO_NCOMP(deriv) * AO_WIN * 33;
     const unsigned nblk = (unsigned)nsb * (unsigned)(sbp / AO_PTS);
     cudaStream_t st = as_stream(stream);
+    int lmax = 0;
+    for (const ShellRec &sh : basis->h_shells) lmax = std::max(lmax, sh.l);
     prof_begin(PROF_AO_EVAL, st);
-    if (deriv == 2) {
-        QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ao_eval_sb_kernel<2><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
-                                                            shell_ids, shell_col, coords, ngrid, sbp, ao);
-    } else if (deriv == 1) {
-        QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ao_eval_sb_kernel<1><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
-                                                            shell_ids, shell_col, coords, ngrid, sbp, ao);
+#define AO_SB_LAUNCH(DERIV, LMAX)                                                                                        \
+    do {                                                                                                                 \
+        QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<DERIV, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)smem));                                                                       \
+        ao_eval_sb_kernel<DERIV, LMAX><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env,                    \
+                                                                      (const SBDesc *)sbdesc, shell_ids, shell_col,      \
+                                                                      coords, ngrid, sbp, ao);                           \
+    } while (0)
+    if (lmax <= 2) {
+        if (deriv == 2) AO_SB_LAUNCH(2, 2); else if (deriv == 1) AO_SB_LAUNCH(1, 2); else AO_SB_LAUNCH(0, 2);
     } else {
-        ao_eval_sb_kernel<0><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env, (const SBDesc *)sbdesc,
-                                                            shell_ids, shell_col, coords, ngrid, sbp, ao);
+        if (deriv == 2) AO_SB_LAUNCH(2, 4); else if (deriv == 1) AO_SB_LAUNCH(1, 4); else AO_SB_LAUNCH(0, 4);
     }
+#undef AO_SB_LAUNCH
     prof_end(st);
     QC_LAUNCHED(1);
     return 0;

@@ -408,11 +408,16 @@ class HamiltonCGTO(BaseHamilton):
                     parts.append(self._dfk_ao_partial(dmtot))
         else:
             dmao = self._orthozer.unconvert_dm(_symm(dmtot)).unsqueeze(0)
-            vj, _ = self._jk_ao_partial(dmao.contiguous(), True, False)
-            parts.append(vj[0])
-            if exx != 0.0:
+            if exx != 0.0 and not polarized:
+                # restricted hybrid: J and K'[D] = -1/2 K[D] from ONE pass over the shell quartets (hcgto.py:238-241)
+                vj, vk = self._jk_ao_partial(dmao.contiguous(), True, True)
+                parts.extend([vj[0], vk[0]])
+            else:
+                vj, _ = self._jk_ao_partial(dmao.contiguous(), True, False)
+                parts.append(vj[0])
+            if exx != 0.0 and polarized:
                 # K'[D] = -1/2 K[D] restricted; per spin -1/2 K[2 D_s] (hcgto.py:238-241)
-                ds = torch.stack([2 * dm.u, 2 * dm.d]) if polarized else dmtot.unsqueeze(0)
+                ds = torch.stack([2 * dm.u, 2 * dm.d])
                 _, vk = self._jk_ao_partial(self._orthozer.unconvert_dm(_symm(ds)).contiguous(), False, True)
                 parts.extend(list(vk))
         nk = len(parts) - 1

@@ -37,6 +37,8 @@ int b200qc_profile_read(double *h_ms_total, int64_t *h_counts);
 /* measured fp64 tensor-pipe (DMMA m8n8k4) peak of this device in TFLOP/s: the roofline
  * denominator of K2 / K4 (MEASURED_PEAKS.json has no fp64 entry).  scratch: >= 1 double (device) */
 int b200qc_peak_fp64_dmma(int iters, double *scratch, double *h_tflops, void *stream);
+/* measured plain fp64 pipe (DFMA) peak of this device in TFLOP/s: the roofline denominator of the J/K quartet kernels */
+int b200qc_peak_fp64_fma(int iters, double *scratch, double *h_tflops, void *stream);
 /* measured tcgen05.mma.kind::i8 issue-rate peak of this device in TOP/s (2 ops per multiply-add; one CTA per SM,
  * M = 128, N = 256, K = 32 MMAs on resident shared-memory operands): the denominator of the int8 (sliced fp64)
  * tensor rooflines -- bench.py measures it in-process instead of assuming 2 x the bf16 figure. */
@@ -258,6 +260,9 @@ int64_t b200qc_jkplan_nquartets(const b200qc_jkplan *plan);
 /* of those, the quartets of classes with l <= 1 on every shell: they run on the register-resident engine (one lane =
  * one contracted quartet, a warp = one bra pair x 128 kets; csrc/jk_reg.cuh), the others on the shared-memory engine */
 int64_t b200qc_jkplan_nquartets_reg(const b200qc_jkplan *plan);
+/* fp64 operations one build needs (Rys roots, 2-D recurrence tables and the sum over roots once per primitive quartet,
+ * plus 2 flops per integral and tile contraction: 2 contractions for J, 4 for K): roofline numerator of the J/K kernels */
+double b200qc_jkplan_flops(const b200qc_jkplan *plan, int with_j, int with_k);
 int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, int nset, double *vj, double *vk, int rank,
                       int world, void *stream);
 int b200qc_jkplan_free(b200qc_jkplan *plan);

@@ -238,7 +238,9 @@ def test_superblock_path_matches_dense_kernels(cuda, eps, sbp, gga):
     ao = _lib.eval_gto(db, 0, nb, xyz, 1 if gga else 0)
     tol = 1e-13 if eps == 0.0 else 200 * eps
     dense = gb.dense_ao()
-    assert float((dense - ao[:, :ng, :nao]).abs().max()) <= (0.0 if eps == 0.0 else 2 * eps * 10)
+    # eps = 0: the same per-shell arithmetic in two kernels that are compiled with different register budgets (the
+    # compiler's FMA contraction may differ): agreement to the last bits, not bitwise
+    assert float((dense - ao[:, :ng, :nao]).abs().max()) <= (1e-14 if eps == 0.0 else 2 * eps * 10)
     dm = util.seeded_dm(nao, nao // 3, seed=4).to(cuda)
     rho_d, grad_d = _lib.rho(ao, _pad_dm(dm, ao.shape[2], cuda), gga)
     rho_s, grad_s = gb.rho(dm, gga)
