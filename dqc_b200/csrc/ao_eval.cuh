@@ -16,10 +16,22 @@
 #define AO_THREADS 256
 #define AO_NCOMP(DERIV) ((DERIV) == 0 ? 1 : ((DERIV) == 1 ? 4 : 5))
 
-template <int L, int DERIV>
+// non-zero pattern of the cart -> real-spherical matrices of s, p and d shells (tables.cuh: p is the identity up to a
+// constant; d rows xy, yz, z^2, xz, x^2 - y^2 over xx xy xz yy yz zz): the structural zeros are not multiplied
+template <int L> __host__ __device__ constexpr bool ao_c2s_nz(int m, int c) {
+    return L == 0 ? true
+         : L == 1 ? m == c
+         : L == 2 ? (m == 0 ? c == 1 : m == 1 ? c == 4 : m == 2 ? (c == 0 || c == 3 || c == 5) : m == 3 ? c == 2 : (c == 0 || c == 3))
+                  : true;
+}
+
+#define AO_TS 66   // row stride (doubles) of the point-major tile: 16-byte aligned rows for 128-bit reads along the AO axis
+
+// PM = false: tile[comp][col][33] (column-major, conflict-free both ways); PM = true: tile[comp][point][AO_TS]
+template <int L, int DERIV, bool PM = false>
 __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const double *__restrict__ env,
                                                  double x, double y, double z, int col0, int lane,
-                                                 double *tile /* [ncomp][AO_WIN][33] */) {
+                                                 double *tile) {
     constexpr int NC = NCART(L), NS = 2 * L + 1;
     const double r2 = x * x + y * y + z * z;
     // rad = sum c e^(-a r^2);  grad rad = r drad, drad = sum -2 a c e^(-a r^2);  lapl rad = d2rad = sum (4 a^2 r^2 - 6 a) c e^(-a r^2)
@@ -79,8 +91,9 @@ __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const doubl
         for (int comp = 0; comp < AO_NCOMP(DERIV); comp++) {
             double s = 0.0;
 #pragma unroll
-            for (int c = 0; c < NC; c++) s += M[m * NC + c] * cv[comp][c];
-            tile[(comp * AO_WIN + col) * 33 + lane] = s;
+            for (int c = 0; c < NC; c++)
+                if (ao_c2s_nz<L>(m, c)) s += M[m * NC + c] * cv[comp][c];
+            tile[PM ? (comp * AO_PTS + lane) * AO_TS + col : (comp * AO_WIN + col) * 33 + lane] = s;
         }
     }
 }

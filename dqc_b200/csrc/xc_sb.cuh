@@ -13,6 +13,7 @@
 // eps bounds the dropped |phi| (and |grad phi|): the results differ from the dense ones by O(eps),
 // i.e. ~1e-11 at the default 1e-12 -- five orders below the 1e-6 parity bar.  eps = 0 keeps everything.
 #pragma once
+#include <cstdlib>
 #include "gemm_f64.cuh"
 #include "sb_common.cuh"
 
@@ -142,6 +143,135 @@ ao_eval_sb_kernel(const ShellRec *__restrict__ shells, const double *__restrict_
     }
 }
 
+// ---- K1, staged form (default) ----
+// A CTA owns AO_CH consecutive 32-point chunks of one superblock.  It first stages the superblock's kept-shell list in
+// shared memory -- centre, l, first compact column and the primitive exponents / coefficients (offsets by a CTA-wide
+// prefix sum) -- so that the evaluation loop has no dependent global loads (the first form walked ids -> shell record
+// -> env for every (warp, shell): 12 % warp occupancy at 228 registers, long-scoreboard bound, 0.14 of the HBM write
+// rate).  Per 64-column window the eight warps split the shells (lane = point), park the values in a POINT-major tile
+// and the CTA streams it out with 128-bit loads / stores: one 512-byte row segment per warp instruction.
+#define AO_CH 4
+struct AOStage {
+    double x, y, z;
+    int l, nprim, col, poff;
+};
+
+template <int DERIV, int LMAX>
+__global__ void __launch_bounds__(AO_THREADS, LMAX <= 2 ? 2 : 1)
+ao_eval_sb2_kernel(const ShellRec *__restrict__ shells, const double *__restrict__ env, const SBDesc *__restrict__ sbd,
+                   const int *__restrict__ shell_ids, const int *__restrict__ shell_col,
+                   const double *__restrict__ coords, int64_t ngrid, int sbp, double *__restrict__ ao, int max_shell,
+                   int max_prim) {
+    extern __shared__ __align__(16) double tile[];
+    constexpr int NCOMP = AO_NCOMP(DERIV);
+    __shared__ int wsum[AO_THREADS / 32];
+    AOStage *stg = reinterpret_cast<AOStage *>(tile + NCOMP * AO_PTS * AO_TS);
+    double *pdat = reinterpret_cast<double *>(stg + max_shell);   // [exponents: max_prim][coefficients: max_prim]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int groups = sbp / (AO_PTS * AO_CH);
+    const int sb = blockIdx.x / groups, grp = blockIdx.x % groups;
+    if ((int64_t)sb * sbp + (int64_t)grp * AO_CH * AO_PTS >= ngrid) return;
+    const SBDesc d = sbd[sb];
+    const int *ids = shell_ids + d.shell_off;
+    const int *cols = shell_col + d.shell_off;   // compact first column of each kept shell
+    // ---- stage the kept shells ----
+    int run = 0;
+    for (int base = 0; base < d.nshell; base += AO_THREADS) {
+        const int s = base + threadIdx.x;
+        ShellRec sh = {};
+        int np = 0;
+        if (s < d.nshell) {
+            sh = shells[ids[s]];
+            np = sh.nprim;
+        }
+        int inc = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < AO_THREADS / 32; w2++) {
+            if (w2 < warp) woff += wsum[w2];
+            tot += wsum[w2];
+        }
+        if (s < d.nshell) {
+            AOStage a;
+            a.x = sh.x; a.y = sh.y; a.z = sh.z;
+            a.l = sh.l; a.nprim = np; a.col = cols[s];
+            a.poff = run + woff + inc - np;
+            stg[s] = a;
+            for (int p = 0; p < np; p++) {
+                pdat[a.poff + p] = env[sh.ptr_exp + p];
+                pdat[max_prim + a.poff + p] = env[sh.ptr_coef + p];
+            }
+        }
+        run += tot;
+        __syncthreads();
+    }
+    for (int ch = 0; ch < AO_CH; ch++) {
+        const int row0 = (grp * AO_CH + ch) * AO_PTS;
+        if ((int64_t)sb * sbp + row0 >= ngrid) break;
+        const int64_t g = (int64_t)sb * sbp + row0 + lane;
+        double gx = 0, gy = 0, gz = 0;
+        if (g < ngrid) {
+            gx = coords[3 * g]; gy = coords[3 * g + 1]; gz = coords[3 * g + 2];
+        }
+        int s_lo = 0;
+        for (int c0 = 0; c0 < d.nsp; c0 += AO_WIN) {
+            while (s_lo < d.nshell && stg[s_lo].col + 2 * stg[s_lo].l + 1 <= c0) s_lo++;
+            int s_hi = s_lo;
+            while (s_hi < d.nshell && stg[s_hi].col < c0 + AO_WIN) s_hi++;
+            if (s_hi == s_lo) continue;   // nothing but padding in this window (buffer is pre-zeroed)
+            // kept shells fill the columns contiguously: only the last window has a tail of padding columns
+            const int cend = min(AO_WIN, stg[s_hi - 1].col + 2 * stg[s_hi - 1].l + 1 - c0);
+            if (cend < AO_WIN) {
+                const int nz = AO_WIN - cend;
+                for (int e = threadIdx.x; e < NCOMP * AO_PTS * nz; e += AO_THREADS)
+                    tile[(e / nz) * AO_TS + cend + e % nz] = 0.0;
+            }
+            for (int s = s_lo + warp; s < s_hi; s += AO_THREADS / 32) {
+                const AOStage a = stg[s];
+                ShellRec sh;
+                sh.l = a.l; sh.nprim = a.nprim;
+                sh.ptr_exp = a.poff; sh.ptr_coef = max_prim + a.poff;
+                const double x = gx - a.x, y = gy - a.y, z = gz - a.z;
+                const int col0 = a.col - c0;
+                if (LMAX <= 2) {
+                    switch (a.l) {
+                        case 0: ao_shell_to_tile<0, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                        case 1: ao_shell_to_tile<1, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                        default: ao_shell_to_tile<2, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                    }
+                } else {
+                    switch (a.l) {
+                        case 0: ao_shell_to_tile<0, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                        case 1: ao_shell_to_tile<1, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                        case 2: ao_shell_to_tile<2, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                        case 3: ao_shell_to_tile<3, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                        default: ao_shell_to_tile<4, DERIV, true>(sh, pdat, x, y, z, col0, lane, tile); break;
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int comp = 0; comp < NCOMP; comp++)
+#pragma unroll
+                for (int pp = 0; pp < 4; pp++) {
+                    const int p = warp * 4 + pp;
+                    if ((int64_t)sb * sbp + row0 + p >= ngrid) continue;
+                    const double2 v = *reinterpret_cast<const double2 *>(tile + (comp * AO_PTS + p) * AO_TS + 2 * lane);
+                    double *row = ao + d.ao_off + ((int64_t)comp * sbp + row0 + p) * d.nsp + c0;
+                    *reinterpret_cast<double2 *>(row + 2 * lane) = v;
+                }
+            __syncthreads();
+        }
+    }
+}
+
 extern "C" int b200qc_eval_gto_sb(const b200qc_basis *basis, int deriv, const double *coords, int64_t ngrid, int sbp,
                                   int nsb, const void *sbdesc, const int *shell_ids, const int *shell_col, double *ao,
                                   void *stream) {
@@ -154,14 +284,49 @@ extern "C" int b200qc_eval_gto_sb(const b200qc_basis *basis, int deriv, const do
     cudaStream_t st = as_stream(stream);
     int lmax = 0;
     for (const ShellRec &sh : basis->h_shells) lmax = std::max(lmax, sh.l);
+    // staged form: shared-memory room for the longest kept-shell list and its primitives (one-off host look at the lists)
+    int max_shell = 0, max_prim = 0;
+    {
+        std::vector<SBDesc> hd(nsb);
+        QC_CHECK(cudaMemcpyAsync(hd.data(), sbdesc, sizeof(SBDesc) * nsb, cudaMemcpyDeviceToHost, st));
+        QC_CHECK(cudaStreamSynchronize(st));
+        int64_t nids = 0;
+        for (const SBDesc &d : hd) nids = std::max<int64_t>(nids, (int64_t)d.shell_off + d.nshell);
+        std::vector<int> hids(nids);
+        if (nids) QC_CHECK(cudaMemcpyAsync(hids.data(), shell_ids, sizeof(int) * nids, cudaMemcpyDeviceToHost, st));
+        QC_CHECK(cudaStreamSynchronize(st));
+        for (const SBDesc &d : hd) {
+            int np = 0;
+            for (int s = 0; s < d.nshell; s++) {
+                const int id = hids[d.shell_off + s];
+                QC_REQUIRE(id >= 0 && id < basis->nbas, "kept-shell list holds a shell outside the basis");
+                np += basis->h_shells[id].nprim;
+            }
+            max_shell = std::max(max_shell, d.nshell);
+            max_prim = std::max(max_prim, np);
+        }
+        max_prim += max_prim & 1;
+    }
+    const size_t smem2 = sizeof(double) * AO_NCOMP(deriv) * AO_PTS * AO_TS + sizeof(AOStage) * max_shell +
+                         sizeof(double) * 2 * max_prim;
+    const bool staged = smem2 <= 200 * 1024 && sbp % (AO_PTS * AO_CH) == 0 && !getenv("B200QC_K1_UNSTAGED");
+    const unsigned nblk2 = (unsigned)nsb * (unsigned)(sbp / (AO_PTS * AO_CH));
     prof_begin(PROF_AO_EVAL, st);
 #define AO_SB_LAUNCH(DERIV, LMAX)                                                                                        \
     do {                                                                                                                 \
-        QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<DERIV, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                      (int)smem));                                                                       \
-        ao_eval_sb_kernel<DERIV, LMAX><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env,                    \
-                                                                      (const SBDesc *)sbdesc, shell_ids, shell_col,      \
-                                                                      coords, ngrid, sbp, ao);                           \
+        if (staged) {                                                                                                    \
+            QC_CHECK(cudaFuncSetAttribute(ao_eval_sb2_kernel<DERIV, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          (int)smem2));                                                                  \
+            ao_eval_sb2_kernel<DERIV, LMAX><<<nblk2, AO_THREADS, smem2, st>>>(                                           \
+                basis->d_shells, basis->d_env, (const SBDesc *)sbdesc, shell_ids, shell_col, coords, ngrid, sbp, ao,     \
+                max_shell, max_prim);                                                                                    \
+        } else {                                                                                                         \
+            QC_CHECK(cudaFuncSetAttribute(ao_eval_sb_kernel<DERIV, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          (int)smem));                                                                   \
+            ao_eval_sb_kernel<DERIV, LMAX><<<nblk, AO_THREADS, smem, st>>>(basis->d_shells, basis->d_env,                \
+                                                                          (const SBDesc *)sbdesc, shell_ids, shell_col,  \
+                                                                          coords, ngrid, sbp, ao);                       \
+        }                                                                                                                \
     } while (0)
     if (lmax <= 2) {
         if (deriv == 2) AO_SB_LAUNCH(2, 2); else if (deriv == 1) AO_SB_LAUNCH(1, 2); else AO_SB_LAUNCH(0, 2);
