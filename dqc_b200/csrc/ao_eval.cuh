@@ -25,9 +25,16 @@ template <int L> __host__ __device__ constexpr bool ao_c2s_nz(int m, int c) {
                   : true;
 }
 
-#define AO_TS 66   // row stride (doubles) of the point-major tile: 16-byte aligned rows for 128-bit reads along the AO axis
+// Point-major tile [comp][point][64 columns], no padding, XOR-swizzled so that BOTH phases are conflict-free: the
+// evaluation writes one column for 32 points (lane = point; unswizzled, the 512-byte rows would put every lane on the
+// same bank), the write-out reads 16-byte column pairs along a row.  Pair c (columns 2c, 2c + 1) of row p sits at pair
+// c ^ (p & 7), its two halves swapped when bit 3 of p is set: 16 consecutive points -> 16 different 8-byte slots.
+#define AO_TS 64
+__device__ __forceinline__ int ao_pm_index(int comp, int p, int col) {
+    return (comp * AO_PTS + p) * AO_TS + ((((col >> 1) ^ (p & 7)) << 1) | ((col & 1) ^ ((p >> 3) & 1)));
+}
 
-// PM = false: tile[comp][col][33] (column-major, conflict-free both ways); PM = true: tile[comp][point][AO_TS]
+// PM = false: tile[comp][col][33] (column-major, conflict-free both ways); PM = true: the swizzled point-major tile
 template <int L, int DERIV, bool PM = false>
 __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const double *__restrict__ env,
                                                  double x, double y, double z, int col0, int lane,
@@ -93,7 +100,7 @@ __device__ __forceinline__ void ao_shell_to_tile(const ShellRec &sh, const doubl
 #pragma unroll
             for (int c = 0; c < NC; c++)
                 if (ao_c2s_nz<L>(m, c)) s += M[m * NC + c] * cv[comp][c];
-            tile[PM ? (comp * AO_PTS + lane) * AO_TS + col : (comp * AO_WIN + col) * 33 + lane] = s;
+            tile[PM ? ao_pm_index(comp, lane, col) : (comp * AO_WIN + col) * 33 + lane] = s;
         }
     }
 }

@@ -38,6 +38,7 @@ struct b200qc_jkplan {
     double *d_q = nullptr;
     JKPair *d_jkpairs = nullptr;         // the same pairs as d_pairs with their geometry (register engine)
     JKPrim *d_prims = nullptr;           // primitive-pair data, pp_off of a pair points in here
+    double *d_scratch_j = nullptr;       // (nao, nao): J sink of K-only runs of the register engine
     std::vector<JKClassPair> cps;
     int64_t nquartets = 0, nquartets_reg = 0;
     double flops_int = 0.0;              // integral evaluation (roots, 2-D tables, sum over roots), one pass per quartet
@@ -255,6 +256,7 @@ extern "C" int b200qc_jkplan_free(b200qc_jkplan *p) {
     cudaFree(p->d_q);
     cudaFree(p->d_jkpairs);
     cudaFree(p->d_prims);
+    cudaFree(p->d_scratch_j);
     for (auto &cp : p->cps) {
         cudaFree(cp.d_work_off);
         cudaFree(cp.d_nket_of_bra);
@@ -391,6 +393,8 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
     QC_CHECK(cudaMemcpy(plan->d_pairs, pairs.data(), sizeof(int2) * pairs.size(), cudaMemcpyHostToDevice));
     QC_CHECK(cudaMalloc(&plan->d_jkpairs, sizeof(JKPair) * jkpairs.size()));
     QC_CHECK(cudaMemcpy(plan->d_jkpairs, jkpairs.data(), sizeof(JKPair) * jkpairs.size(), cudaMemcpyHostToDevice));
+    QC_CHECK(cudaMalloc(&plan->d_scratch_j, sizeof(double) * (size_t)plan->nao * plan->nao));
+    QC_CHECK(cudaMemset(plan->d_scratch_j, 0, sizeof(double) * (size_t)plan->nao * plan->nao));
     QC_CHECK(cudaMalloc(&plan->d_prims, sizeof(JKPrim) * prims.size()));
     QC_CHECK(cudaMemcpy(plan->d_prims, prims.data(), sizeof(JKPrim) * prims.size(), cudaMemcpyHostToDevice));
     // 3. class pairs (bra class >= ket class) with their work items
@@ -502,7 +506,7 @@ extern "C" int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, in
             h_fill_c2s(2, R.c2s_d);
             for (int s = 0; s < nset; s++) {   // one density per launch: the block stays in registers
                 R.dm = dm + s * nn;
-                R.vj = vj ? vj + s * nn : nullptr;
+                R.vj = vj ? vj + s * nn : plan->d_scratch_j;   // K only: the J+K kernels with a scratch J
                 R.vk = vk ? vk + s * nn : nullptr;
                 int rc = jkr_launch(R, st);
                 if (rc) return rc;

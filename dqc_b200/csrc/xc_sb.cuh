@@ -149,7 +149,8 @@ ao_eval_sb_kernel(const ShellRec *__restrict__ shells, const double *__restrict_
 // prefix sum) -- so that the evaluation loop has no dependent global loads (the first form walked ids -> shell record
 // -> env for every (warp, shell): 12 % warp occupancy at 228 registers, long-scoreboard bound, 0.14 of the HBM write
 // rate).  Per 64-column window the eight warps split the shells (lane = point), park the values in a POINT-major tile
-// and the CTA streams it out with 128-bit loads / stores: one 512-byte row segment per warp instruction.
+// (XOR-swizzled: conflict-free for the column writes and the row reads) and the CTA streams it out with 128-bit loads /
+// stores: one 512-byte row segment per warp instruction.
 #define AO_CH 4
 struct AOStage {
     double x, y, z;
@@ -230,8 +231,10 @@ ao_eval_sb2_kernel(const ShellRec *__restrict__ shells, const double *__restrict
             const int cend = min(AO_WIN, stg[s_hi - 1].col + 2 * stg[s_hi - 1].l + 1 - c0);
             if (cend < AO_WIN) {
                 const int nz = AO_WIN - cend;
-                for (int e = threadIdx.x; e < NCOMP * AO_PTS * nz; e += AO_THREADS)
-                    tile[(e / nz) * AO_TS + cend + e % nz] = 0.0;
+                for (int e = threadIdx.x; e < NCOMP * AO_PTS * nz; e += AO_THREADS) {
+                    const int r = e / nz;
+                    tile[ao_pm_index(r / AO_PTS, r % AO_PTS, cend + e % nz)] = 0.0;
+                }
             }
             for (int s = s_lo + warp; s < s_hi; s += AO_THREADS / 32) {
                 const AOStage a = stg[s];
@@ -263,7 +266,13 @@ ao_eval_sb2_kernel(const ShellRec *__restrict__ shells, const double *__restrict
                 for (int pp = 0; pp < 4; pp++) {
                     const int p = warp * 4 + pp;
                     if ((int64_t)sb * sbp + row0 + p >= ngrid) continue;
-                    const double2 v = *reinterpret_cast<const double2 *>(tile + (comp * AO_PTS + p) * AO_TS + 2 * lane);
+                    double2 v = *reinterpret_cast<const double2 *>(tile + (comp * AO_PTS + p) * AO_TS +
+                                                                   2 * (lane ^ (p & 7)));
+                    if (p & 8) {
+                        const double t = v.x;
+                        v.x = v.y;
+                        v.y = t;
+                    }
                     double *row = ao + d.ao_off + ((int64_t)comp * sbp + row0 + p) * d.nsp + c0;
                     *reinterpret_cast<double2 *>(row + 2 * lane) = v;
                 }

@@ -386,7 +386,7 @@ class HamiltonCGTO(BaseHamilton):
             if exx != 0.0 and not config.DF_EXCHANGE:
                 raise RuntimeError("Exact exchange cannot be computed with density fitting")
             dmao_j = self._orthozer.unconvert_dm(dmtot).contiguous()
-            if self._ctx.world > 1 and dmao_j.is_cuda and config.DFJ_SIDE_STREAM:
+            if (self._ctx.world > 1 or config.DFJ_SIDE_STREAM_SINGLE) and dmao_j.is_cuda and config.DFJ_SIDE_STREAM:
                 # sharded build: DF-J has a collective in its middle (the fitting coefficients need every rank's slice
                 # of temp).  It runs on a second stream so that the exchange and its latency hide behind the XC kernels
                 # of the main stream instead of stalling the step (round 1, 8 GPUs: 0.56 ms of the 3.97 ms step was in
