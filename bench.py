@@ -585,7 +585,7 @@ def main():
                     "algorithmic_flops_per_build": fl,
                     "contracted_shell_quartets_per_s": h._jkplan.nquartets / (jk_ms * 1e-3),
                     "quartets": h._jkplan.nquartets, "quartets_register_engine": h._jkplan.nquartets_reg,
-                    "launches_per_build": prof["jk_kernel"][0] / args.steps}
+                    "note": "jk_kernel time = the whole region of class-pair kernels (4 side streams), bracketed once"}
     # secondary rooflines (HBM-bound kernels) for context
     extra = {}
     if "dfj_pass1_kernel" in kern and h.df is not None and h.df._j3c_packed is not None:

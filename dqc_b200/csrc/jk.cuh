@@ -19,6 +19,10 @@
 
 #define JK_CHUNK 16
 #define JK_MAXSET 2
+#define JK_NSTREAM 4
+static cudaStream_t g_jk_streams[64][JK_NSTREAM];
+static cudaEvent_t g_jk_join[64][JK_NSTREAM], g_jk_fork[64];
+static bool g_jk_streams_ready[64] = {};
 
 struct JKClassPair {
     IntClass K;
@@ -483,7 +487,37 @@ extern "C" int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, in
     if (vj) QC_CHECK(cudaMemsetAsync(vj, 0, sizeof(double) * nn * nset, st));
     if (vk) QC_CHECK(cudaMemsetAsync(vk, 0, sizeof(double) * nn * nset, st));
     const RysTable &rt = g_rys_host[plan->basis->device];
+    // The class-pair kernels are independent (they only add into J / K): they go round-robin onto JK_NSTREAM side
+    // streams forked from the caller's stream, so the tail of one persistent grid overlaps the start of the next
+    // (hundreds of launches per build; sharded builds shrink every one of them).  The profiler then brackets the whole
+    // region once on the caller's stream instead of every launch.
+    const int dev = plan->basis->device;
+    const bool multi = !getenv("B200QC_JK_ONE_STREAM");
+    cudaStream_t js[JK_NSTREAM];
+    if (multi) {
+        if (!g_jk_streams_ready[dev]) {
+            for (int i = 0; i < JK_NSTREAM; i++) {
+                QC_CHECK(cudaStreamCreateWithFlags(&g_jk_streams[dev][i], cudaStreamNonBlocking));
+                QC_CHECK(cudaEventCreateWithFlags(&g_jk_join[dev][i], cudaEventDisableTiming));
+            }
+            QC_CHECK(cudaEventCreateWithFlags(&g_jk_fork[dev], cudaEventDisableTiming));
+            g_jk_streams_ready[dev] = true;
+        }
+        prof_begin(PROF_JK, st);
+        QC_CHECK(cudaEventRecord(g_jk_fork[dev], st));
+        for (int i = 0; i < JK_NSTREAM; i++) {
+            js[i] = g_jk_streams[dev][i];
+            QC_CHECK(cudaStreamWaitEvent(js[i], g_jk_fork[dev], 0));
+        }
+    } else {
+        for (int i = 0; i < JK_NSTREAM; i++) js[i] = st;
+    }
+    const bool prof_was_on = g_prof_on;
+    if (multi) g_prof_on = false;
+    int rc_all = 0;
+    size_t icp = 0;
     for (const JKClassPair &cp : plan->cps) {
+        cudaStream_t st = js[icp++ % JK_NSTREAM];   // shadows the caller's stream inside the loop
         if (cp.reg) {
             JKRArgs R = {};
             for (int s = 0; s < 4; s++) R.l[s] = cp.K.l[s];
@@ -508,9 +542,10 @@ extern "C" int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, in
                 R.dm = dm + s * nn;
                 R.vj = vj ? vj + s * nn : plan->d_scratch_j;   // K only: the J+K kernels with a scratch J
                 R.vk = vk ? vk + s * nn : nullptr;
-                int rc = jkr_launch(R, st);
-                if (rc) return rc;
+                rc_all = jkr_launch(R, st);
+                if (rc_all) break;
             }
+            if (rc_all) break;
             continue;
         }
         IntArgs A = {};
@@ -530,8 +565,17 @@ extern "C" int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, in
         else if (nc <= 256) rc = jk_launch_t<16, 16>(cp, A, rank, world, st);
         else if (nc <= 512) rc = jk_launch_t<32, 16>(cp, A, rank, world, st);
         else rc = jk_launch_t<32, 41>(cp, A, rank, world, st);
-        if (rc) return rc;
+        if (rc) { rc_all = rc; break; }
     }
+    if (multi) {
+        g_prof_on = prof_was_on;
+        for (int i = 0; i < JK_NSTREAM; i++) {
+            QC_CHECK(cudaEventRecord(g_jk_join[dev][i], js[i]));
+            QC_CHECK(cudaStreamWaitEvent(st, g_jk_join[dev][i], 0));
+        }
+        prof_end(st);
+    }
+    if (rc_all) return rc_all;
     const int64_t tot = nn * nset;
     if (vj) { jk_symm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(vj, plan->nao, nset); QC_LAUNCHED(1); }
     if (vk) { jk_symm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(vk, plan->nao, nset); QC_LAUNCHED(1); }

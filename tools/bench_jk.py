@@ -55,6 +55,10 @@ for spec in (sys.argv[1:] or ["taxol_like:3-21g"]):
             res["%s_%s_quartets_per_s" % (label, mode)] = float("%.3g" % (plan.nquartets / (ms * 1e-3)))
             if mode == "jk":
                 out[label] = o
+        if label == "register":
+            for world in (2, 4, 8):     # one rank's share of a sharded build, timed on this GPU
+                ms, _ = timed(lambda: plan.run(dm, True, True, rank=0, world=world), 3)
+                res["register_jk_ms_rank0_of_%d" % world] = round(ms, 2)
         del plan
     if with_shared:
       res["max_abs_diff_J"] = float((out["register"][0] - out["shared"][0]).abs().max())
