@@ -364,6 +364,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from dqc_b200 import Mol, get_xc, _lib
     from dqc_b200.utils.dist import get_context
+    from dqc_b200.utils.config import config as qc_config
     ctx = get_context()
     assert ctx.world == world
 
@@ -386,6 +387,9 @@ def main():
     occ = torch.full((orb_host.shape[1],), 2.0, dtype=torch.float64, device=dev)
     dm = h.ao_orb2dm(orb_host.to(dev), occ)
     ngrid = int(mol.get_grid().get_rgrid().shape[0]) if xc is not None else 0
+    if h.df is not None:
+        impl_config["dfj_pair_rows_read"] = "%.3f of the (ij|P) pair rows (the others are below %g in every column: skipped)" % (
+            getattr(h.df, "row_kept_fraction", 1.0), qc_config.DFJ_ROW_SKIP)
     if aux is None:
         impl_config["jk_engine"] = type(h._jkplan).__name__ + (
             " (both dense (ij|kl) layouts resident in HBM, J/K = GEMVs)" if type(h._jkplan).__name__ == "StoredERI"
@@ -589,7 +593,7 @@ def main():
     # secondary rooflines (HBM-bound kernels) for context
     extra = {}
     if "dfj_pass1_kernel" in kern and h.df is not None and h.df._j3c_packed is not None:
-        nb = h.df._j3c_packed.numel() * 8.0
+        nb = h.df._j3c_packed.numel() * 8.0 * getattr(h.df, "row_kept_fraction", 1.0)   # rows the passes really read
         for k in ("dfj_pass1_kernel", "dfj_pass2_kernel"):
             extra[k] = {"GB/s": nb / (kern[k]["ms_per_launch"] * 1e-3) / 1e9, "frac_of_hbm": nb / (
                 kern[k]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}

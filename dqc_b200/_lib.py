@@ -129,6 +129,13 @@ _SIGS = {
     "b200qc_dfj_worksize": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int64]),
     "b200qc_dfj": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_dfj_rowmask": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "b200qc_dfj_pass1_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int64, ctypes.c_void_p]),
+    "b200qc_dfj_pass2_masked": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_dfj_pass1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_dfj_pass2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
@@ -601,23 +608,35 @@ def dfj(j3c_packed, nao, naux, inv_j2c, dm):
     return vj
 
 
-def dfj_pass1(j3c_packed, nao, naux, dm):
+def dfj_rowmask(j3c_packed, nao, naux, thresh):
+    """uint8 (npair,): 1 for pair rows whose every |(ij|P)| is below thresh (skipped by the masked passes)."""
+    lib = load()
+    mask = torch.empty(j3c_packed.shape[0], dtype=torch.uint8, device=j3c_packed.device)
+    _check(lib.b200qc_dfj_rowmask(_ptr(j3c_packed), nao, naux, j3c_packed.shape[1], float(thresh), _ptr(mask),
+                                  _stream()), "dfj_rowmask")
+    return mask
+
+
+def dfj_pass1(j3c_packed, nao, naux, dm, rows=None):
+    """temp_P = sum_ij D_ij (ij|P); rows: optional int32 list of the pair rows to read (ascending)."""
     lib = load()
     ld = j3c_packed.shape[1]
     work = _workspace(int(lib.b200qc_dfj_worksize(nao, ld)), dm.device)
     temp = torch.empty(naux, dtype=torch.float64, device=dm.device)
-    _check(lib.b200qc_dfj_pass1(_ptr(j3c_packed), nao, naux, ld, _ptr(dm.contiguous()), _ptr(temp), _ptr(work),
-                                _stream()), "dfj_pass1")
+    assert rows is None or rows.dtype == torch.int32
+    _check(lib.b200qc_dfj_pass1_rows(_ptr(j3c_packed), nao, naux, ld, _ptr(dm.contiguous()), _ptr(temp), _ptr(work),
+                                     _ptr(rows), 0 if rows is None else rows.numel(), _stream()), "dfj_pass1")
     return temp
 
 
-def dfj_pass2(j3c_packed, nao, naux, coef):
+def dfj_pass2(j3c_packed, nao, naux, coef, mask=None):
     lib = load()
     ld = j3c_packed.shape[1]
     cpad = torch.zeros(ld, dtype=torch.float64, device=coef.device)
     cpad[:naux] = coef
     vj = torch.empty((nao, nao), dtype=torch.float64, device=coef.device)
-    _check(lib.b200qc_dfj_pass2(_ptr(j3c_packed), nao, naux, ld, _ptr(cpad), _ptr(vj), _stream()), "dfj_pass2")
+    _check(lib.b200qc_dfj_pass2_masked(_ptr(j3c_packed), nao, naux, ld, _ptr(cpad), _ptr(vj), _ptr(mask), _stream()),
+           "dfj_pass2")
     return vj
 
 

@@ -2,9 +2,10 @@
 //   temp_P = sum_ij D_ij (ij|P);  c = temp . inv_j2c;  J_ij = sum_P c_P (ij|P).
 // (ij|P) is held once, packed over i >= j: B[pair][P], pair = i(i+1)/2 + j, row stride `ld`.
 // Both contractions are GEMVs over B (0.25 flop/byte) => HBM-bound: 2 * npair * naux * 8 bytes per
-// call.  Pass 1 streams row blocks of B through CTAs that keep 8 columns per thread in registers
-// and writes one partial row per CTA (fixed-order reduction afterwards: deterministic, no atomics);
-// pass 2 is one warp per pair row with the fitted coefficients served from L1.
+// call.  Pass 1 streams the rows of B through CTAs that keep 8 columns per
+// thread in registers (one contiguous slab of rows per CTA) and writes one partial row per CTA (fixed-order reduction afterwards: deterministic, no
+// atomics); pass 2 is one warp per pair row with the fitted coefficients served from L1.  Pair rows that are
+// negligible in every column (b200qc_dfj_rowmask) are read by neither pass.
 #pragma once
 #include "common.cuh"
 
@@ -29,11 +30,15 @@ __global__ void dfj_gather_dm_kernel(const double *__restrict__ dm, int nao, int
     dvec[r] = i == j ? dm[(int64_t)i * nao + i] : dm[(int64_t)i * nao + j] + dm[(int64_t)j * nao + i];
 }
 
+// LIST: the CTA walks entries [i0, i1) of a list of pair rows (the rows b200qc_dfj_rowmask keeps, ascending) instead of
+// the rows themselves; the next index is fetched one step ahead so that the row loads never wait for it.  (A mask test
+// with a data-dependent `continue` in front of the loads cost more than the skipped rows saved.)
+template <bool LIST>
 __global__ void __launch_bounds__(DFJ_TPB)
-dfj_pass1_kernel(const double *__restrict__ B, int64_t npair, int64_t ld, const double *__restrict__ dvec,
-                 int64_t rows_per_cta, double *__restrict__ partial) {
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r1 = min(r0 + rows_per_cta, npair);
+dfj_pass1_kernel(const double *__restrict__ B, int64_t nrows, int64_t ld, const double *__restrict__ dvec,
+                 int64_t rows_per_cta, double *__restrict__ partial, const int *__restrict__ rows) {
+    const int64_t i0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t i1 = min(i0 + rows_per_cta, nrows);
     const int64_t c0 = (int64_t)blockIdx.y * DFJ_COLS + 2 * threadIdx.x;
     double2 acc[DFJ_SLOTS];
     bool ok[DFJ_SLOTS];
@@ -42,16 +47,33 @@ dfj_pass1_kernel(const double *__restrict__ B, int64_t npair, int64_t ld, const 
         acc[s] = make_double2(0.0, 0.0);
         ok[s] = c0 + (int64_t)s * 2 * DFJ_TPB < ld;
     }
-    const double *row = B + r0 * ld + c0;
-    for (int64_t r = r0; r < r1; r++, row += ld) {
-        const double d = __ldg(dvec + r);
+    if (LIST) {
+        int64_t r = i0 < i1 ? rows[i0] : 0;
+        for (int64_t i = i0; i < i1; i++) {
+            const int64_t rn = i + 1 < i1 ? rows[i + 1] : 0;
+            const double *row = B + r * ld + c0;
+            const double d = __ldg(dvec + r);
 #pragma unroll
-        for (int s = 0; s < DFJ_SLOTS; s++)
-            if (ok[s]) {
-                const double2 v = __ldcs(reinterpret_cast<const double2 *>(row + s * 2 * DFJ_TPB));
-                acc[s].x += d * v.x;
-                acc[s].y += d * v.y;
-            }
+            for (int s = 0; s < DFJ_SLOTS; s++)
+                if (ok[s]) {
+                    const double2 v = __ldcs(reinterpret_cast<const double2 *>(row + s * 2 * DFJ_TPB));
+                    acc[s].x += d * v.x;
+                    acc[s].y += d * v.y;
+                }
+            r = rn;
+        }
+    } else {
+        const double *row = B + i0 * ld + c0;
+        for (int64_t r = i0; r < i1; r++, row += ld) {
+            const double d = __ldg(dvec + r);
+#pragma unroll
+            for (int s = 0; s < DFJ_SLOTS; s++)
+                if (ok[s]) {
+                    const double2 v = __ldcs(reinterpret_cast<const double2 *>(row + s * 2 * DFJ_TPB));
+                    acc[s].x += d * v.x;
+                    acc[s].y += d * v.y;
+                }
+        }
     }
     double *out = partial + (int64_t)blockIdx.x * ld + c0;
 #pragma unroll
@@ -63,31 +85,34 @@ dfj_pass1_kernel(const double *__restrict__ B, int64_t npair, int64_t ld, const 
 // thread would leave a single load in flight per thread (0.6 of the HBM rate on the 8-GPU C60 build); here a thread
 // keeps FOUR consecutive rows in flight for its column pair.
 __global__ void __launch_bounds__(DFJ_TPB)
-dfj_pass1_narrow_kernel(const double *__restrict__ B, int64_t npair, int64_t ld, const double *__restrict__ dvec,
-                        int64_t rows_per_cta, double *__restrict__ partial) {
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r1 = min(r0 + rows_per_cta, npair);
+dfj_pass1_narrow_kernel(const double *__restrict__ B, int64_t nrows, int64_t ld, const double *__restrict__ dvec,
+                        int64_t rows_per_cta, double *__restrict__ partial, const int *__restrict__ rows) {
+    const int64_t i0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t i1 = min(i0 + rows_per_cta, nrows);
     const int64_t c0 = 2 * threadIdx.x;
     if (c0 >= ld) return;
     double2 acc[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) acc[u] = make_double2(0.0, 0.0);
-    const double *row = B + r0 * ld + c0;
-    int64_t r = r0;
-    for (; r + 4 <= r1; r += 4, row += 4 * ld) {
+    int64_t i = i0;
+    for (; i + 4 <= i1; i += 4) {
+        int64_t r[4];
         double2 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = __ldcs(reinterpret_cast<const double2 *>(row + u * ld));
+        for (int u = 0; u < 4; u++) r[u] = rows ? (int64_t)rows[i + u] : i + u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldcs(reinterpret_cast<const double2 *>(B + r[u] * ld + c0));
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const double d = __ldg(dvec + r + u);
+            const double d = __ldg(dvec + r[u]);
             acc[u].x += d * v[u].x;
             acc[u].y += d * v[u].y;
         }
     }
-    for (; r < r1; r++, row += ld) {
+    for (; i < i1; i++) {
+        const int64_t r = rows ? (int64_t)rows[i] : i;
         const double d = __ldg(dvec + r);
-        const double2 v = __ldcs(reinterpret_cast<const double2 *>(row));
+        const double2 v = __ldcs(reinterpret_cast<const double2 *>(B + r * ld + c0));
         acc[0].x += d * v.x;
         acc[0].y += d * v.y;
     }
@@ -124,7 +149,7 @@ __global__ void dfj_vecmat_kernel(const double *__restrict__ t, const double *__
 // J[i][j] = J[j][i] = sum_P B[pair][P] c[P]; one warp per row, two rows in flight
 __global__ void __launch_bounds__(256)
 dfj_pass2_kernel(const double *__restrict__ B, int64_t npair, int64_t naux, int64_t ld, const double *__restrict__ c,
-                 int nao, double *__restrict__ vj) {
+                 int nao, double *__restrict__ vj, const unsigned char *__restrict__ mask) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -132,7 +157,7 @@ dfj_pass2_kernel(const double *__restrict__ B, int64_t npair, int64_t naux, int6
     for (int64_t r = warp; r < npair; r += nwarp) {
         const double2 *row = reinterpret_cast<const double2 *>(B + r * ld);
         double s0 = 0.0, s1 = 0.0;
-        int64_t k = lane;
+        int64_t k = (mask && mask[r]) ? nhalf : lane;   // negligible pair row: J_ij = 0 without reading it
         for (; k + 32 < nhalf; k += 64) {
             const double2 v0 = __ldcs(row + k), v1 = __ldcs(row + k + 32);
             const double2 c0 = __ldg(reinterpret_cast<const double2 *>(c) + k);
@@ -155,6 +180,31 @@ dfj_pass2_kernel(const double *__restrict__ B, int64_t npair, int64_t naux, int6
             vj[(int64_t)j * nao + i] = s;
         }
     }
+}
+
+// mask[r] = 1 when every |(ij|P)| of pair row r (this rank's columns) is below thresh: both passes then skip the row.
+// On C60/def2-SVP 22 % of the rows are below 1e-14 (pairs of tight functions on distant atoms), 35 % on the 113-atom
+// system: the error they would add is of the order of the rounding of the sums they are left out of.
+__global__ void __launch_bounds__(256)
+dfj_rowmask_kernel(const double *__restrict__ B, int64_t npair, int64_t naux, int64_t ld, double thresh,
+                   unsigned char *__restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= npair) return;
+    double m = 0.0;
+    for (int64_t k = lane; k < naux; k += 32) m = fmax(m, fabs(B[r * ld + k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) mask[r] = m < thresh ? 1 : 0;
+}
+
+extern "C" int b200qc_dfj_rowmask(const double *j3c, int64_t nao, int64_t naux, int64_t ld, double thresh,
+                                  unsigned char *mask, void *stream) {
+    QC_REQUIRE(j3c && mask && ld >= naux, "bad arguments");
+    const int64_t npair = nao * (nao + 1) / 2;
+    dfj_rowmask_kernel<<<(unsigned)((npair + 7) / 8), 256, 0, as_stream(stream)>>>(j3c, npair, naux, ld, thresh, mask);
+    QC_LAUNCHED(1);
+    return 0;
 }
 
 __global__ void pack_tril_kernel(const double *__restrict__ full, int nao, int64_t naux, int64_t ld, int64_t npair,
@@ -185,23 +235,27 @@ extern "C" int64_t b200qc_dfj_worksize(int64_t nao, int64_t ld) {
 }
 
 // temp_P = sum_ij D_ij (ij|P) over this rank's columns (pass 1 only; multi-GPU DF splits the aux axis)
-extern "C" int b200qc_dfj_pass1(const double *j3c, int64_t nao, int64_t naux, int64_t ld, const double *dm,
-                                double *temp, double *work, void *stream) {
+// pass 1 over a list of pair rows (ascending row indices, e.g. the rows b200qc_dfj_rowmask keeps); rows = NULL: all rows
+extern "C" int b200qc_dfj_pass1_rows(const double *j3c, int64_t nao, int64_t naux, int64_t ld, const double *dm,
+                                     double *temp, double *work, const int *rows, int64_t nrows, void *stream) {
     QC_REQUIRE(ld % 2 == 0 && ld >= naux, "ld must be even and >= naux");
     QC_REQUIRE(((uintptr_t)j3c | (uintptr_t)work) % 16 == 0, "j3c and work must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     const int64_t npair = nao * (nao + 1) / 2;
+    if (!rows) nrows = npair;
+    QC_REQUIRE(nrows >= 0 && nrows <= npair, "bad row list");
     double *dvec = work, *partial = work + dfj_dvec_len(npair) + 2 * ld;
     prof_begin(PROF_DFJ_SMALL, st);
     dfj_gather_dm_kernel<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(dm, (int)nao, npair, dvec);
     prof_end(st);
     QC_LAUNCHED(1);
     const int nslab = dfj_nslab(npair, ld);
-    const int64_t rows = (npair + nslab - 1) / nslab;
+    const int64_t per = (nrows + nslab - 1) / nslab;
     dim3 grid((unsigned)nslab, (unsigned)((ld + DFJ_COLS - 1) / DFJ_COLS));
     prof_begin(PROF_DFJ_PASS1, st);
-    if (ld <= 2 * DFJ_TPB) dfj_pass1_narrow_kernel<<<grid, DFJ_TPB, 0, st>>>(j3c, npair, ld, dvec, rows, partial);
-    else dfj_pass1_kernel<<<grid, DFJ_TPB, 0, st>>>(j3c, npair, ld, dvec, rows, partial);
+    if (ld <= 2 * DFJ_TPB) dfj_pass1_narrow_kernel<<<grid, DFJ_TPB, 0, st>>>(j3c, nrows, ld, dvec, per, partial, rows);
+    else if (rows) dfj_pass1_kernel<true><<<grid, DFJ_TPB, 0, st>>>(j3c, nrows, ld, dvec, per, partial, rows);
+    else dfj_pass1_kernel<false><<<grid, DFJ_TPB, 0, st>>>(j3c, nrows, ld, dvec, per, partial, rows);
     prof_end(st);
     QC_LAUNCHED(1);
     prof_begin(PROF_DFJ_SMALL, st);
@@ -211,17 +265,27 @@ extern "C" int b200qc_dfj_pass1(const double *j3c, int64_t nao, int64_t naux, in
     return 0;
 }
 
+extern "C" int b200qc_dfj_pass1(const double *j3c, int64_t nao, int64_t naux, int64_t ld, const double *dm,
+                                double *temp, double *work, void *stream) {
+    return b200qc_dfj_pass1_rows(j3c, nao, naux, ld, dm, temp, work, nullptr, 0, stream);
+}
+
 // vj_ij = sum_P (ij|P) c_P over this rank's columns (c padded to ld with zeros by the caller)
-extern "C" int b200qc_dfj_pass2(const double *j3c, int64_t nao, int64_t naux, int64_t ld, const double *coef,
-                                double *vj, void *stream) {
+extern "C" int b200qc_dfj_pass2_masked(const double *j3c, int64_t nao, int64_t naux, int64_t ld, const double *coef,
+                                       double *vj, const unsigned char *mask, void *stream) {
     QC_REQUIRE(ld % 2 == 0 && ld >= naux, "ld must be even and >= naux");
     QC_REQUIRE(((uintptr_t)j3c | (uintptr_t)coef) % 16 == 0, "j3c and coef must be 16-byte aligned");
     const int64_t npair = nao * (nao + 1) / 2;
     prof_begin(PROF_DFJ_PASS2, as_stream(stream));
-    dfj_pass2_kernel<<<NUM_SMS * 8, 256, 0, as_stream(stream)>>>(j3c, npair, naux, ld, coef, (int)nao, vj);
+    dfj_pass2_kernel<<<NUM_SMS * 8, 256, 0, as_stream(stream)>>>(j3c, npair, naux, ld, coef, (int)nao, vj, mask);
     prof_end(as_stream(stream));
     QC_LAUNCHED(1);
     return 0;
+}
+
+extern "C" int b200qc_dfj_pass2(const double *j3c, int64_t nao, int64_t naux, int64_t ld, const double *coef,
+                                double *vj, void *stream) {
+    return b200qc_dfj_pass2_masked(j3c, nao, naux, ld, coef, vj, nullptr, stream);
 }
 
 extern "C" int b200qc_dfj(const double *j3c, int64_t nao, int64_t naux, int64_t ld, const double *inv_j2c,

@@ -18,6 +18,7 @@ from dqc_b200.hamilton.intor import molintor as intor
 from dqc_b200.utils.datastruct import DensityFitInfo
 from dqc_b200.utils.linop import LinearOperator
 from dqc_b200.utils.dist import ParallelContext, get_context
+from dqc_b200.utils.config import config
 from dqc_b200.utils.misc import logger
 
 __all__ = ["DFMol", "dfk_chunking"]
@@ -85,6 +86,12 @@ class DFMol(BaseDF):
             self._j3c_packed = intor.coul3c_packed(basisw, auxbw, aux_slice=(bounds[rank], bounds[rank + 1]))
         else:
             self._j3c_packed = None
+        # pair rows of (ij|P) that are negligible on this rank's columns are not read by the two DF-J passes
+        self._row_mask, self._row_list, self.row_kept_fraction = None, None, 1.0
+        if self._j3c_packed is not None and self._j3c_packed.is_cuda and config.DFJ_ROW_SKIP > 0.0:
+            self._row_mask = _lib.dfj_rowmask(self._j3c_packed, self._nao, self._naux_local, config.DFJ_ROW_SKIP)
+            self.row_kept_fraction = 1.0 - float(self._row_mask.double().mean())
+            self._row_list = torch.nonzero(self._row_mask == 0).flatten().to(torch.int32).contiguous()
         logger.log("Density fitting done")
         return self
 
@@ -93,14 +100,14 @@ class DFMol(BaseDF):
         """dmao (nao, nao) in the AO basis -> this rank's partial J (nao, nao); the caller sums over ranks."""
         nao, nl = self._nao, self._naux_local
         if nl > 0:
-            temp_l = _lib.dfj_pass1(self._j3c_packed, nao, nl, dmao)
+            temp_l = _lib.dfj_pass1(self._j3c_packed, nao, nl, dmao, self._row_list)
         else:
             temp_l = torch.zeros(0, dtype=dmao.dtype, device=dmao.device)
         temp = self._ctx.allgather_cat(temp_l, self._aux_sizes)
         coef = torch.matmul(temp, self._inv_j2c)                      # temp @ inv_j2c (dfmol.py:72)
         if nl == 0:
             return torch.zeros(nao, nao, dtype=dmao.dtype, device=dmao.device)
-        return _lib.dfj_pass2(self._j3c_packed, nao, nl, coef[self._aux_off:self._aux_off + nl])
+        return _lib.dfj_pass2(self._j3c_packed, nao, nl, coef[self._aux_off:self._aux_off + nl], self._row_mask)
 
     # ---- density-fitted exact exchange (extension: the reference raises, hcgto.py:229-230) ----
     def build_exchange(self, nslice: Optional[int] = None) -> "DFMol":

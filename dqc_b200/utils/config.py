@@ -52,6 +52,8 @@ class _Config:
     DFJ_SIDE_STREAM: bool = os.environ.get("B200QC_DFJ_SIDE_STREAM", "1") != "0"
     # the same on a single GPU (no exchange to hide there: the HBM-bound DF-J passes then overlap the tensor-bound Vxc GEMM)
     DFJ_SIDE_STREAM_SINGLE: bool = os.environ.get("B200QC_DFJ_SIDE_STREAM_SINGLE", "0") != "0"
+    # DF-J: pair rows of (ij|P) whose largest element is below this are skipped by both passes (0 reads every row)
+    DFJ_ROW_SKIP: float = float(os.environ.get("B200QC_DFJ_ROW_SKIP", "1e-14"))
     # weight of the linear term of the superblock cost model nsp^2 + c nsp used to deal superblocks to ranks
     SB_COST_LINEAR: float = float(os.environ.get("B200QC_SB_COST_LINEAR", "900"))
     # a shell is dropped from a superblock when its envelope stays below this on every point of it

@@ -278,6 +278,17 @@ int b200qc_jk_direct(const b200qc_basis *basis, int sh0, int sh1, const double *
  * aux-sharded multi-GPU layout (each rank holds a column slice of j3c; temp is all-gathered,
  * the partial vj all-reduced); coef must be zero beyond naux up to ld. */
 int64_t b200qc_dfj_worksize(int64_t nao, int64_t ld);
+/* pair rows whose every |(ij|P)| (this rank's columns) is below thresh: mask[npair] = 1.  The masked variants of the
+ * two passes do not read those rows (temp gets no contribution, J_ij = 0): -22 % of the HBM traffic at C60/def2-SVP,
+ * -35 % on the 113-atom system with thresh = 1e-14; mask = NULL reads everything. */
+int b200qc_dfj_rowmask(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, double thresh,
+                       unsigned char *mask, void *stream);
+/* pass 1 over a list of pair rows (ascending indices into the npair rows, device; NULL = every row): with the rows the
+ * mask keeps, the kernel is the plain streaming loop on fewer rows (the next index is fetched one step ahead) */
+int b200qc_dfj_pass1_rows(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, const double *dm,
+                          double *temp, double *work, const int *rows, int64_t nrows, void *stream);
+int b200qc_dfj_pass2_masked(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, const double *coef,
+                            double *vj, const unsigned char *mask, void *stream);
 int b200qc_dfj(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, const double *inv_j2c,
                const double *dm, double *vj, double *work, void *stream);
 int b200qc_dfj_pass1(const double *j3c_packed, int64_t nao, int64_t naux, int64_t ld, const double *dm,

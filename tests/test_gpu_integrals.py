@@ -275,3 +275,31 @@ def test_efield_enters_the_core_hamiltonian(cuda):
     dip = intor.int1e("r0", w)
     diff = h1.get_kinnucl().fullmatrix() - h0.get_kinnucl().fullmatrix()
     assert float((diff - torch.einsum("dab,d->ab", dip, e.to(dip.device))).abs().max()) < 1e-12
+
+
+def test_dfj_row_skipping(cuda):
+    """The row-skipping DF-J passes (b200qc_dfj_rowmask / _pass1_rows / _pass2_masked) give exactly what the plain passes
+    give on a copy of (ij|P) whose masked pair rows are zeroed, and the mask is the row-maximum test it says it is."""
+    from dqc_b200 import _lib
+    bw, aw = _df_wrappers()
+    b0, b1 = bw.shell_idxs
+    a0, a1 = aw.shell_idxs
+    db = aw.device_basis(cuda)
+    packed = _lib.int3c2e_packed(db, (b0, b1, b0, b1, a0, a1))
+    loc = aw.full_shell_to_aoloc
+    nao, naux = int(loc[b1] - loc[b0]), int(loc[a1] - loc[a0])
+    assert packed.shape[0] == nao * (nao + 1) // 2 and packed.shape[1] >= naux
+    rowmax = packed[:, :naux].abs().amax(1)
+    thresh = float(rowmax.median())
+    mask = _lib.dfj_rowmask(packed, nao, naux, thresh)
+    assert torch.equal(mask.bool(), rowmax < thresh) and 0 < int(mask.sum()) < mask.numel()
+    zeroed = packed.clone()
+    zeroed[mask.bool()] = 0.0
+    g = torch.Generator().manual_seed(5)
+    dm = torch.randn(nao, nao, dtype=torch.float64, generator=g).to(cuda)
+    coef = torch.randn(naux, dtype=torch.float64, generator=g).to(cuda)
+    rows = torch.nonzero(mask == 0).flatten().to(torch.int32)
+    t_ref, t_m = _lib.dfj_pass1(zeroed, nao, naux, dm), _lib.dfj_pass1(packed, nao, naux, dm, rows)
+    assert float((t_ref - t_m).abs().max()) <= 1e-13 * float(t_ref.abs().max())
+    j_ref, j_m = _lib.dfj_pass2(zeroed, nao, naux, coef), _lib.dfj_pass2(packed, nao, naux, coef, mask)
+    assert float((j_ref - j_m).abs().max()) <= 1e-13 * float(j_ref.abs().max())
