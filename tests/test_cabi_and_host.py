@@ -288,3 +288,26 @@ def test_equilibrium_solvers_on_a_contraction_map():
         warnings.simplefilter("always")
         equilibrium(lambda v: a @ v + b, torch.zeros(12, dtype=dtype), method="simple", maxiter=2, f_tol=1e-12, info=info)
     assert not info["converged"] and any(issubclass(r.category, ConvergenceWarning) for r in rec)
+
+
+def test_jk_unit_table_is_in_sync_with_its_generator(tmp_path):
+    """csrc/jk_reg_units.inc (class table, per-unit entry definitions, dispatcher of the register-resident J/K engine)
+    is generated by tools/gen_jk_units.py: the committed file must be what the generator writes, every class must
+    satisfy li >= lj, lk >= ll, (li, lj) >= (lk, ll), and the passes must divide the bra components."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_jk_units", os.path.join(root, "tools", "gen_jk_units.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    ncart = lambda l: (l + 1) * (l + 2) // 2
+    seen = set()
+    for li, lj, lk, ll, npass, parts, _ in gen.CLASSES:
+        assert li >= lj and lk >= ll and (li, lj) >= (lk, ll) and (li, lj, lk, ll) not in seen
+        seen.add((li, lj, lk, ll))
+        assert (ncart(li) * ncart(lj)) % npass == 0 and npass % parts == 0
+        assert (li + lj + lk + ll) // 2 + 1 <= 5
+    out = str(tmp_path / "jk_reg_units.inc")
+    gen.main(out)
+    committed = open(os.path.join(root, "dqc_b200", "csrc", "jk_reg_units.inc")).read()
+    assert open(out).read() == committed, "run python tools/gen_jk_units.py and commit csrc/jk_reg_units.inc"
