@@ -644,7 +644,7 @@ def dfj_pass2(j3c_packed, nao, naux, coef, mask=None):
 # block-sparse grid path (csrc/xc_sb.cuh)
 
 SB_DTYPE = np.dtype([("ao_off", np.int64), ("d_off", np.int64), ("nsp", np.int32), ("idx_off", np.int32),
-                     ("shell_off", np.int32), ("nshell", np.int32)])
+                     ("shell_off", np.int32), ("nshell", np.int32), ("dsb_idx_off", np.int32), ("pad", np.int32)])
 
 
 # ------------------------------------------------------------------------------------------
@@ -779,6 +779,17 @@ class GridBlocks(object):
         desc = np.zeros(self.nsb, dtype=SB_DTYPE)
         desc["ao_off"], desc["d_off"], desc["nsp"] = ao_off, d_off, nsp
         desc["idx_off"], desc["shell_off"], desc["nshell"] = idx_off, shell_off, nsh
+        # superblocks with the kept-AO list of their predecessor (consecutive radial shells of an atom: a quarter of
+        # them at C60) use its gathered, sliced D_sb: rep[sb] = first superblock of the run
+        same = np.zeros(self.nsb, dtype=bool)
+        if self.nsb > 1:
+            same[1:] = (kept[1:] == kept[:-1]).all(1)
+        rep = np.arange(self.nsb)
+        for sb in range(1, self.nsb):
+            if same[sb]:
+                rep[sb] = rep[sb - 1]
+        self.sb_rep = rep
+        desc["dsb_idx_off"] = idx_off[rep]
         self.nsp = nsp
         self.max_nsp = int(nsp.max()) if self.nsb else 64
         self.kept_fraction = float(nsig.sum()) / max(1, self.nao * self.nsb)
@@ -841,7 +852,9 @@ class GridBlocks(object):
             self.rho_bn = rbn = _cfg.RHO_I8_BN if (_cfg.RHO_I8_BN in (64, 128) or (S == 5 and _cfg.RHO_I8_BN == 96)) else 128
             rb_bytes = S * nsp * ((nsp + rbn - 1) // rbn * rbn)      # sliced density: whole row tiles (zero padding)
             self.d_ra_off = tt(excl(S * self.sbp * nsp), torch.int64)
-            self.d_rb_off = tt(excl(rb_bytes), torch.int64)
+            rb_off = excl(np.where(self.sb_rep == np.arange(self.nsb), rb_bytes, 0))   # planes of the distinct lists only
+            self.d_rb_off = tt(rb_off[self.sb_rep], torch.int64)
+            rb_bytes = np.where(self.sb_rep == np.arange(self.nsb), rb_bytes, 0)
             self.r_aplanes = torch.empty(int((S * self.sbp * nsp).sum()), dtype=torch.int8, device=dev)
             self.r_bplanes = torch.zeros(int(rb_bytes.sum()), dtype=torch.int8, device=dev)
             self.r_rscale = torch.empty(self.nsb * self.sbp, dtype=torch.float64, device=dev)

@@ -72,7 +72,7 @@ sb_gather_slice_dm_kernel(const SBDesc *__restrict__ sbd, const int *__restrict_
     const SBDesc d = sbd[sb];
     const int lane = threadIdx.x & 31;
     const int nu = blockIdx.x * 8 + (threadIdx.x >> 5);    // one warp per row of D_sb
-    if (nu >= d.nsp) return;
+    if (nu >= d.nsp || d.dsb_idx_off != d.idx_off) return;  // same AO list as an earlier superblock: its planes are used
     const int *ix = idx + d.idx_off;
     const int a = ix[nu];
     const double *row = dm + (int64_t)(a < nao ? a : 0) * nao;
@@ -321,7 +321,7 @@ rho_i8_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double *__
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
                 // column scales, then the row dots with the fp64 AO values of this row
                 const int n0 = tn * BN + c0;
-                const double *cs = cscale + d.idx_off + n0;
+                const double *cs = cscale + d.dsb_idx_off + n0;
                 if (variant == 1 || variant == 3) {
 #pragma unroll
                     for (int j = 0; j < NC; j++) part[0] += x[j];

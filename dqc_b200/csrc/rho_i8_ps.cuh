@@ -257,7 +257,7 @@ rho_i8_ps_kernel(const SBDesc *__restrict__ sbd, int nsb, int sbp, const double 
                 double cs[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++)
-                    cs[r] = live ? ldexp(cscale[d.idx_off + mt * I8_BM + lg * 32 + 4 * q + r], -12 - 7 * (S - 1)) : 0.0;
+                    cs[r] = live ? ldexp(cscale[d.dsb_idx_off + mt * I8_BM + lg * 32 + 4 * q + r], -12 - 7 * (S - 1)) : 0.0;
                 mbar_wait(&accum_full, nt & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 double x[32];                                        // x[(k * 4 + r) * 2 + c]

@@ -22,6 +22,9 @@ struct SBDesc {
     int idx_off;      // start of this SB's AO index list (nsp entries, padding = nao)
     int shell_off;    // start of this SB's kept-shell list
     int nshell;       // number of kept shells
+    int dsb_idx_off;  // idx_off of the superblock whose gathered, sliced D_sb this one uses (its own, or that of an earlier
+                      // superblock with the same kept-AO list: consecutive radial shells of an atom mostly share it)
+    int pad_;
 };
 
 template <int NCOMP>
