@@ -350,9 +350,13 @@ class HamiltonCGTO(BaseHamilton):
     def _finish_ao_operator(self, mat_ao: torch.Tensor) -> LinearOperator:
         return LinearOperator.m(_symm(self._orthozer.convert2(mat_ao)), is_hermitian=True)
 
-    def _vxc_ao_partial(self, dm):
-        """AO-basis Vxc matrix summed over this rank's grid slice: (*BD, nao_ao, nao_ao) or SpinParam."""
-        densinfo = SpinParam.apply_fcn(lambda dm_: self._dm2densinfo(dm_), dm)
+    def _vxc_ao_partial(self, dm, dmao=None):
+        """AO-basis Vxc matrix summed over this rank's grid slice: (*BD, nao_ao, nao_ao) or SpinParam.
+        dmao: the AO-basis density (densities) X sym(dm) X^T if already formed (same structure as dm)."""
+        if dmao is None:
+            densinfo = SpinParam.apply_fcn(lambda dm_: self._dm2densinfo(dm_), dm)
+        else:
+            densinfo = SpinParam.apply_fcn(lambda dm_, ao_: self._dm2densinfo(dm_, ao_), dm, dmao)
         potinfo = self.xc.get_vxc(densinfo)
         return SpinParam.apply_fcn(lambda p: self._potinfo2mat(p), potinfo)
 
@@ -382,10 +386,17 @@ class HamiltonCGTO(BaseHamilton):
         _warn_if_in_graph(dmtot, "get_fock_2e")
         parts: List[torch.Tensor] = []
         side = None
+        # AO-basis densities X sym(D) X^T, formed once: J (linear in D, (ij|P) symmetric in ij: sym(D) gives the same J)
+        # and the grid densities use the same matrices
+        if polarized:
+            dmao_s = SpinParam(u=self._orthozer.unconvert_dm(_symm(dm.u)), d=self._orthozer.unconvert_dm(_symm(dm.d)))
+            dmao_tot = dmao_s.u + dmao_s.d
+        else:
+            dmao_s = dmao_tot = self._orthozer.unconvert_dm(_symm(dmtot))
         if self._df is not None:
             if exx != 0.0 and not config.DF_EXCHANGE:
                 raise RuntimeError("Exact exchange cannot be computed with density fitting")
-            dmao_j = self._orthozer.unconvert_dm(dmtot).contiguous()
+            dmao_j = dmao_tot.contiguous()
             if (self._ctx.world > 1 or config.DFJ_SIDE_STREAM_SINGLE) and dmao_j.is_cuda and config.DFJ_SIDE_STREAM:
                 # sharded build: DF-J has a collective in its middle (the fitting coefficients need every rank's slice
                 # of temp).  It runs on a second stream so that the exchange and its latency hide behind the XC kernels
@@ -407,7 +418,7 @@ class HamiltonCGTO(BaseHamilton):
                 else:
                     parts.append(self._dfk_ao_partial(dmtot))
         else:
-            dmao = self._orthozer.unconvert_dm(_symm(dmtot)).unsqueeze(0)
+            dmao = dmao_tot.unsqueeze(0)
             if exx != 0.0 and not polarized:
                 # restricted hybrid: J and K'[D] = -1/2 K[D] from ONE pass over the shell quartets (hcgto.py:238-241)
                 vj, vk = self._jk_ao_partial(dmao.contiguous(), True, True)
@@ -417,12 +428,11 @@ class HamiltonCGTO(BaseHamilton):
                 parts.append(vj[0])
             if exx != 0.0 and polarized:
                 # K'[D] = -1/2 K[D] restricted; per spin -1/2 K[2 D_s] (hcgto.py:238-241)
-                ds = torch.stack([2 * dm.u, 2 * dm.d])
-                _, vk = self._jk_ao_partial(self._orthozer.unconvert_dm(_symm(ds)).contiguous(), False, True)
+                _, vk = self._jk_ao_partial(torch.stack([2 * dmao_s.u, 2 * dmao_s.d]).contiguous(), False, True)
                 parts.extend(list(vk))
         nk = len(parts) - 1
         if with_xc and self.xc is not None:
-            vx = self._vxc_ao_partial(dm)
+            vx = self._vxc_ao_partial(dm, dmao_s)
             parts.extend([vx.u, vx.d] if polarized else [vx])
         if side is not None:
             torch.cuda.current_stream(self.device).wait_stream(side)
@@ -490,13 +500,14 @@ class HamiltonCGTO(BaseHamilton):
         return self._ctx.allreduce_(e.reshape(-1).clone()).reshape(e.shape)
 
     # ---- density on (this rank's slice of) the grid ----
-    def _dm2densinfo(self, dm: torch.Tensor) -> ValGrad:
+    def _dm2densinfo(self, dm: torch.Tensor, dmao: Optional[torch.Tensor] = None) -> ValGrad:
         # dm: (*BD, nao, nao) -> value (*BD, nr), grad (*BD, 3, nr)   (hcgto.py:371-443)
+        # dmao: X sym(dm) X^T when the caller has it already (get_fock_2e forms it once for J and for the densities)
         if not self.is_ao_set:
             raise RuntimeError("Please call `setup_grid(grid, xc)` to call this function")
         _warn_if_in_graph(dm, "_dm2densinfo")
         bshape, dm2 = self._flat(dm)
-        dmdmt = self._orthozer.unconvert_dm(_symm(dm2))
+        dmdmt = self._orthozer.unconvert_dm(_symm(dm2)) if dmao is None else dmao.reshape(dm2.shape)
         ng, gga = self.rgrid.shape[0], self.xcfamily == 2
         if self.xcfamily == 4:
             # meta-GGA: also lapl rho = 2 (sum X lapl phi + gg) and tau = gg / 2 (hcgto.py:420-438)
