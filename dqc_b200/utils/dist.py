@@ -20,7 +20,8 @@ class ParallelContext(object):
 
     def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
         """In-place sum over ranks.  NCCL/gloo reduce in a fixed (rank-ordered ring/tree) order for a
-        fixed world size, so repeated builds are bitwise reproducible."""
+        fixed world size, so the collective itself adds no run-to-run noise; the partial matrices it sums are
+        reproducible to ~1e-13 relative, not bitwise (fp64 atomics in the Vxc scatter and the J/K digestion)."""
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
