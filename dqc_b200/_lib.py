@@ -44,6 +44,8 @@ _SIGS = {
     "b200qc_basis_free": (ctypes.c_int, [ctypes.c_void_p]),
     "b200qc_basis_set_cartesian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "b200qc_c2s_matrix": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
+    "b200qc_rys_refine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p]),
     "b200qc_rys_upload": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double,
                                          ctypes.c_void_p, ctypes.c_void_p]),
     "b200qc_eval_gto": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

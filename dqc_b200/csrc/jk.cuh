@@ -402,7 +402,7 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
     QC_CHECK(cudaMalloc(&plan->d_prims, sizeof(JKPrim) * prims.size()));
     QC_CHECK(cudaMemcpy(plan->d_prims, prims.data(), sizeof(JKPrim) * prims.size(), cudaMemcpyHostToDevice));
     // 3. class pairs (bra class >= ket class) with their work items
-    const RysTable &rt = g_rys_host[basis->device];
+    const RysTable &rt = g_rys_fine[basis->device];   // the register engine reads the refined root table
     const size_t ncls = cla.size();
     for (size_t cb = 0; cb < ncls; cb++)
         for (size_t ck = 0; ck <= cb; ck++) {
@@ -410,7 +410,7 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
             const int l[4] = {cla[cb], clb[cb], cla[ck], clb[ck]};
             const int pr[4] = {1, 1, 1, 1};
             cp.reg = cbucket[cb] < JKR_NBUCKET && cbucket[ck] < JKR_NBUCKET && jkr_supported(l) &&
-                     rt.nint == 64 && rt.deg == 13;
+                     rt.nint == 128 && rt.deg == 9;
             if (int_make_class(cp.K, INT_MODE_ERI, SINK_JK, l, pr, 0)) {
                 b200qc_jkplan_free(plan);
                 b200qc_set_error("J/K class outside the supported range");
@@ -530,9 +530,10 @@ extern "C" int b200qc_jkplan_run(const b200qc_jkplan *plan, const double *dm, in
             R.item0 = rank; R.item_stride = world;
             R.nao = plan->nao;
             const int nr = cp.K.nroots;
-            R.rys_coef = rt.coef[nr - 1];
-            R.rys_nint = rt.nint; R.rys_deg = rt.deg;
-            R.rys_h = rt.h; R.rys_xmax = rt.xmax;
+            const RysTable &rf = g_rys_fine[plan->basis->device];
+            R.rys_coef = rf.coef[nr - 1];
+            R.rys_nint = rf.nint; R.rys_deg = rf.deg;
+            R.rys_h = rf.h; R.rys_xmax = rt.xmax;
             for (int r = 0; r < nr; r++) {
                 R.herm_u[r] = rt.herm[nr - 1][0][r];
                 R.herm_w[r] = rt.herm[nr - 1][1][r];

@@ -30,8 +30,8 @@
 
 #define JKR_THREADS 128
 #define JKR_WARPS (JKR_THREADS / 32)
-#define JKR_NINT 64
-#define JKR_NCOEF 14
+#define JKR_NINT 128   // the refined root table (tables.cuh: b200qc_rys_refine): intervals of width 1/2,
+#define JKR_NCOEF 10   // Chebyshev degree 9
 #define JKR_WSM (JKR_MAXPP * 6 + 36 + 36 + 32)   // doubles of shared memory per warp: bra primitive pairs, D_ij and J_ij
                                                 // tiles (cartesian), D_ij as stored
 

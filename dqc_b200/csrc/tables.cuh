@@ -215,7 +215,49 @@ extern "C" int b200qc_basis_free(b200qc_basis *b) {
     return 0;
 }
 
+// Finer form of the root table for the register-resident J/K engine (jk_reg.cuh): every interval of the base table is
+// split into `nsub` and re-expanded in Chebyshev polynomials truncated to `ncoef` coefficients.  A degree-13 expansion
+// on intervals of width 1 and a degree-9 expansion on intervals of width 1/2 have the same truncation error (3e-16 ..
+// 6e-16 relative: the base table's own), but the engine's Clenshaw sums -- more than half of the work of an (ss|ss) ..
+// (pp|ps) primitive quartet -- are 10 steps instead of 14.  Pure host arithmetic: in (nint, nf, deg + 1), out
+// (nint * nsub, nf, ncoef).
+extern "C" int b200qc_rys_refine(const double *h_coef, int nint, int nf, int deg, int nsub, int ncoef, double *h_out) {
+    QC_REQUIRE(h_coef && h_out && nint > 0 && nf > 0 && deg >= 1 && deg < 32 && nsub >= 1 && ncoef >= 1 && ncoef <= deg + 1,
+               "bad arguments");
+    const int N = deg + 1;
+    const double PI = 3.14159265358979323846;
+    std::vector<double> node(N), val(N);
+    for (int k = 0; k < N; k++) node[k] = std::cos(PI * (k + 0.5) / N);
+    for (int it = 0; it < nint; it++)
+        for (int f = 0; f < nf; f++) {
+            const double *c = h_coef + ((size_t)it * nf + f) * N;
+            for (int sub = 0; sub < nsub; sub++) {
+                const double a = -1.0 + 2.0 * sub / nsub, b = a + 2.0 / nsub;
+                for (int k = 0; k < N; k++) {   // base polynomial at the Chebyshev nodes of the sub-interval (Clenshaw)
+                    const double t = a + (node[k] + 1.0) * (b - a) * 0.5;
+                    double b1 = 0.0, b2 = 0.0;
+                    for (int j = N - 1; j >= 1; j--) {
+                        const double b0 = c[j] + 2.0 * t * b1 - b2;
+                        b2 = b1;
+                        b1 = b0;
+                    }
+                    val[k] = c[0] + t * b1 - b2;
+                }
+                double *o = h_out + (((size_t)it * nsub + sub) * nf + f) * ncoef;
+                for (int m = 0; m < ncoef; m++) {   // discrete Chebyshev transform (exact for degree <= deg)
+                    double sacc = 0.0;
+                    for (int k = 0; k < N; k++) sacc += val[k] * std::cos(PI * m * (k + 0.5) / N);
+                    o[m] = sacc * (m == 0 ? 1.0 : 2.0) / N;
+                }
+            }
+        }
+    return 0;
+}
+#define QC_RYS_FINE_NSUB 2
+#define QC_RYS_FINE_NCOEF 10
+
 static std::vector<double *> g_rys_dev[QC_MAX_DEVICES];
+static RysTable g_rys_fine[QC_MAX_DEVICES];   // the refined table (device pointers; h, nint, deg of the fine form)
 static RysTable g_rys_host[QC_MAX_DEVICES];   // host copy of each device's table descriptor (jk.cuh hands it to jk_reg.cuh)   // per device, like the __constant__ RysTable that points at them
 
 extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
@@ -246,6 +288,21 @@ extern "C" int b200qc_rys_upload(int nmax, double h, int deg, double xmax,
     }
     QC_CHECK(cudaMemcpyToSymbol(c_rys, &t, sizeof(t)));
     g_rys_host[dev] = t;
+    // the refined form for jk_reg.cuh
+    RysTable tf = t;
+    tf.h = h / QC_RYS_FINE_NSUB;
+    tf.deg = QC_RYS_FINE_NCOEF - 1;
+    tf.nint = t.nint * QC_RYS_FINE_NSUB;
+    for (int n = 1; n <= nmax; n++) {
+        std::vector<double> fine((size_t)tf.nint * 2 * n * QC_RYS_FINE_NCOEF);
+        if (b200qc_rys_refine(h_coef[n - 1], t.nint, 2 * n, deg, QC_RYS_FINE_NSUB, QC_RYS_FINE_NCOEF, fine.data())) return 2;
+        double *d = nullptr;
+        QC_CHECK(cudaMalloc(&d, fine.size() * sizeof(double)));
+        QC_CHECK(cudaMemcpy(d, fine.data(), fine.size() * sizeof(double), cudaMemcpyHostToDevice));
+        g_rys_dev[dev].push_back(d);
+        tf.coef[n - 1] = d;
+    }
+    g_rys_fine[dev] = tf;
     g_rys_ready[dev] = true;
     return 0;
 }

@@ -63,6 +63,10 @@ int b200qc_c2s_matrix(int l, double *h_out);
  * (molintor.py:695-708).  h_coef[n-1] points to (nint, 2n, deg+1) doubles, h_herm[n-1] to (2, n). */
 int b200qc_rys_upload(int nmax, double h, int deg, double xmax, const double *const *h_coef,
                       const double *const *h_herm);
+/* host arithmetic only: the table of one root count split into nsub sub-intervals per interval and truncated to ncoef
+ * Chebyshev coefficients -- h_coef (nint, nf, deg + 1) -> h_out (nint * nsub, nf, ncoef).  b200qc_rys_upload keeps the
+ * (2, 10) form beside the base table for the register-resident J/K engine (10 Clenshaw steps instead of 14). */
+int b200qc_rys_refine(const double *h_coef, int nint, int nf, int deg, int nsub, int ncoef, double *h_out);
 
 /* ---- K1: AO values on the grid -- replaces GTOval_sph / GTOval_ip_sph ------------------ */
 /* gtoeval.py:196-260 (eval_gto / eval_gradgto / eval_laplgto with to_transpose=True).

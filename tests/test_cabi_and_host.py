@@ -311,3 +311,35 @@ def test_jk_unit_table_is_in_sync_with_its_generator(tmp_path):
     gen.main(out)
     committed = open(os.path.join(root, "dqc_b200", "csrc", "jk_reg_units.inc")).read()
     assert open(out).read() == committed, "run python tools/gen_jk_units.py and commit csrc/jk_reg_units.inc"
+
+
+def test_refined_rys_table_reproduces_the_base_table():
+    """b200qc_rys_refine (host arithmetic; the form the register-resident J/K engine reads: intervals of width 1/2,
+    Chebyshev degree 9) against the base table (width 1, degree 13) at random x: roots and weights agree to 2e-15."""
+    import ctypes
+    import os
+    import numpy as np
+    from numpy.polynomial import chebyshev as C
+    from dqc_b200 import _lib
+    lib = _lib.load(require_cuda=False)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.RandomState(3)
+    with np.load(os.path.join(root, "dqc_b200", "data", "rys_table.npz")) as z:
+        nmax, h, deg, xmax = z["meta"]
+        for n in (1, 2, 3, 5):
+            base = np.ascontiguousarray(z["coef_%d" % n], dtype=np.float64)      # (nint, 2n, deg + 1)
+            nint, nf = base.shape[0], base.shape[1]
+            fine = np.empty((nint * 2, nf, 10), dtype=np.float64)
+            rc = lib.b200qc_rys_refine(base.ctypes.data_as(ctypes.c_void_p), nint, nf, int(deg), 2, 10,
+                                       fine.ctypes.data_as(ctypes.c_void_p))
+            assert rc == 0
+            x = np.concatenate([rng.uniform(0.0, float(xmax), 4000), [0.0, 0.5, 1.0, float(xmax) - 1e-9]])
+            it = np.minimum((x / h).astype(int), nint - 1)
+            t = 2.0 * (x - it * h) / h - 1.0
+            itf = np.minimum((x / (h / 2)).astype(int), 2 * nint - 1)
+            tf = 2.0 * (x - itf * (h / 2)) / (h / 2) - 1.0
+            for f in range(nf):
+                vb = np.array([C.chebval(t[i], base[it[i], f]) for i in range(x.size)])
+                vf = np.array([C.chebval(tf[i], fine[itf[i], f]) for i in range(x.size)])
+                assert np.abs(vf - vb).max() <= 2e-15 * max(1.0, 0.0) + 2e-15 * np.abs(vb).max(), (n, f)
+                assert (np.abs(vf - vb) / np.abs(vb)).max() < 5e-14, (n, f)      # also relatively, for the small roots
