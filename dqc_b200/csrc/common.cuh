@@ -145,7 +145,7 @@ struct JKRArgs {
     double c2s_d[30];             // cart -> real-spherical matrix of d shells, [m][c] (tables.cuh)
 };
 #define JKR_CHUNK 128      // kets per work item (four per lane)
-#define JKR_MAXPP 36       // primitive pairs per shell pair the engine stages (6 x 6)
+#define JKR_MAXPP 81       // primitive pairs per shell pair the engine stages (9 x 9: the contracted s shells of cc-pVDZ)
 QC_HIDDEN int jkr_supported(const int l[4]);
 QC_HIDDEN int jkr_launch(const JKRArgs &A, cudaStream_t st);
 

@@ -67,7 +67,7 @@ static double jk_prim_flops(const int l[4]) {
 // Primitive pairs whose Gaussian-product factor exp(-a_i a_j |AB|^2 / (a_i + a_j)) is below e^-50 = 2e-22 are left out
 // of the register engine's pair data (the shared-memory engine skips primitive quartets beyond e^-80).
 #define JKR_EACUT 50.0
-static const int g_jkr_buckets[] = {1, 2, 3, 4, 6, 9, 16, JKR_MAXPP};
+static const int g_jkr_buckets[] = {1, 2, 3, 4, 6, 9, 16, 36, JKR_MAXPP};
 #define JKR_NBUCKET ((int)(sizeof(g_jkr_buckets) / sizeof(int)))
 // bucket of a primitive-pair count: lanes of a warp walk kets of one bucket, so their trip counts are close
 static int jkr_bucket(int npp) {

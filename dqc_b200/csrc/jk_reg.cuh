@@ -281,10 +281,13 @@ template <int N> __device__ __forceinline__ double pick(const double (&a)[N], in
 
 // One pass over one contracted quartet per lane (valid lanes): integrals of the pass's bra components, digestion.
 // Every lane of the warp calls it (the J_ij partial sums are reduced over the warp at the end).
-template <int LI, int LJ, int LK, int LL, class P, bool DOJ, bool DOK>
+// DEFER (single-pass classes with small bra tiles): the lane keeps its J_ij partial sums in registers (jacc) across its
+// kets and the warp sum happens once per work item instead of once per round of 32 kets.
+template <int LI, int LJ, int LK, int LL, class P, bool DOJ, bool DOK, bool DEFER>
 __device__ __forceinline__ void quartet_pass(bool valid, const JKPair &bp, const JKPair &kp, const double *wprim,
                                              const double *wdij, double *wjij, const double *__restrict__ rt,
-                                             const JKRArgs &A, double ih, int lane) {
+                                             const JKRArgs &A, double ih, int lane,
+                                             double (&jacc)[DEFER ? Shape<LI, LJ, LK, LL>::NIJ : 1]) {
     using S = Shape<LI, LJ, LK, LL>;
     constexpr int NI = S::NI, NJ = S::NJ, NK = S::NK, NL = S::NL, NR = S::NR, NKL = S::NKL;
     constexpr int E0 = P::E0, NE = P::NE;
@@ -447,7 +450,10 @@ __device__ __forceinline__ void quartet_pass(bool valid, const JKPair &bp, const
             }
         }
     }
-    if (DOJ) {
+    if (DOJ && DEFER) {
+#pragma unroll
+        for (int e = 0; e < NE; e++) jacc[E0 + e] += jc[e];
+    } else if (DOJ) {
         // bra-tile J_ij: summed over the warp, kept (cartesian) in the warp's shared memory until the work item ends
 #pragma unroll
         for (int e = 0; e < NE; e++) {
@@ -459,13 +465,15 @@ __device__ __forceinline__ void quartet_pass(bool valid, const JKPair &bp, const
     }
 }
 
-template <int LI, int LJ, int LK, int LL, int NPASS, int P0, bool DOJ, bool DOK, int... Ps>
+template <int LI, int LJ, int LK, int LL, int NPASS, int P0, bool DOJ, bool DOK, bool DEFER, int... Ps>
 __device__ __forceinline__ void quartet_passes(bool valid, const JKPair &bp, const JKPair &kp, const double *wprim,
                                                const double *wdij, double *wjij, const double *__restrict__ rt,
-                                               const JKRArgs &A, double ih, int lane, std::integer_sequence<int, Ps...>) {
+                                               const JKRArgs &A, double ih, int lane,
+                                               double (&jacc)[DEFER ? Shape<LI, LJ, LK, LL>::NIJ : 1],
+                                               std::integer_sequence<int, Ps...>) {
     using S = Shape<LI, LJ, LK, LL>;
-    (quartet_pass<LI, LJ, LK, LL, Pass<S, (P0 + Ps) * S::NIJ / NPASS, (P0 + Ps + 1) * S::NIJ / NPASS>, DOJ, DOK>(
-         valid, bp, kp, wprim, wdij, wjij, rt, A, ih, lane), ...);
+    (quartet_pass<LI, LJ, LK, LL, Pass<S, (P0 + Ps) * S::NIJ / NPASS, (P0 + Ps + 1) * S::NIJ / NPASS>, DOJ, DOK, DEFER>(
+         valid, bp, kp, wprim, wdij, wjij, rt, A, ih, lane, jacc), ...);
 }
 
 // c2s coefficient with run-time indices (staging code only): c2sd = the d matrix in shared memory
@@ -522,12 +530,25 @@ __global__ void __launch_bounds__(JKR_THREADS) jk_reg_kernel(const JKRArgs A) {
             wjij[e] = 0.0;
         }
         __syncwarp();
+        constexpr bool DEFER = DOJ && NPASS == 1 && S::NC <= 54;
+        double jacc[DEFER ? NIJ : 1];
+#pragma unroll
+        for (int e = 0; e < (DEFER ? NIJ : 1); e++) jacc[e] = 0.0;
         for (int kk0 = k0; kk0 < k1; kk0 += 32) {
             const int kk = kk0 + lane;
             const bool valid = kk < k1;
             const JKPair kp = A.ket[valid ? kk : k0];
-            quartet_passes<LI, LJ, LK, LL, NPASS, P0, DOJ, DOK>(valid, bp, kp, wprim, wdij, wjij, rt, A, ih, lane,
-                                                                std::make_integer_sequence<int, P1 - P0>());
+            quartet_passes<LI, LJ, LK, LL, NPASS, P0, DOJ, DOK, DEFER>(valid, bp, kp, wprim, wdij, wjij, rt, A, ih, lane,
+                                                                       jacc, std::make_integer_sequence<int, P1 - P0>());
+        }
+        if (DEFER) {
+#pragma unroll
+            for (int e = 0; e < (DEFER ? NIJ : 1); e++) {
+                double v = jacc[e];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) wjij[e] = v;
+            }
         }
         if (DOJ) {
             __syncwarp();
