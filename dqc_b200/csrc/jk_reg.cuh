@@ -570,10 +570,20 @@ static int launch_t(const JKRArgs &A, cudaStream_t st) {
     static_assert(S::NR <= JKR_MAXROOTS && S::NIJ <= 36, "class outside the staged sizes");
     const size_t smem = sizeof(double) * ((size_t)JKR_NCOEF * 2 * S::NR * JKR_NINT + 32 + (size_t)JKR_WARPS * JKR_WSM);
     auto kern = jk_reg_kernel<LI, LJ, LK, LL, NPASS, P0, P1, DOJ, DOK>;
-    QC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    QC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JKR_THREADS, smem));
-    QC_REQUIRE(occ >= 1, "J/K register kernel does not fit on an SM");
+    // attribute + occupancy once per kernel and device: a build is hundreds of launches, and on small systems the
+    // host side of a launch is what bounds it
+    static int occ_of_device[64] = {};
+    int dev = 0;
+    QC_CHECK(cudaGetDevice(&dev));
+    QC_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    if (occ_of_device[dev] == 0) {
+        QC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int o = 0;
+        QC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, JKR_THREADS, smem));
+        QC_REQUIRE(o >= 1, "J/K register kernel does not fit on an SM");
+        occ_of_device[dev] = o;
+    }
+    const int occ = occ_of_device[dev];
     const int64_t mine = (A.nitems - A.item0 + A.item_stride - 1) / A.item_stride;   // items item0, item0 + stride, ...
     if (mine <= 0) return 0;
     const int64_t nblk = std::min<int64_t>((mine + JKR_WARPS - 1) / JKR_WARPS, (int64_t)NUM_SMS * occ);
