@@ -9,14 +9,17 @@
 //   * the bra pair's primitive data (p, 1/2p, P, c_i c_j e^(-a_i a_j |AB|^2 / p) / p: precomputed once per geometry by
 //     the plan) and its density tile D_ij are staged in shared memory by the warp and read as broadcasts; the ket pair's
 //     primitive data come from the same plan array, one pair per lane;
-//   * Rys roots and weights by Clenshaw summation of the piecewise Chebyshev table (rys.cuh), which the CTA keeps in
-//     shared memory TRANSPOSED -- [coefficient][function][interval], so lanes in different intervals hit different
-//     banks (from global memory every lane would touch its own cache line: 2 n x 14 wavefronts per primitive quartet);
+//   * Rys roots and weights by Clenshaw summation of a piecewise Chebyshev table -- the refined form of the base table
+//     of rys.cuh (tables.cuh, b200qc_rys_refine: intervals of width 1/2, degree 9: 10 steps instead of 14 at the same
+//     truncation error) -- which the CTA keeps in shared memory TRANSPOSED, [coefficient][function][interval], so lanes
+//     in different intervals hit different banks (from global memory every lane would touch its own cache line: 2 n x
+//     10 wavefronts per primitive quartet);
 //   * 2-D recurrence tables (vertical + both horizontal transfers) and the sum over roots are compile-time unrolled
 //     per angular-momentum class -- every table entry and every cartesian component is a register;
-//   * digestion: the lane contracts its block with the six density tiles; the bra-tile J_ij stays in registers across
-//     the lane's kets, is summed over the warp by shuffles and leaves as ONE atomic per element per work item; the
-//     ket-side J_kl and the four K tiles go out with fp64 atomics (RED.E.ADD.F64.STRONG.GPU).
+//   * digestion: the lane contracts its block with the six density tiles; the bra-tile J_ij is summed over the warp by
+//     shuffles (once per work item for the single-pass classes, whose lanes keep it in registers across their kets; once
+//     per round of 32 kets otherwise), collected in the warp's shared memory and leaves as ONE atomic per element per
+//     work item; the ket-side J_kl and the four K tiles go out with fp64 atomics (REDG.E.ADD.F64.RN.STRONG.GPU).
 // s, p and d shells.  For l <= 1 the real-spherical transform is a constant per shell that the plan folds into the
 // primitive coefficients; d shells are digested in CARTESIAN components: the density tiles are expanded with the 5 x 6
 // c2s matrix when they are loaded and the J / K tiles contracted with it before they are added (J = C J_cart C^T with
