@@ -328,6 +328,11 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
     std::vector<PairTmp> all;
     static const double c2s_const[2] = {0.282094791773878143, 0.488602511902919921};   // s, p (tables.cuh)
     const bool reg_ok = !getenv("B200QC_JK_NOREG");
+    // small systems (a few thousand shell pairs) are bound by the number of launches, not by the spread of the primitive
+    // loops inside a warp: one bucket per (l_i, l_j) there -- 21 class pairs instead of ~400 for benzene / cc-pVDZ
+    // (B200QC_JK_ONE_BUCKET = 0 / 1 overrides the size test: the tests run both forms on the same molecule)
+    const char *ob = getenv("B200QC_JK_ONE_BUCKET");
+    const bool one_bucket = ob ? ob[0] == '1' : tri.h.size() < 4096;
     for (size_t e = 0; e < tri.h.size(); e++) {
         int2 p = tri.h[e];
         const double qq = q[(size_t)p.x * nb + p.y];
@@ -354,7 +359,8 @@ extern "C" int b200qc_jkplan_create(const b200qc_basis *basis, int sh0, int sh1,
                 r.c = sc * basis->h_env[si.ptr_coef + ip] * basis->h_env[sj.ptr_coef + jp] * std::exp(-ea) / pp;
                 t.prims.push_back(r);
             }
-        const int bucket = reg_ok ? jkr_bucket((int)t.prims.size()) : JKR_NBUCKET;
+        int bucket = reg_ok ? jkr_bucket((int)t.prims.size()) : JKR_NBUCKET;
+        if (one_bucket && bucket < JKR_NBUCKET) bucket = 0;
         t.key = (si.l * 8 + sj.l) * 16 + bucket;
         all.push_back(std::move(t));
     }

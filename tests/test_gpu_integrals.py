@@ -161,9 +161,15 @@ def test_jk_register_engine_matches_stored_eri_and_shared_engine(cuda, monkeypat
     nb, nao = len(w), w.nao()
     db = w.device_basis(cuda)
     dms = torch.stack([util.seeded_dm(nao, nao // 4, seed=1), util.seeded_dm(nao, nao // 5, seed=2)]).to(cuda)
+    monkeypatch.setenv("B200QC_JK_ONE_BUCKET", "0")       # classes split by primitive-pair count, as on large systems
     plan = _lib.JKPlan(db, 0, nb, 1e-14)
     assert plan.nquartets_reg == plan.nquartets > 0       # s and p shells only: nothing left on the other engine
     vj, vk = plan.run(dms)
+    monkeypatch.delenv("B200QC_JK_ONE_BUCKET")             # default for a system of this size: one bucket per (l_i, l_j)
+    plan1 = _lib.JKPlan(db, 0, nb, 1e-14)
+    assert plan1.nquartets == plan.nquartets
+    vj1, vk1 = plan1.run(dms)
+    assert float((vj1 - vj).abs().max()) < 1e-11 and float((vk1 - vk).abs().max()) < 1e-11
     js, ks = _lib.StoredERI(db, 0, nb).run(dms)
     assert float((vj - js).abs().max()) < 1e-10 and float((vk - ks).abs().max()) < 1e-10
     # J only / K only launches, and three "ranks" adding up
