@@ -139,3 +139,63 @@ def test_register_engine_arithmetic_matches_the_oracle(rys, quartet):
     got = quartet_block(rys, *[shell(atm, bas, env, s) for s in quartet])
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def test_unique_quartet_digestion_matches_dense_contraction():
+    """The digestion of jk_reg.cuh / jk.cuh in numpy: unique shell quartets (pairs i >= j, ket pair <= bra pair), factors
+    1/2 per coincidence, J_ij += 2f B.D_kl, J_kl += 2f B.D_ij, K_ik += f B.D_jl, K_jk += f B.D_il, K_il += f B.D_jk,
+    K_jl += f B.D_ik, then acc + acc^T -- on the oracle's (ij|kl) blocks of H2O / def2-SVP against the reference's dense
+    einsums (hcgto.py:209,234)."""
+    import torch
+    from oracle import cint
+    w, _ = util.make_wrapper(*util.H2O, "def2-svp")
+    atm, bas, env = w.atm_bas_env
+    eri = cint.int2e(atm, bas, env)
+    nao = eri.shape[0]
+    loc = cint.ao_loc_sph(bas)
+    dm = util.seeded_dm(nao, 5, seed=3).numpy()
+    nb = len(bas)
+    pairs = [(i, j) for i in range(nb) for j in range(i + 1)]
+    J, K = np.zeros((nao, nao)), np.zeros((nao, nao))
+    sl = lambda s: slice(int(loc[s]), int(loc[s + 1]))
+    for b, (i, j) in enumerate(pairs):
+        for (k, l) in pairs[:b + 1]:
+            f = 1.0
+            if i == j:
+                f *= 0.5
+            if k == l:
+                f *= 0.5
+            if (i, j) == (k, l):
+                f *= 0.5
+            B = eri[sl(i), sl(j), sl(k), sl(l)]
+            J[sl(i), sl(j)] += 2 * f * np.einsum("abcd,cd->ab", B, dm[sl(k), sl(l)])
+            J[sl(k), sl(l)] += 2 * f * np.einsum("abcd,ab->cd", B, dm[sl(i), sl(j)])
+            K[sl(i), sl(k)] += f * np.einsum("abcd,bd->ac", B, dm[sl(j), sl(l)])
+            K[sl(j), sl(k)] += f * np.einsum("abcd,ad->bc", B, dm[sl(i), sl(l)])
+            K[sl(i), sl(l)] += f * np.einsum("abcd,bc->ad", B, dm[sl(j), sl(k)])
+            K[sl(j), sl(l)] += f * np.einsum("abcd,ac->bd", B, dm[sl(i), sl(k)])
+    J, K = J + J.T, K + K.T
+    jref = np.einsum("ij,ijkl->kl", dm, eri)
+    kref = np.einsum("il,ijkl->jk", dm, eri)
+    assert np.abs(J - jref).max() < 1e-12 and np.abs(K - kref).max() < 1e-12
+
+
+def test_k1_tile_swizzle_is_a_conflict_free_bijection():
+    """ao_pm_index of csrc/ao_eval.cuh (point-major K1 tile, 64 columns per row, no padding): for every point p the map
+    column -> position is a bijection of the row; the 16 lanes of a half-warp writing one column for 16 consecutive points
+    hit 16 different 8-byte slots of the 128-byte bank window; lane l of the write-out reads pair l ^ (p & 7), which holds
+    columns 2 l, 2 l + 1 (swapped when bit 3 of p is set)."""
+    def idx(p, col):
+        return p * 64 + ((((col >> 1) ^ (p & 7)) << 1) | ((col & 1) ^ ((p >> 3) & 1)))
+    for p in range(32):
+        assert sorted(idx(p, c) - p * 64 for c in range(64)) == list(range(64))
+        for lane in range(32):
+            pair = lane ^ (p & 7)
+            got = [c for c in range(64) if (idx(p, c) - p * 64) >> 1 == pair]
+            assert sorted(got) == [2 * lane, 2 * lane + 1]
+            first = [c for c in got if (idx(p, c) & 1) == 0][0]
+            assert first == (2 * lane + 1 if p & 8 else 2 * lane)
+    for col in range(64):
+        for p0 in (0, 16):
+            slots = {idx(p, col) % 16 for p in range(p0, p0 + 16)}
+            assert len(slots) == 16
