@@ -4,14 +4,19 @@
 //   K_jk = sum_il D_il (ij|kl)            dqc/hamilton/hcgto.py:224-241
 // (the reference materialises nao^4 doubles: 12.7 TB for Taxol/def2-SVP).
 //
-// A plan (built once per geometry) holds, per (li lj) class, the shell pairs i >= j sorted by
-// their Schwarz bound Q_ij = sqrt(max |(ij|ij)|), and per class pair a prefix table of work items
-// (bra pair, chunk of <= JK_CHUNK ket pairs with Q_bra Q_ket >= thresh and ket <= bra in the
-// canonical order).  Unique quartets only (8-fold symmetry); D must be symmetric (the caller
-// symmetrises, which leaves the reference's symmetrised J and K unchanged).
-// A lane group digests its chunk keeping the J_ij partial sums of the bra tile in shared memory
-// (one atomic per element per chunk); the ket-side J and the four K tiles go out with fp64
-// atomics (sums of O(1e4) terms: reproducible to ~1e-14, far inside the 1e-6 parity bar).
+// A plan (built once per geometry) holds the shell pairs that survive the Schwarz test, in canonical orientation
+// l(i) >= l(j), grouped into classes (l_i, l_j, bucket of the primitive-pair count) and sorted inside a class by their
+// Schwarz bound Q_ij = sqrt(max |(ij|ij)|); per pair a geometry record and its primitive-pair data (JKPair / JKPrim,
+// common.cuh); per class pair (bra class >= ket class) the work items: (bra pair, chunk of ket pairs with
+// Q_bra Q_ket >= thresh and ket <= bra in the canonical order).  Unique quartets only (8-fold symmetry); D must be
+// symmetric (the caller symmetrises, which leaves the reference's symmetrised J and K unchanged).
+// Two engines digest the items:
+//   * classes of s, p, d shells (<= 81 primitive pairs per shell pair): the register-resident quartet engine of
+//     jk_reg.cuh (third translation unit; chunks of 128 kets, one lane per contracted quartet);
+//   * everything else (f, g shells): jk_kernel below -- a lane group per quartet, 2-D tables in shared memory
+//     (int_compute_block of ints.cuh), chunks of 16 kets, J_ij partial sums of the bra tile in shared memory.
+// The class-pair launches of a build go round-robin onto four side streams (b200qc_jkplan_run).  fp64 atomics for the
+// ket-side J and the four K tiles (sums of O(1e4) terms: reproducible to ~1e-14, far inside the 1e-6 parity bar).
 #pragma once
 #include "ints.cuh"
 #include <algorithm>
